@@ -1,0 +1,168 @@
+// abi.cu -- the extern "C" surface declared in include/hgsfusion_b200.h.
+// Validation, parameter packing, workspace carving; no allocation, no host synchronisation.
+#include "contract_ops.cuh"
+#include "pillar_path.cuh"
+
+#include <climits>
+
+using namespace hgsf;
+
+static thread_local int g_last_launches = 0;
+
+extern "C" {
+
+int hgsf_abi_version(void) { return HGSF_ABI_VERSION; }
+
+const char *hgsf_status_string(int status) {
+    switch (status) {
+        case HGSF_OK: return "ok";
+        case HGSF_ERR_INVALID_ARG: return "invalid argument";
+        case HGSF_ERR_UNSUPPORTED: return "configuration outside the compiled kernel set";
+        case HGSF_ERR_WORKSPACE: return "workspace too small or misaligned";
+        case HGSF_ERR_DRIVER: return "cuTensorMapEncodeTiled unavailable or failed";
+        default: return status > 0 ? cudaGetErrorString((cudaError_t)status) : "unknown status";
+    }
+}
+
+int hgsf_last_launch_count(void) { return g_last_launches; }
+
+static bool geom_ok(const hgsf_geometry *g) {
+    if (!g) return false;
+    for (int j = 0; j < 3; ++j)
+        if (g->grid[j] <= 0 || !(g->voxel_size[j] > 0.f)) return false;
+    return true;
+}
+
+int64_t hgsf_pillar_capacity(const hgsf_geometry *g, int64_t n, int32_t B, int32_t max_voxels) {
+    if (!geom_ok(g) || n < 0 || B <= 0 || max_voxels < 0) return -1;
+    const int64_t cells = (int64_t)g->grid[0] * g->grid[1] * g->grid[2];
+    const int64_t per_frame = cells < max_voxels ? cells : max_voxels;
+    const int64_t cap = per_frame * B;
+    return n < cap ? n : cap;
+}
+
+int hgsf_workspace_size(const hgsf_geometry *g, int64_t n, int32_t B, int32_t F, size_t *bytes) {
+    if (!geom_ok(g) || !bytes || n < 0 || B <= 0 || F < 3) return HGSF_ERR_INVALID_ARG;
+    const int64_t cells = (int64_t)g->grid[0] * g->grid[1] * g->grid[2];
+    if (cells * B > INT_MAX || n > INT_MAX) return HGSF_ERR_UNSUPPORTED;
+    *bytes = workspace_layout(n, B, cells, F).total;
+    return HGSF_OK;
+}
+
+static int run_path(const hgsf_geometry *g, const hgsf_points *pt, const hgsf_pfn *pfn, int32_t P, int32_t max_voxels,
+                    void *ws, size_t ws_bytes, const hgsf_pillar_outputs *out, hgsf_stream_t stream) {
+    g_last_launches = 0;
+    if (!geom_ok(g) || !pt || !out || !ws) return HGSF_ERR_INVALID_ARG;
+    if (pt->n < 0 || pt->batch_size <= 0 || pt->num_features < 3 || pt->xyz_col < 0 ||
+        pt->xyz_col + pt->num_features > pt->stride || (pt->n > 0 && !pt->data))
+        return HGSF_ERR_INVALID_ARG;
+    if (!pt->frame_offsets && (pt->batch_col < 0 || pt->batch_col >= pt->stride)) return HGSF_ERR_INVALID_ARG;
+    if (P <= 0 || max_voxels < 0) return HGSF_ERR_INVALID_ARG;
+    if (!out->voxel_coords || !out->voxel_num_points || !out->num_pillars) return HGSF_ERR_INVALID_ARG;
+    if (P > 32) return HGSF_ERR_UNSUPPORTED;           // one warp orders a pillar: at most 32 slots
+    const int64_t cells = (int64_t)g->grid[0] * g->grid[1] * g->grid[2];
+    if (cells * pt->batch_size > INT_MAX || pt->n > INT_MAX) return HGSF_ERR_UNSUPPORTED;
+    if (out->pillar_capacity < hgsf_pillar_capacity(g, pt->n, pt->batch_size, max_voxels)) return HGSF_ERR_INVALID_ARG;
+    const WorkspaceLayout w = workspace_layout(pt->n, pt->batch_size, cells, pt->num_features);
+    if (ws_bytes < w.total || (reinterpret_cast<uintptr_t>(ws) & 255)) return HGSF_ERR_WORKSPACE;
+
+    PathParams p{};
+    p.pts = pt->data; p.n = (int)pt->n; p.stride = pt->stride; p.xyz_col = pt->xyz_col; p.F = pt->num_features;
+    p.batch_col = pt->batch_col; p.frame_offsets_in = pt->frame_offsets; p.B = pt->batch_size;
+    for (int j = 0; j < 3; ++j) { p.rmin[j] = g->pc_range[j]; p.vsize[j] = g->voxel_size[j]; p.voff[j] = g->centre_off[j]; }
+    p.nx = g->grid[0]; p.ny = g->grid[1]; p.nz = g->grid[2]; p.cells = (int)cells;
+    p.P = P; p.max_voxels = max_voxels;
+    uint8_t *base = static_cast<uint8_t *>(ws);
+    p.ticket = reinterpret_cast<uint32_t *>(base + w.off_ticket);
+    p.scan_desc = reinterpret_cast<uint64_t *>(base + w.off_desc);
+    p.frame_raw_base = reinterpret_cast<int32_t *>(base + w.off_raw_base);
+    p.table = reinterpret_cast<CellEntry *>(base + w.off_table);
+    p.frame_offsets = pt->frame_offsets ? const_cast<int32_t *>(pt->frame_offsets)
+                                        : reinterpret_cast<int32_t *>(base + w.off_frame_offsets);
+    p.key = reinterpret_cast<int32_t *>(base + w.off_key);
+    p.arrival = reinterpret_cast<uint32_t *>(base + w.off_arrival);
+    p.sorted_idx = reinterpret_cast<int32_t *>(base + w.off_sorted_idx);
+    p.sorted_rows = reinterpret_cast<float *>(base + w.off_sorted_rows);
+    p.RW = w.RW;
+    p.coords = out->voxel_coords; p.num = out->voxel_num_points; p.num_pillars = out->num_pillars;
+    p.voxels = out->voxels;
+    bool abs_xyz = true, dist = false;
+    if (pfn) {
+        if (!pfn->weight || pfn->out_channels <= 0) return HGSF_ERR_INVALID_ARG;
+        const bool bn = pfn->bn_weight || pfn->bn_bias || pfn->bn_mean || pfn->bn_var;
+        if (bn && !(pfn->bn_weight && pfn->bn_bias && pfn->bn_mean && pfn->bn_var)) return HGSF_ERR_INVALID_ARG;
+        if (!bn && !pfn->bias) return HGSF_ERR_INVALID_ARG;
+        abs_xyz = pfn->use_absolute_xyz != 0; dist = pfn->with_distance != 0;
+        const int cin = (abs_xyz ? p.F : p.F - 3) + 6 + (dist ? 1 : 0);
+        if (cin != pfn->in_channels) return HGSF_ERR_INVALID_ARG;
+        if (out->spatial_features && g->grid[2] != 1) return HGSF_ERR_INVALID_ARG;   // PointPillarScatter asserts nz == 1
+        p.W = pfn->weight; p.bias = pfn->bias; p.bn_w = pfn->bn_weight; p.bn_b = pfn->bn_bias;
+        p.bn_m = pfn->bn_mean; p.bn_v = pfn->bn_var; p.eps = pfn->bn_eps;
+        p.Cin = cin; p.C = pfn->out_channels;
+        p.feats = out->pillar_features; p.canvas = out->spatial_features;
+    }
+    return launch_pillar_path(p, pfn != nullptr, abs_xyz, dist, w.zero_bytes, base, static_cast<cudaStream_t>(stream),
+                              &g_last_launches);
+}
+
+int hgsf_pillarize(const hgsf_geometry *g, const hgsf_points *pt, int32_t P, int32_t max_voxels, void *ws,
+                   size_t ws_bytes, const hgsf_pillar_outputs *out, hgsf_stream_t stream) {
+    return run_path(g, pt, nullptr, P, max_voxels, ws, ws_bytes, out, stream);
+}
+
+int hgsf_points_to_bev(const hgsf_geometry *g, const hgsf_points *pt, const hgsf_pfn *pfn, int32_t P,
+                       int32_t max_voxels, void *ws, size_t ws_bytes, const hgsf_pillar_outputs *out,
+                       hgsf_stream_t stream) {
+    if (!pfn) return HGSF_ERR_INVALID_ARG;
+    return run_path(g, pt, pfn, P, max_voxels, ws, ws_bytes, out, stream);
+}
+
+int hgsf_pillar_vfe(const hgsf_geometry *g, const hgsf_pfn *pfn, const float *voxels, const void *coords,
+                    const void *num, int32_t coords_are_float, int32_t num_are_float, int64_t M, int32_t P,
+                    int32_t F, float *pillar_features, hgsf_stream_t stream) {
+    g_last_launches = 0;
+    if (!geom_ok(g) || !pfn || M < 0 || P <= 0 || F < 3) return HGSF_ERR_INVALID_ARG;
+    if (M > 0 && (!voxels || !coords || !num || !pillar_features)) return HGSF_ERR_INVALID_ARG;
+    if (!pfn->weight) return HGSF_ERR_INVALID_ARG;
+    const bool bn = pfn->bn_weight != nullptr;
+    if (bn && !(pfn->bn_bias && pfn->bn_mean && pfn->bn_var)) return HGSF_ERR_INVALID_ARG;
+    if (!bn && !pfn->bias) return HGSF_ERR_INVALID_ARG;
+    const bool abs_xyz = pfn->use_absolute_xyz != 0, dist = pfn->with_distance != 0;
+    if ((abs_xyz ? F : F - 3) + 6 + (dist ? 1 : 0) != pfn->in_channels) return HGSF_ERR_INVALID_ARG;
+    VfeParams q{};
+    q.voxels = voxels; q.coords = coords; q.num = num; q.coords_float = coords_are_float; q.num_float = num_are_float;
+    q.M = M; q.P = P; q.F = F; q.C = pfn->out_channels;
+    for (int j = 0; j < 3; ++j) { q.vsize[j] = g->voxel_size[j]; q.voff[j] = g->centre_off[j]; }
+    q.pfn = PfnArgs{pfn->weight, pfn->bias, pfn->bn_weight, pfn->bn_bias, pfn->bn_mean, pfn->bn_var, pfn->bn_eps};
+    q.out = pillar_features;
+    const int st = launch_vfe(q, abs_xyz, dist, static_cast<cudaStream_t>(stream));
+    if (st == HGSF_OK) g_last_launches = M > 0 ? 1 : 0;
+    return st;
+}
+
+int hgsf_scatter_workspace_size(const hgsf_geometry *g, int32_t B, size_t *bytes) {
+    if (!geom_ok(g) || !bytes || B <= 0) return HGSF_ERR_INVALID_ARG;
+    *bytes = align_up(sizeof(unsigned) * (size_t)B * g->grid[0] * g->grid[1] * g->grid[2], 256);
+    return HGSF_OK;
+}
+
+int hgsf_pointpillar_scatter(const hgsf_geometry *g, const float *feats, const void *coords, int32_t coords_are_float,
+                             int64_t M, int32_t C, int32_t B, void *ws, size_t ws_bytes, float *canvas,
+                             hgsf_stream_t stream) {
+    g_last_launches = 0;
+    if (!geom_ok(g) || M < 0 || B <= 0 || C <= 0 || !canvas || !ws) return HGSF_ERR_INVALID_ARG;
+    if (M > 0 && (!feats || !coords)) return HGSF_ERR_INVALID_ARG;
+    if (g->grid[2] != 1) return HGSF_ERR_INVALID_ARG;          // pointpillar_scatter.py:12 asserts nz == 1
+    if (C % 32 != 0 || C > 256) return HGSF_ERR_UNSUPPORTED;
+    size_t need = 0;
+    hgsf_scatter_workspace_size(g, B, &need);
+    if (ws_bytes < need || (reinterpret_cast<uintptr_t>(ws) & 255)) return HGSF_ERR_WORKSPACE;
+    if ((int64_t)g->grid[0] * g->grid[1] * B > INT_MAX || M >= UINT_MAX) return HGSF_ERR_UNSUPPORTED;
+    ScatterParams q{};
+    q.feats = feats; q.coords = coords; q.coords_float = coords_are_float; q.M = M; q.C = C; q.B = B;
+    q.ny = g->grid[1]; q.nx = g->grid[0]; q.plane = (long long)g->grid[0] * g->grid[1];
+    q.map = static_cast<unsigned *>(ws); q.canvas = canvas;
+    return launch_scatter(q, static_cast<cudaStream_t>(stream), &g_last_launches);
+}
+
+}  // extern "C"

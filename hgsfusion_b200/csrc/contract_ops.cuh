@@ -1,0 +1,38 @@
+// contract_ops.cuh -- parameter blocks of the stand-alone PillarVFE / PointPillarScatter ops.
+#pragma once
+#include "common.cuh"
+#include "pfn.cuh"
+
+namespace hgsf {
+
+struct VfeParams {
+    const float *voxels;      // [M, P, F]
+    const void *coords;       // [M, 4] (b, z, y, x) fp32 or int32
+    const void *num;          // [M] fp32 or int32
+    int coords_float, num_float;
+    long long M;
+    int P, F, C;
+    float vsize[3], voff[3];
+    PfnArgs pfn;
+    float *out;               // [M, C]
+};
+
+struct ScatterParams {
+    const float *feats;       // [M, C]
+    const void *coords;       // [M, 4]
+    int coords_float;
+    long long M;
+    int C, B, ny, nx;
+    long long plane;          // nz*ny*nx (nz == 1)
+    unsigned *map;            // [B*plane] workspace
+    float *canvas;            // [B, C, ny, nx]
+};
+
+int launch_vfe(const VfeParams &q, bool abs_xyz, bool dist, cudaStream_t stream);
+int launch_scatter(const ScatterParams &q, cudaStream_t stream, int *launches);
+
+// shared host helpers (pillar_path.cu)
+int make_canvas_map(CUtensorMap *map, float *canvas, int B, int C, int ny, int nx);
+int sm_count();
+
+}  // namespace hgsf

@@ -1,0 +1,157 @@
+/*
+ * hgsfusion_b200.h -- C ABI of the B200-native radar pillarization hot path.
+ *
+ * One shared library (hgsfusion_b200/libhgsfusion_b200.so), sm_100a only.  Every entry
+ * point takes raw DEVICE pointers, sizes, a geometry struct and a cudaStream_t; writes only
+ * caller-provided buffers; never allocates, never synchronises the host, never calls exit();
+ * and returns an int status: 0 ok, <0 invalid use (HGSF_ERR_*), >0 a cudaError_t.  Safe to
+ * call concurrently on different streams / devices with different workspaces.
+ *
+ * Each entry names the reference interface it replaces (file:line under the HGSFusion repo).
+ * The reference binds its native code through pybind11 (pcdet/ops/pillar_ops/src/pillar_api.cpp:10-22:
+ * `int f(at::Tensor...)`, outputs pre-allocated by the Python caller, legacy default stream,
+ * exit(-1) on kernel failure); this header is the torch-free equivalent of that surface.
+ */
+#ifndef HGSFUSION_B200_H
+#define HGSFUSION_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HGSF_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define HGSF_API __attribute__((visibility("default")))
+#else
+#define HGSF_API
+#endif
+
+/* status codes (<0); positive values are cudaError_t */
+#define HGSF_OK                 0
+#define HGSF_ERR_INVALID_ARG   (-1)   /* null pointer, negative size, inconsistent geometry          */
+#define HGSF_ERR_UNSUPPORTED   (-2)   /* a configuration outside the compiled kernel set             */
+#define HGSF_ERR_WORKSPACE     (-3)   /* workspace too small / misaligned                            */
+#define HGSF_ERR_DRIVER        (-4)   /* cuTensorMapEncodeTiled unavailable or failed                */
+
+typedef void *hgsf_stream_t;          /* a cudaStream_t */
+
+/* Voxel grid.  Mirrors what DataProcessor / PillarVFE derive from the YAML:
+ *   grid        = round((range[3:6]-range[0:3]) / VOXEL_SIZE)   data_processor.py:135-136
+ *   voxel_size  = VOXEL_SIZE as fp32 scalars                    pillar_vfe.py:76-78
+ *   centre_off  = voxel/2 + range_min, evaluated by the host exactly as pillar_vfe.py:79-81 does */
+typedef struct hgsf_geometry {
+    float   pc_range[6];      /* xmin ymin zmin xmax ymax zmax */
+    float   voxel_size[3];    /* vx vy vz */
+    int32_t grid[3];          /* nx ny nz */
+    float   centre_off[3];    /* x_offset y_offset z_offset */
+} hgsf_geometry;
+
+/* A batch of points as DatasetTemplate.collate_batch lays it out (pcdet/datasets/dataset.py:237-244):
+ * [n, stride] fp32 rows, frames contiguous and in batch order.  Either `frame_offsets` (device
+ * int32[batch_size+1]) or `batch_col` (column holding the batch index as a float, normally 0) says
+ * where frames start; when both are given frame_offsets wins. */
+typedef struct hgsf_points {
+    const float   *data;          /* device */
+    int64_t        n;             /* rows */
+    int32_t        stride;        /* floats per row */
+    int32_t        xyz_col;       /* column of x (y, z follow); the F features are columns xyz_col .. xyz_col+F-1 */
+    int32_t        num_features;  /* F */
+    int32_t        batch_col;     /* -1 if absent */
+    const int32_t *frame_offsets; /* device int32[batch_size+1] or NULL */
+    int32_t        batch_size;    /* B */
+} hgsf_points;
+
+/* The single (last) PFN layer of PillarVFE (pillar_vfe.py:8-49,63-74), eval mode.
+ * weight = pfn_layers.0.linear.weight [C, Cin]; USE_NORM=True: BatchNorm1d(eps=1e-3) running stats;
+ * USE_NORM=False: bias = pfn_layers.0.linear.bias and the four bn_* are NULL. */
+typedef struct hgsf_pfn {
+    const float *weight;      /* device [C, Cin] row-major */
+    const float *bias;        /* device [C] or NULL */
+    const float *bn_weight;   /* device [C] or NULL */
+    const float *bn_bias;
+    const float *bn_mean;
+    const float *bn_var;
+    float        bn_eps;
+    int32_t      in_channels;       /* Cin = (F or F-3) + 6 (+1) */
+    int32_t      out_channels;      /* C */
+    int32_t      use_absolute_xyz;  /* USE_ABSLOTE_XYZ */
+    int32_t      with_distance;     /* WITH_DISTANCE */
+} hgsf_pfn;
+
+/* Outputs of the pillar path.  All device pointers; any of voxels / pillar_features /
+ * spatial_features may be NULL to skip that output.  Rows are in the reference's first-seen
+ * order, frames concatenated (collate_batch).  `pillar_capacity` rows are available in each
+ * per-pillar buffer; the number actually written is num_pillars[0] (<= capacity, see
+ * hgsf_pillar_capacity). */
+typedef struct hgsf_pillar_outputs {
+    int32_t *voxel_coords;       /* [cap, 4] (b, z, y, x)                                   */
+    int32_t *voxel_num_points;   /* [cap]                                                   */
+    float   *voxels;             /* [cap, P, F] zero padded, or NULL                        */
+    float   *pillar_features;    /* [cap, C] or NULL                                        */
+    float   *spatial_features;   /* [B, C*nz, ny, nx] or NULL (requires nz == 1)            */
+    int32_t *num_pillars;        /* [1 + B]: total, then per frame                          */
+    int64_t  pillar_capacity;
+} hgsf_pillar_outputs;
+
+HGSF_API int hgsf_abi_version(void);
+HGSF_API const char *hgsf_status_string(int status);
+
+/* Upper bound on the number of pillars: min(n, B*min(max_voxels, nx*ny*nz)). */
+HGSF_API int64_t hgsf_pillar_capacity(const hgsf_geometry *geom, int64_t n_points, int32_t batch_size, int32_t max_voxels);
+
+/* Bytes of device workspace hgsf_pillarize / hgsf_points_to_bev need (256-byte aligned base). */
+HGSF_API int hgsf_workspace_size(const hgsf_geometry *geom, int64_t n_points, int32_t batch_size, int32_t num_features,
+                        size_t *bytes);
+
+/* points -> voxels, voxel_coords, voxel_num_points.
+ * Replaces DataProcessor.transform_points_to_voxels + VoxelGeneratorWrapper.generate
+ * (pcdet/datasets/processor/data_processor.py:16-61,133-183; spconv Point2VoxelCPU3d.point_to_voxel)
+ * and the voxel part of collate_batch (pcdet/datasets/dataset.py:232-244): first-seen pillar order,
+ * first `max_points_per_voxel` points per pillar in input order, at most `max_voxels` pillars per frame.
+ * Uses out->voxel_coords, voxel_num_points, voxels (optional), num_pillars. */
+HGSF_API int hgsf_pillarize(const hgsf_geometry *geom, const hgsf_points *points,
+                   int32_t max_points_per_voxel, int32_t max_voxels,
+                   void *workspace, size_t workspace_bytes,
+                   const hgsf_pillar_outputs *out, hgsf_stream_t stream);
+
+/* points -> (voxel_coords, voxel_num_points, [voxels]) + pillar_features + spatial_features in one pass.
+ * Replaces, fused: transform_points_to_voxels (above), PillarVFE.forward
+ * (pcdet/models/backbones_3d/vfe/pillar_vfe.py:94-123 incl. PFNLayer.forward :29-49) and
+ * PointPillarScatter.forward (pcdet/models/backbones_2d/map_to_bev/pointpillar_scatter.py:14-41). */
+HGSF_API int hgsf_points_to_bev(const hgsf_geometry *geom, const hgsf_points *points, const hgsf_pfn *pfn,
+                       int32_t max_points_per_voxel, int32_t max_voxels,
+                       void *workspace, size_t workspace_bytes,
+                       const hgsf_pillar_outputs *out, hgsf_stream_t stream);
+
+/* batch_dict contract mode: voxels [M,P,F], voxel_coords [M,4], voxel_num_points [M] -> pillar_features [M,C].
+ * Replaces PillarVFE.forward (pillar_vfe.py:94-123).  coords / num_points arrive as float32 in the
+ * reference (pcdet/models/__init__.py:36); `coords_are_float` / `num_are_float` select fp32 or int32. */
+HGSF_API int hgsf_pillar_vfe(const hgsf_geometry *geom, const hgsf_pfn *pfn,
+                    const float *voxels, const void *voxel_coords, const void *voxel_num_points,
+                    int32_t coords_are_float, int32_t num_are_float,
+                    int64_t num_pillars, int32_t max_points_per_voxel, int32_t num_features,
+                    float *pillar_features, hgsf_stream_t stream);
+
+/* Bytes of workspace hgsf_pointpillar_scatter needs. */
+HGSF_API int hgsf_scatter_workspace_size(const hgsf_geometry *geom, int32_t batch_size, size_t *bytes);
+
+/* pillar_features [M,C] + voxel_coords [M,4] -> spatial_features [B,C,ny,nx] (zero elsewhere).
+ * Replaces PointPillarScatter.forward (pointpillar_scatter.py:14-41).  Rows whose batch index is
+ * outside [0,B) are ignored; duplicate cells resolve to the last row (CPU index_put order). */
+HGSF_API int hgsf_pointpillar_scatter(const hgsf_geometry *geom, const float *pillar_features,
+                             const void *voxel_coords, int32_t coords_are_float,
+                             int64_t num_pillars, int32_t channels, int32_t batch_size,
+                             void *workspace, size_t workspace_bytes,
+                             float *spatial_features, hgsf_stream_t stream);
+
+/* Number of kernels / memsets the last call on this host thread enqueued (bench.py's gpu_launches). */
+HGSF_API int hgsf_last_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HGSFUSION_B200_H */

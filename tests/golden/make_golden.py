@@ -1,0 +1,143 @@
+"""Generates tests/golden/vfe_*.npz by running the REFERENCE's own PillarVFE and
+PointPillarScatter (imported by file path from /root/reference, CPU, eval mode) on seeded
+synthetic inputs.  Runs only in the build container (the reference mount does not exist on
+the GPU box); the .npz fixtures it writes are committed.
+
+    python tests/golden/make_golden.py            # rewrite fixtures
+    python tests/golden/make_golden.py --check    # also compare the C oracle against them
+
+The voxelizer that feeds these fixtures is oracle.voxelize (spconv is not available, see
+oracle/pillar_oracle.c header); the fixtures pin PillarVFE + PointPillarScatter, whose inputs
+(voxels, voxel_coords, voxel_num_points) are stored alongside the outputs.
+"""
+import importlib.util
+import os
+import sys
+import types
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+REF = "/root/reference"
+
+from hgsfusion_b200 import synthetic  # noqa: E402
+from oracle import oracle  # noqa: E402
+
+
+def load_reference():
+    """pillar_vfe.py has one relative import (.vfe_template); give it a synthetic parent package."""
+    pkg = types.ModuleType("refvfe")
+    pkg.__path__ = []
+    sys.modules["refvfe"] = pkg
+
+    def load(name, path):
+        spec = importlib.util.spec_from_file_location(name, path)
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules[name] = mod
+        spec.loader.exec_module(mod)
+        return mod
+
+    load("refvfe.vfe_template", f"{REF}/pcdet/models/backbones_3d/vfe/vfe_template.py")
+    vfe = load("refvfe.pillar_vfe", f"{REF}/pcdet/models/backbones_3d/vfe/pillar_vfe.py")
+    sc = load("refscatter", f"{REF}/pcdet/models/backbones_2d/map_to_bev/pointpillar_scatter.py")
+    return vfe.PillarVFE, sc.PointPillarScatter
+
+
+CASES = [
+    # name, config, B, n/frame, P, max_voxels, mode, use_abs, with_dist
+    ("vod_p32",        "vod",    2, 3000, 32, 40000, "clustered", True,  False),
+    ("vod_p10",        "vod",    2, 3000, 10, 40000, "clustered", True,  False),
+    ("vod_p5_trunc",   "vod",    1, 6000,  5,  1500, "clustered", True,  False),
+    ("vod_uniform",    "vod",    2, 2000, 32, 40000, "uniform",   True,  False),
+    ("tj4d_p32",       "tj4d",   2, 3000, 32, 40000, "clustered", True,  False),
+    ("stress_p10",     "stress", 1, 8000, 10, 40000, "clustered", True,  False),
+    ("vod_relxyz",     "vod",    1, 2000, 32, 40000, "clustered", False, False),
+    ("vod_dist",       "vod",    1, 2000, 32, 40000, "clustered", True,  True),
+]
+
+
+def run_case(PillarVFE, PointPillarScatter, name, config, B, n, P, max_voxels, mode, use_abs, with_dist):
+    cfg = synthetic.CONFIGS[config]
+    F = cfg["F"]
+    geom = oracle.Geometry(cfg["pc_range"], cfg["voxel_size"])
+    grid = geom.grid
+    pts, offs = synthetic.make_batch(config, B, n, mode, seed0=11, oob_fraction=0.02)
+    vox, coords, num = [], [], []
+    for b in range(B):
+        v, c, k = oracle.voxelize(pts[offs[b]:offs[b + 1]], geom, P, max_voxels, F=F, xcol=1)
+        vox.append(v)
+        coords.append(np.concatenate([np.full((c.shape[0], 1), b, np.int32), c], axis=1))
+        num.append(k)
+    vox, coords, num = np.concatenate(vox), np.concatenate(coords), np.concatenate(num)
+
+    Cin = (F if use_abs else F - 3) + 6 + (1 if with_dist else 0)
+    w = synthetic.make_pfn(Cin, 64, seed=len(name))
+    model_cfg = SimpleNamespace(USE_NORM=True, WITH_DISTANCE=with_dist, USE_ABSLOTE_XYZ=use_abs, NUM_FILTERS=[64])
+    # the reference is constructed exactly as detector3d_template.py:93-108 does:
+    # voxel_size is the YAML list of python floats, point_cloud_range an np.float32 array
+    vfe = PillarVFE(model_cfg=model_cfg, num_point_features=F, voxel_size=list(cfg["voxel_size"]),
+                    point_cloud_range=np.array(cfg["pc_range"], dtype=np.float32))
+    sd = vfe.state_dict()
+    sd["pfn_layers.0.linear.weight"] = torch.from_numpy(w.weight)
+    sd["pfn_layers.0.norm.weight"] = torch.from_numpy(w.gamma)
+    sd["pfn_layers.0.norm.bias"] = torch.from_numpy(w.beta)
+    sd["pfn_layers.0.norm.running_mean"] = torch.from_numpy(w.running_mean)
+    sd["pfn_layers.0.norm.running_var"] = torch.from_numpy(w.running_var)
+    vfe.load_state_dict(sd)
+    vfe.eval()
+    scatter = PointPillarScatter(model_cfg=SimpleNamespace(NUM_BEV_FEATURES=64), grid_size=grid)
+    # load_data_to_gpu converts everything to float32 (pcdet/models/__init__.py:36)
+    bd = dict(voxels=torch.from_numpy(vox).float(), voxel_coords=torch.from_numpy(coords).float(),
+              voxel_num_points=torch.from_numpy(num).float())
+    with torch.no_grad():
+        bd = vfe(bd)
+        bd = scatter(bd)
+    feats = bd["pillar_features"].numpy()
+    canvas = bd["spatial_features"].numpy()
+    # the canvas is pillar_features scattered (exact copy); store it sparsely: occupied cells only
+    nz = np.argwhere(np.abs(canvas).sum(axis=1) != 0)          # (b, y, x)
+    return dict(points=pts, frame_offsets=offs, voxels=vox, voxel_coords=coords, voxel_num_points=num,
+                weight=w.weight, gamma=w.gamma, beta=w.beta, running_mean=w.running_mean,
+                running_var=w.running_var, pillar_features=feats,
+                # torch's own 1/sqrt(var+eps) (MKL VML sqrt: not always correctly rounded)
+                ref_invstd=(1 / torch.sqrt(torch.from_numpy(w.running_var) + 1e-3)).numpy(),
+                canvas_shape=np.asarray(canvas.shape), canvas_nonzero_byx=nz.astype(np.int32),
+                canvas_checksum=np.asarray([canvas.astype(np.float64).sum(), np.abs(canvas).astype(np.float64).sum()]),
+                meta=np.asarray([config, str(P), str(max_voxels), str(int(use_abs)), str(int(with_dist)),
+                                 torch.__version__, np.__version__])), canvas
+
+
+def main():
+    check = "--check" in sys.argv
+    PillarVFE, PointPillarScatter = load_reference()
+    torch.manual_seed(0)
+    for case in CASES:
+        data, canvas = run_case(PillarVFE, PointPillarScatter, *case)
+        path = os.path.join(HERE, f"vfe_{case[0]}.npz")
+        np.savez_compressed(path, **data)
+        msg = f"{case[0]:14s} M={data['voxels'].shape[0]:6d} -> {os.path.basename(path)} ({os.path.getsize(path) / 1e3:.0f} kB)"
+        if check:
+            cfg = synthetic.CONFIGS[case[1]]
+            geom = oracle.Geometry(cfg["pc_range"], cfg["voxel_size"])
+            pfn = oracle.PfnParams(data["weight"], data["gamma"], data["beta"], data["running_mean"], data["running_var"])
+            got = oracle.pillar_vfe(data["voxels"], data["voxel_coords"], data["voxel_num_points"], geom, pfn,
+                                    use_absolute_xyz=case[7], with_distance=case[8])
+            ref = data["pillar_features"]
+            ieee = (got.view(np.uint32) == ref.view(np.uint32)).mean()
+            got = oracle.pillar_vfe(data["voxels"], data["voxel_coords"], data["voxel_num_points"], geom, pfn,
+                                    use_absolute_xyz=case[7], with_distance=case[8],
+                                    invstd_override=data["ref_invstd"])
+            eq = (got.view(np.uint32) == ref.view(np.uint32)).mean()
+            msg += f" | ieee-invstd bit-equal {100 * ieee:.3f}%"
+            g = geom.grid
+            cv = oracle.pointpillar_scatter(got, data["voxel_coords"], canvas.shape[0], 64, int(g[1]), int(g[0]))
+            msg += f" | torch-invstd bit-equal {100 * eq:.3f}% max|d|={np.abs(got - ref).max():.3g} canvas_eq={np.array_equal(cv.view(np.uint32), canvas.view(np.uint32)) if eq == 1 else np.allclose(cv, canvas)}"
+        print(msg)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,42 @@
+"""Shared helpers for the parity tests: the oracle is the checker, the CUDA library the thing checked."""
+from __future__ import annotations
+
+import numpy as np
+
+from hgsfusion_b200 import synthetic
+from oracle import oracle
+
+
+def geom_for(config: str) -> oracle.Geometry:
+    c = synthetic.CONFIGS[config]
+    return oracle.Geometry(c["pc_range"], c["voxel_size"])
+
+
+def oracle_pfn(w) -> oracle.PfnParams:
+    return oracle.PfnParams(w.weight, w.gamma, w.beta, w.running_mean, w.running_var, bias=w.bias, eps=w.eps)
+
+
+def device_pfn(w, device, use_absolute_xyz=True, with_distance=False):
+    import torch
+    from hgsfusion_b200.ops import PfnWeights
+    t = lambda a: None if a is None else torch.from_numpy(np.ascontiguousarray(a)).to(device)
+    return PfnWeights(weight=t(w.weight), bn_weight=t(w.gamma), bn_bias=t(w.beta), running_mean=t(w.running_mean),
+                      running_var=t(w.running_var), bias=t(w.bias), eps=w.eps,
+                      use_absolute_xyz=use_absolute_xyz, with_distance=with_distance)
+
+
+def bits_equal(a: np.ndarray, b: np.ndarray) -> bool:
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    b = np.ascontiguousarray(b, dtype=np.float32)
+    return a.shape == b.shape and np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+def max_rel_err(got: np.ndarray, ref: np.ndarray) -> float:
+    """max |got-ref| / max(|ref|, 1e-5*max|ref|): the 1e-5 relative bar of BASELINE.json with the
+    atol = 1e-5*max|ref| floor SURVEY.md §7 allows for values near zero."""
+    got = got.astype(np.float64)
+    ref = ref.astype(np.float64)
+    if ref.size == 0:
+        return 0.0
+    floor = 1e-5 * max(np.abs(ref).max(), 1e-30)
+    return float((np.abs(got - ref) / np.maximum(np.abs(ref), floor)).max())
