@@ -81,7 +81,6 @@ static int run_path(const hgsf_geometry *g, const hgsf_points *pt, const hgsf_pf
                                         : reinterpret_cast<int32_t *>(base + w.off_frame_offsets);
     p.key = reinterpret_cast<int32_t *>(base + w.off_key);
     p.arrival = reinterpret_cast<uint32_t *>(base + w.off_arrival);
-    p.sorted_idx = reinterpret_cast<int32_t *>(base + w.off_sorted_idx);
     p.sorted_rows = reinterpret_cast<float *>(base + w.off_sorted_rows);
     p.RW = w.RW;
     p.coords = out->voxel_coords; p.num = out->voxel_num_points; p.num_pillars = out->num_pillars;

@@ -6,7 +6,7 @@
 //   k_scan   (1024 points / CTA) single-pass decoupled look-back scan over points: a point that is the
 //                                first of its cell gets (raw pillar id, CSR start) = exclusive prefix of
 //                                (first-flags, cell counts) -> pillar ids come out in first-seen order
-//   k_fill   (1 thread / point)  copies each point's features to its pillar's CSR segment
+//   k_fill   (1 thread / point)  copies each point's features (+ its index) to its pillar's CSR segment
 //   k_emit   (persistent CTAs, one 32-cell x C-channel canvas tile at a time) orders each pillar's
 //                                points by index, keeps the first P, decorates, runs the PFN with the
 //                                weights in registers, takes the max, writes pillar_features /
@@ -208,15 +208,16 @@ __global__ void __launch_bounds__(256) k_fill(const PathParams p) {
     const int local = (int)(e.x - 1u) - __ldg(p.frame_raw_base + b);
     if (local >= p.max_voxels) return;            // pillar beyond max_voxels: never created
     const size_t pos = (size_t)e.z + p.arrival[i];
-    p.sorted_idx[pos] = i;
     const float *src = p.pts + (size_t)i * p.stride + p.xyz_col;
     float4 *dst = reinterpret_cast<float4 *>(p.sorted_rows + pos * p.RW);
     for (int k = 0; k < p.RW; k += 4) {
         float4 v;
-        v.x = (k + 0 < p.F) ? __ldg(src + k + 0) : 0.f;
-        v.y = (k + 1 < p.F) ? __ldg(src + k + 1) : 0.f;
-        v.z = (k + 2 < p.F) ? __ldg(src + k + 2) : 0.f;
-        v.w = (k + 3 < p.F) ? __ldg(src + k + 3) : 0.f;
+        // F features, then the point index (slot F) that k_emit orders the pillar by
+        const float fi = __int_as_float(i);
+        v.x = (k + 0 < p.F) ? __ldg(src + k + 0) : (k + 0 == p.F ? fi : 0.f);
+        v.y = (k + 1 < p.F) ? __ldg(src + k + 1) : (k + 1 == p.F ? fi : 0.f);
+        v.z = (k + 2 < p.F) ? __ldg(src + k + 2) : (k + 2 == p.F ? fi : 0.f);
+        v.w = (k + 3 < p.F) ? __ldg(src + k + 3) : (k + 3 == p.F ? fi : 0.f);
         dst[k >> 2] = v;
     }
 }
@@ -240,12 +241,12 @@ __device__ __forceinline__ void warp_bitonic(uint32_t &key, int &val, int lane, 
 }
 
 // cnt > 32 arrivals in a cell: positions of the 32 smallest point indices, ascending, one per lane
-__device__ __noinline__ int select_first32(const int32_t *__restrict__ seg, int cnt, int lane) {
+__device__ __noinline__ int select_first32(const float *__restrict__ idx0, int stride, int cnt, int lane) {
     uint32_t best = 0xFFFFFFFFu;
     int bestv = 0;
     for (int base = 0; base < cnt; base += 32) {
         const int j = base + lane;
-        uint32_t k = (j < cnt) ? (uint32_t)__ldg(seg + j) : 0xFFFFFFFFu;
+        uint32_t k = (j < cnt) ? __float_as_uint(__ldg(idx0 + (size_t)j * stride)) : 0xFFFFFFFFu;
         int v = j;
         if (base > 0) {
             const uint32_t worst = __shfl_sync(FULL, best, 31);
@@ -262,22 +263,59 @@ __device__ __noinline__ int select_first32(const int32_t *__restrict__ seg, int 
     return bestv;
 }
 
+// Position of a canvas tile, advanced by gridDim.x tiles at a time without any division:
+//   r  = BEV row index (b*nz + z)*ny + y,  xt = tile within the row,  b = frame,  zy = row within the frame
+struct TilePos {
+    int r, xt, b, zy;
+};
+struct TileStep {
+    int dr, dxt, tiles_per_row, rows_per_frame;
+    __device__ __forceinline__ void advance(TilePos &t) const {
+        t.xt += dxt;
+        int dr2 = dr;
+        if (t.xt >= tiles_per_row) { t.xt -= tiles_per_row; ++dr2; }
+        t.r += dr2;
+        t.zy += dr2;
+        while (t.zy >= rows_per_frame) { t.zy -= rows_per_frame; ++t.b; }
+    }
+};
+
+// A tile's plan: which of its 32 cells hold a (kept) pillar, and where that pillar's points sit in
+// the staging buffer (off < 0: not staged -- more than 32 arrivals or the buffer is full -- read
+// straight from global memory).
+struct TilePlan {
+    int nocc;
+    int cell[32], m[32], cnt[32], start[32], off[32];
+};
+constexpr int STAGE_ROWS = 256;   // staged point rows per tile (typical tiles hold ~10, dense blobs ~200)
+
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Persistent CTAs walk the canvas tiles (32 cells of one BEV row x all C channels).  Software pipeline,
+// per iteration i:   plan(i+1) from the prefetched table entries  ->  cp.async gather of tile i+1's point
+// rows into stage[(i+1)&1]  ->  compute tile i from stage[i&1]  ->  one TMA tensor store of the tile.
 template <int F, bool ABS, bool DIST, int C, int NWARPS, bool PFN, bool TMA>
 __global__ void __launch_bounds__(NWARPS * 32) k_emit(const __grid_constant__ CUtensorMap tmap, const PathParams p) {
     using Lane = PfnLane<F, ABS, DIST, C>;
     constexpr int CPL = Lane::CPL;
-    constexpr int RW = (F + 3) / 4 * 4;
-    constexpr int NV = RW / 4;
-    constexpr int TILE = C * 32;   // floats per canvas tile: C channel rows of 32 cells (128 B each)
+    constexpr int RWc = (F + 1 + 3) / 4 * 4;   // F features + the point index, padded to float4
+    constexpr int TILE = C * 32;               // floats per canvas tile: C channel rows of 32 cells (128 B each)
     constexpr int NT = NWARPS * 32;
+    const int Fr = PFN ? F : p.F, RW = PFN ? RWc : p.RW, NV = RW >> 2;
 
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     float *tilebuf = reinterpret_cast<float *>(smem_raw);        // [2][TILE]
     float *zerobuf = tilebuf + 2 * TILE;                          // [TILE]
-    int *s_R = reinterpret_cast<int *>(zerobuf + TILE);           // [B+1] raw pillar base per frame
+    float *stage = zerobuf + TILE;                                // [2][STAGE_ROWS * RW]
+    int *s_R = reinterpret_cast<int *>(stage + 2 * STAGE_ROWS * RW);   // [B+1] raw pillar base per frame
     int *s_K = s_R + (p.B + 1);                                   // [B+1] kept (final) pillar base per frame
-    __shared__ int s_nocc[2];
-    __shared__ int s_cell[2][32], s_m[2][32], s_cnt[2][32], s_start[2][32];
+    __shared__ TilePlan s_plan[2];
     __shared__ int s_perm[NWARPS][32];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -299,52 +337,102 @@ __global__ void __launch_bounds__(NWARPS * 32) k_emit(const __grid_constant__ CU
         if (blockIdx.x == 0) p.num_pillars[0] = acc;
     }
     if (canvas_on && TMA) fence_proxy_async_smem();
-    __syncthreads();
 
     // per-lane PFN constants: lane owns channels lane, lane+32, ...
     Lane pfn;
     if (PFN) pfn.load(PfnArgs{p.W, p.bias, p.bn_w, p.bn_b, p.bn_m, p.bn_v, p.eps}, lane);
 
     const int tiles_per_row = (p.nx + 31) >> 5;
-    const int rows = p.B * p.nz * p.ny;
-    const long long n_tiles = (long long)rows * tiles_per_row;
+    const int rows_per_frame = p.nz * p.ny;
+    const int n_rows = p.B * rows_per_frame;
     const int P4 = (p.P >> 2) << 2;
+    TileStep step;
+    step.tiles_per_row = tiles_per_row; step.rows_per_frame = rows_per_frame;
+    step.dr = (int)gridDim.x / tiles_per_row; step.dxt = (int)gridDim.x - step.dr * tiles_per_row;
 
-    auto load_entry = [&](long long t) -> uint4 {
-        const int r = (int)(t / tiles_per_row);
-        const int x = (int)(t - (long long)r * tiles_per_row) * 32 + lane;
+    auto load_entry = [&](const TilePos &t) -> uint4 {
+        const int x = t.xt * 32 + lane;
         // row r = (b*nz + z)*ny + y and the table is [b][z][y][x]: the cell index is r*nx + x
-        return (x < p.nx) ? __ldg(reinterpret_cast<const uint4 *>(p.table + (size_t)r * p.nx + x)) : make_uint4(0, 0, 0, 0);
+        return (t.r < n_rows && x < p.nx) ? __ldg(reinterpret_cast<const uint4 *>(p.table + (size_t)t.r * p.nx + x))
+                                          : make_uint4(0, 0, 0, 0);
     };
-
-    long long tile = blockIdx.x;
-    uint4 e_next = make_uint4(0, 0, 0, 0);
-    if (warp == 0 && tile < n_tiles) e_next = load_entry(tile);
-    int nb = 0;   // non-empty tiles so far (selects the smem tile buffer)
-    for (int it = 0; tile < n_tiles; ++it, tile += gridDim.x) {
-        const int slot = it & 1;
-        const int r = (int)(tile / tiles_per_row);
-        const int x0 = (int)(tile - (long long)r * tiles_per_row) * 32;
-        const int b = r / (p.nz * p.ny);
-        const int zy = r - b * (p.nz * p.ny);
-        const int z = zy / p.ny, y = zy - z * p.ny;
-        if (warp == 0) {
-            const uint4 e = e_next;
-            const long long nt = tile + gridDim.x;
-            if (nt < n_tiles) e_next = load_entry(nt);
-            const bool occ = (e.x != 0u) && ((int)(e.x - 1u) - s_R[b] < p.max_voxels);
-            const unsigned bal = __ballot_sync(FULL, occ);
-            if (occ) {
-                const int k = __popc(bal & ((1u << lane) - 1u));
-                s_cell[slot][k] = lane; s_m[slot][k] = (int)(e.x - 1u); s_cnt[slot][k] = (int)e.y; s_start[slot][k] = (int)e.z;
-            }
-            if (lane == 0) {
-                s_nocc[slot] = __popc(bal);
-                if (canvas_on && TMA && bal) tma_wait_read<1>();   // the buffer used two non-empty tiles ago is free
+    // warp 0: entries -> plan
+    auto make_plan = [&](TilePlan &q, const uint4 e, const TilePos &t) {
+        const int b = t.r < n_rows ? t.b : 0;
+        const bool occ = (e.x != 0u) && ((int)(e.x - 1u) - s_R[b] < p.max_voxels);
+        const unsigned bal = __ballot_sync(FULL, occ);
+        const int need = (occ && e.y <= 32u) ? (int)e.y : 0;
+        int incl = need;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int o = __shfl_up_sync(FULL, incl, d);
+            if (lane >= d) incl += o;
+        }
+        if (occ) {
+            const int k = __popc(bal & ((1u << lane) - 1u));
+            q.cell[k] = lane; q.m[k] = (int)(e.x - 1u); q.cnt[k] = (int)e.y; q.start[k] = (int)e.z;
+            q.off[k] = (need > 0 && incl <= STAGE_ROWS) ? (incl - need) : -1;
+        }
+        if (lane == 0) q.nocc = __popc(bal);
+    };
+    // all warps: start the gather of a planned tile (warp per pillar, lane per point)
+    auto issue_gather = [&](const TilePlan &q, float *stg) {
+        const int nocc = q.nocc;
+        for (int k = warp; k < nocc; k += NWARPS) {
+            const int off = q.off[k];
+            if (off >= 0 && lane < q.cnt[k]) {
+                const float *src = p.sorted_rows + (size_t)(q.start[k] + lane) * RW;
+                float *dst = stg + (size_t)(off + lane) * RW;
+                for (int v = 0; v < NV; ++v) cp_async16(dst + 4 * v, src + 4 * v);
             }
         }
+        cp_async_commit();
+    };
+
+    // the only divisions of the kernel: where this CTA starts
+    TilePos cur;
+    cur.r = (int)blockIdx.x / tiles_per_row; cur.xt = (int)blockIdx.x - cur.r * tiles_per_row;
+    cur.b = cur.r / rows_per_frame; cur.zy = cur.r - cur.b * rows_per_frame;
+    TilePos nxt = cur;
+    step.advance(nxt);
+    TilePos nxt2 = nxt;
+    step.advance(nxt2);
+    uint4 e_next = make_uint4(0, 0, 0, 0);
+    __syncthreads();                                       // s_R / s_K / zerobuf ready
+    if (warp == 0) {
+        make_plan(s_plan[0], load_entry(cur), cur);
+        e_next = load_entry(nxt);
+    }
+    __syncthreads();
+    issue_gather(s_plan[0], stage);
+
+    int nb = 0;   // non-empty tiles so far (selects the smem tile buffer)
+    for (int it = 0; cur.r < n_rows; ++it, cur = nxt, nxt = nxt2, step.advance(nxt2)) {
+        const int slot = it & 1;
+        const TilePlan &q = s_plan[slot];
+        const float *stg = stage + (size_t)slot * STAGE_ROWS * RW;
+        const int x0 = cur.xt * 32;
+        const int b = cur.b, zy = cur.zy;
+        const int z = (p.nz == 1) ? 0 : zy / p.ny;
+        const int y = zy - z * p.ny;
+        // (1) plan the next tile, prefetch the entries of the one after it
+        if (warp == 0) {
+            make_plan(s_plan[slot ^ 1], e_next, nxt);
+            e_next = load_entry(nxt2);
+            if (canvas_on && TMA && lane == 0 && q.nocc > 0) tma_wait_read<1>();   // tile buffer of two tiles ago is free
+        }
         __syncthreads();   // (A)
-        const int n_occ = s_nocc[slot];
+        // (2) start the next tile's gather, clear this tile's buffer
+        issue_gather(s_plan[slot ^ 1], stage + (size_t)(slot ^ 1) * STAGE_ROWS * RW);
+        const int n_occ = q.nocc;
+        float *tb = tilebuf + (nb & 1) * TILE;
+        if (n_occ > 0) {
+            ++nb;
+            if (canvas_on)
+                for (int t = tid * 4; t < TILE; t += NT * 4) *reinterpret_cast<float4 *>(tb + t) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        cp_async_wait<1>();   // this tile's rows have landed (for this thread's copies)
+        __syncthreads();      // (B) ... and everybody else's; tile buffer cleared
         if (n_occ == 0) {
             if (canvas_on) {
                 if (TMA) {
@@ -356,67 +444,76 @@ __global__ void __launch_bounds__(NWARPS * 32) k_emit(const __grid_constant__ CU
             }
             continue;
         }
-        float *tb = tilebuf + (nb & 1) * TILE;
-        ++nb;
-        if (canvas_on) {
-            for (int t = tid * 4; t < TILE; t += NT * 4) *reinterpret_cast<float4 *>(tb + t) = make_float4(0.f, 0.f, 0.f, 0.f);
-            __syncthreads();   // (B)
-        }
+        // (3) compute: warp per pillar
         for (int k = warp; k < n_occ; k += NWARPS) {
-            const int cell = s_cell[slot][k], m = s_m[slot][k], cnt = s_cnt[slot][k], start = s_start[slot][k];
+            const int cell = q.cell[k], m = q.m[k], cnt = q.cnt[k], start = q.start[k], off = q.off[k];
             const int f = s_K[b] + (m - s_R[b]);          // final pillar id (first-seen order, frames concatenated)
             const int n_keep = min(cnt, p.P);
-            const int32_t *seg = p.sorted_idx + start;
+            const bool staged = off >= 0;
+            const float *grow = p.sorted_rows + (size_t)start * RW;   // the pillar's rows in global memory
+            const float *srow = stg + (size_t)(staged ? off : 0) * RW; // ... and in the staging buffer
             // ---- order the cell's points by input index, keep the first P ----
             if (cnt == 1) {
                 if (lane == 0) s_perm[warp][0] = 0;
             } else if (cnt <= 32) {
-                const uint32_t mine = (lane < cnt) ? (uint32_t)__ldg(seg + lane) : 0xFFFFFFFFu;
+                uint32_t mine = 0xFFFFFFFFu;
+                if (lane < cnt) mine = staged ? __float_as_uint(srow[lane * RW + Fr]) : __float_as_uint(__ldg(grow + (size_t)lane * RW + Fr));
                 int rank = 0;
-                for (int q = 0; q < cnt; ++q) rank += (__shfl_sync(FULL, mine, q) < mine) ? 1 : 0;
+                for (int qq = 0; qq < cnt; ++qq) rank += (__shfl_sync(FULL, mine, qq) < mine) ? 1 : 0;
                 if (lane < cnt) s_perm[warp][rank] = lane;
             } else {
-                const int v = select_first32(seg, cnt, lane);
-                s_perm[warp][lane] = v;
+                s_perm[warp][lane] = select_first32(grow + Fr, RW, cnt, lane);
             }
             __syncwarp();
             if (lane == 0) {
                 p.num[f] = n_keep;
                 *reinterpret_cast<int4 *>(p.coords + 4 * (size_t)f) = make_int4(b, z, y, x0 + cell);
             }
-            const int Fr = PFN ? F : p.F, RWr = PFN ? RW : p.RW;
-            const float *rows_base = p.sorted_rows + (size_t)start * RWr;
             if (p.voxels) {
                 float *vo = p.voxels + (size_t)f * p.P * Fr;
                 for (int t = lane; t < p.P * Fr; t += 32) {
                     const int s = t / Fr, kk = t - s * Fr;
-                    vo[t] = (s < n_keep) ? __ldg(rows_base + (size_t)s_perm[warp][s] * RWr + kk) : 0.f;
+                    float v = 0.f;
+                    if (s < n_keep) v = staged ? srow[s_perm[warp][s] * RW + kk] : __ldg(grow + (size_t)s_perm[warp][s] * RW + kk);
+                    vo[t] = v;
                 }
             }
             if (PFN) {
-                // ---- mean of the kept points (torch CPU sum order, pfn.cuh) ----
-                SlotSum sum;
-                for (int s = 0; s < n_keep; ++s) {
-                    const float4 v = __ldg(reinterpret_cast<const float4 *>(rows_base + (size_t)s_perm[warp][s] * RW));
-                    sum.add(s, P4, v.x, v.y, v.z);
-                }
-                const float fn = (float)n_keep;
-                const float mx = __fdiv_rn(sum.sx(), fn), my = __fdiv_rn(sum.sy(), fn), mz = __fdiv_rn(sum.sz(), fn);
+                auto load_row = [&](int s, float (&rowf)[RWc]) {
+                    const int pp = s_perm[warp][s];
+#pragma unroll
+                    for (int v = 0; v < RWc / 4; ++v) {
+                        const float4 t4 = staged ? *reinterpret_cast<const float4 *>(srow + pp * RWc + 4 * v)
+                                                 : __ldg(reinterpret_cast<const float4 *>(grow + (size_t)pp * RWc) + v);
+                        rowf[4 * v] = t4.x; rowf[4 * v + 1] = t4.y; rowf[4 * v + 2] = t4.z; rowf[4 * v + 3] = t4.w;
+                    }
+                };
                 // pillar centre: fl(fl(c*v)+off), two roundings, no FMA (pillar_vfe.py:101-103)
                 const float cx = __fadd_rn(__fmul_rn((float)(x0 + cell), p.vsize[0]), p.voff[0]);
                 const float cy = __fadd_rn(__fmul_rn((float)y, p.vsize[1]), p.voff[1]);
                 const float cz = __fadd_rn(__fmul_rn((float)z, p.vsize[2]), p.voff[2]);
                 float vmax[CPL];
                 pfn.init_max(vmax, n_keep < p.P);
-                for (int s = 0; s < n_keep; ++s) {
-                    const float4 *r4 = reinterpret_cast<const float4 *>(rows_base + (size_t)s_perm[warp][s] * RW);
-                    float rowf[RW];
-#pragma unroll
-                    for (int q = 0; q < NV; ++q) {
-                        const float4 v = __ldg(r4 + q);
-                        rowf[4 * q] = v.x; rowf[4 * q + 1] = v.y; rowf[4 * q + 2] = v.z; rowf[4 * q + 3] = v.w;
+                float rowf[RWc];
+                if (n_keep == 1) {
+                    // mean of one point is the point (x/1 is exact): skip the slot sum
+                    load_row(0, rowf);
+                    pfn.point(rowf, rowf[0], rowf[1], rowf[2], cx, cy, cz, vmax);
+                } else {
+                    // ---- mean of the kept points (torch CPU sum order, pfn.cuh) ----
+                    SlotSum sum;
+                    for (int s = 0; s < n_keep; ++s) {
+                        const int pp = s_perm[warp][s];
+                        const float4 v = staged ? *reinterpret_cast<const float4 *>(srow + pp * RWc)
+                                                : __ldg(reinterpret_cast<const float4 *>(grow + (size_t)pp * RWc));
+                        sum.add(s, P4, v.x, v.y, v.z);
                     }
-                    pfn.point(rowf, mx, my, mz, cx, cy, cz, vmax);
+                    const float fn = (float)n_keep;
+                    const float mx = __fdiv_rn(sum.sx(), fn), my = __fdiv_rn(sum.sy(), fn), mz = __fdiv_rn(sum.sz(), fn);
+                    for (int s = 0; s < n_keep; ++s) {
+                        load_row(s, rowf);
+                        pfn.point(rowf, mx, my, mz, cx, cy, cz, vmax);
+                    }
                 }
 #pragma unroll
                 for (int j = 0; j < CPL; ++j) {
@@ -427,6 +524,7 @@ __global__ void __launch_bounds__(NWARPS * 32) k_emit(const __grid_constant__ CU
             }
             __syncwarp();
         }
+        // (4) the tile goes out in one piece
         if (canvas_on) {
             if (TMA) {
                 fence_proxy_async_smem();
@@ -437,8 +535,11 @@ __global__ void __launch_bounds__(NWARPS * 32) k_emit(const __grid_constant__ CU
                 for (int c = warp; c < C; c += NWARPS)
                     if (x0 + lane < p.nx) p.canvas[(((size_t)b * C + c) * p.ny + y) * p.nx + x0 + lane] = tb[swz128(c, lane)];
             }
+        } else {
+            __syncthreads();       // plan / stage buffers are recycled two iterations later
         }
     }
+    cp_async_wait<0>();
     if (canvas_on && TMA && tid == 0) tma_wait_read<0>();
 }
 
@@ -496,7 +597,7 @@ static int launch_emit_t(const PathParams &p, cudaStream_t stream) {
         const int st = make_canvas_map(&map, p.canvas, p.B, C, p.ny, p.nx);
         if (st != HGSF_OK) return st;
     }
-    const size_t smem = sizeof(float) * 3 * C * 32 + sizeof(int) * 2 * (size_t)(p.B + 1);
+    const size_t smem = sizeof(float) * (3 * C * 32 + 2 * STAGE_ROWS * (size_t)p.RW) + sizeof(int) * 2 * (size_t)(p.B + 1);
     const long long n_tiles = (long long)p.B * p.nz * p.ny * ((p.nx + 31) / 32);
     if (n_tiles == 0) return HGSF_OK;
     auto go = [&](auto kern) -> int {

@@ -23,8 +23,7 @@ struct PathParams {
     int32_t *frame_offsets;            // [B+1] (aliases frame_offsets_in when given)
     int32_t *key;                      // [n] cell key of each point, -1 = outside the grid
     uint32_t *arrival;                 // [n] unordered arrival rank of the point inside its cell
-    int32_t *sorted_idx;               // [n] point index, grouped by pillar (CSR order)
-    float *sorted_rows;                // [n, RW] the F features of that point, grouped by pillar
+    float *sorted_rows;                // [n, RW] F features + point index of each point, grouped by pillar (CSR order)
     int RW;
     // ---- PFN ----
     const float *W, *bias, *bn_w, *bn_b, *bn_m, *bn_v;
@@ -38,7 +37,7 @@ struct PathParams {
 struct WorkspaceLayout {
     size_t zero_bytes;     // leading region that must be zero at the start of every call
     size_t off_ticket, off_desc, off_raw_base, off_table;
-    size_t off_frame_offsets, off_key, off_arrival, off_sorted_idx, off_sorted_rows;
+    size_t off_frame_offsets, off_key, off_arrival, off_sorted_rows;
     size_t total;
     int scan_tiles, RW;
 };
@@ -49,7 +48,7 @@ inline WorkspaceLayout workspace_layout(int64_t n, int B, int64_t cells, int F) 
     WorkspaceLayout w{};
     size_t o = 0;
     w.scan_tiles = (int)((n + SCAN_TILE - 1) / SCAN_TILE);
-    w.RW = (F + 3) / 4 * 4;
+    w.RW = (F + 1 + 3) / 4 * 4;   // F features + the point index
     w.off_ticket = o;      o = align_up(o + 16, 256);
     w.off_desc = o;        o = align_up(o + sizeof(uint64_t) * (size_t)(w.scan_tiles > 0 ? w.scan_tiles : 1), 256);
     w.off_raw_base = o;    o = align_up(o + sizeof(int32_t) * (size_t)(B + 1), 256);
@@ -58,7 +57,6 @@ inline WorkspaceLayout workspace_layout(int64_t n, int B, int64_t cells, int F) 
     w.off_frame_offsets = o; o = align_up(o + sizeof(int32_t) * (size_t)(B + 1), 256);
     w.off_key = o;         o = align_up(o + sizeof(int32_t) * (size_t)n, 256);
     w.off_arrival = o;     o = align_up(o + sizeof(uint32_t) * (size_t)n, 256);
-    w.off_sorted_idx = o;  o = align_up(o + sizeof(int32_t) * (size_t)n, 256);
     w.off_sorted_rows = o; o = align_up(o + sizeof(float) * (size_t)n * (size_t)w.RW, 256);
     w.total = o;
     return w;
