@@ -200,7 +200,7 @@ int launch_scatter(const ScatterParams &q, cudaStream_t stream, int *launches) {
     CUtensorMap map;
     memset(&map, 0, sizeof(map));
     if (tma) {
-        const int st = make_canvas_map(&map, q.canvas, q.B, q.C, q.ny, q.nx);
+        const int st = make_canvas_map(&map, q.canvas, q.B, q.C, q.ny, q.nx, q.C);
         if (st != HGSF_OK) return st;
     }
     const size_t smem = sizeof(float) * 3 * (size_t)q.C * 32;

@@ -32,7 +32,7 @@ int launch_vfe(const VfeParams &q, bool abs_xyz, bool dist, cudaStream_t stream)
 int launch_scatter(const ScatterParams &q, cudaStream_t stream, int *launches);
 
 // shared host helpers (pillar_path.cu)
-int make_canvas_map(CUtensorMap *map, float *canvas, int B, int C, int ny, int nx);
+int make_canvas_map(CUtensorMap *map, float *canvas, int B, int C, int ny, int nx, int box_c);
 int sm_count();
 
 }  // namespace hgsf

@@ -280,14 +280,22 @@ struct TileStep {
     }
 };
 
-// A tile's plan: which of its 32 cells hold a (kept) pillar, and where that pillar's points sit in
-// the staging buffer (off < 0: not staged -- more than 32 arrivals or the buffer is full -- read
-// straight from global memory).
-struct TilePlan {
-    int nocc;
-    int cell[32], m[32], cnt[32], start[32], off[32];
-};
-constexpr int STAGE_ROWS = 256;   // staged point rows per tile (typical tiles hold ~10, dense blobs ~200)
+// ---- k_emit -------------------------------------------------------------------------------------
+// Every WARP is an autonomous worker: it walks its own sequence of canvas tiles (a tile = 32 cells of
+// one BEV row x all C channels = C rows of 128 B) with its own tile buffer, staging buffers and
+// software pipeline; there is no CTA barrier inside the loop, so a warp that waits (gather, TMA
+// read-out) never holds up another.  The CTA only shares the PFN weights (k-major in shared memory,
+// read as broadcast float4s) and a small zero tile.
+//
+// Lane l owns cell l of the tile for the bookkeeping (table entry, ordering, mean: all in registers).
+// The arithmetic is cut into UNITS of (pillar, 4 output channels) dealt round-robin to the 32 lanes, so
+// lanes stay busy whatever the number of pillars in the tile.
+//
+// Pipeline of one warp, iteration i:  prefetch table entries of tile i+2  |  cp.async gather of tile
+// i+1's point rows  |  order + mean + units of tile i  |  one TMA tensor store of tile i.
+constexpr int EMIT_WARPS = 4;
+constexpr int EMIT_THREADS = EMIT_WARPS * 32;
+constexpr int STAGE_W = 64;           // staged point rows per tile (a typical tile holds ~10; the rest is read from L2)
 
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)
@@ -297,33 +305,67 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// Persistent CTAs walk the canvas tiles (32 cells of one BEV row x all C channels).  Software pipeline,
-// per iteration i:   plan(i+1) from the prefetched table entries  ->  cp.async gather of tile i+1's point
-// rows into stage[(i+1)&1]  ->  compute tile i from stage[i&1]  ->  one TMA tensor store of the tile.
-template <int F, bool ABS, bool DIST, int C, int NWARPS, bool PFN, bool TMA>
-__global__ void __launch_bounds__(NWARPS * 32) k_emit(const __grid_constant__ CUtensorMap tmap, const PathParams p) {
-    using Lane = PfnLane<F, ABS, DIST, C>;
-    constexpr int CPL = Lane::CPL;
+// what a lane knows about its cell of a tile
+struct CellState {
+    int m, cnt, start, off;     // raw pillar id, arrivals, CSR start, staging offset
+    bool occ, staged;           // holds a kept pillar / its rows are (being) staged
+};
+
+template <int F, bool ABS, bool DIST, bool BN, int C, bool PFN, bool TMA>
+__global__ void __launch_bounds__(EMIT_THREADS, 4)
+k_emit(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap zmap, const PathParams p) {
+    constexpr int CIN = PFN ? ((ABS ? F : F - 3) + 6 + (DIST ? 1 : 0)) : 1;
     constexpr int RWc = (F + 1 + 3) / 4 * 4;   // F features + the point index, padded to float4
-    constexpr int TILE = C * 32;               // floats per canvas tile: C channel rows of 32 cells (128 B each)
-    constexpr int NT = NWARPS * 32;
+    constexpr int TILE = C * 32;               // floats per tile
+    constexpr int ZC = C / 4;                  // channels of the shared zero tile (an empty tile = 4 stores of it)
+    constexpr int NT = EMIT_THREADS;
+    static_assert(C == 64, "units are 4 of 64 channels; the fallback path maps 2 channels per lane");
     const int Fr = PFN ? F : p.F, RW = PFN ? RWc : p.RW, NV = RW >> 2;
 
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    float *tilebuf = reinterpret_cast<float *>(smem_raw);        // [2][TILE]
-    float *zerobuf = tilebuf + 2 * TILE;                          // [TILE]
-    float *stage = zerobuf + TILE;                                // [2][STAGE_ROWS * RW]
-    int *s_R = reinterpret_cast<int *>(stage + 2 * STAGE_ROWS * RW);   // [B+1] raw pillar base per frame
-    int *s_K = s_R + (p.B + 1);                                   // [B+1] kept (final) pillar base per frame
-    __shared__ TilePlan s_plan[2];
-    __shared__ int s_perm[NWARPS][32];
+    float *tiles = reinterpret_cast<float *>(smem_raw);                    // [EMIT_WARPS][TILE]
+    float *zerobuf = tiles + EMIT_WARPS * TILE;                            // [ZC*32]
+    float *s_W = zerobuf + ZC * 32;                                        // [CIN][C]  k-major Linear weight
+    float *s_bn = s_W + CIN * C;                                           // [5][C]    mean, invstd, gamma, beta(bias), pad value
+    float *stage_all = s_bn + 5 * C;                                       // [EMIT_WARPS][2][STAGE_W * RW]
+    float4 *rec_all = reinterpret_cast<float4 *>(stage_all + EMIT_WARPS * 2 * STAGE_W * RW);   // [EMIT_WARPS][32][2]
+    int *s_R = reinterpret_cast<int *>(rec_all + EMIT_WARPS * 64);         // [B+1] raw pillar base per frame
+    int *s_K = s_R + (p.B + 1);                                            // [B+1] kept (final) pillar base per frame
+    __shared__ unsigned char s_perm_all[EMIT_WARPS][STAGE_W];              // per pillar: arrival position of its rank-th point
+    __shared__ int s_bperm_all[EMIT_WARPS][32];                            // warp-per-pillar path
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool canvas_on = PFN && (p.canvas != nullptr);
+    float *tile = tiles + warp * TILE;
+    float *stage = stage_all + (size_t)warp * 2 * STAGE_W * RW;
+    float4 *rec = rec_all + warp * 64;
+    unsigned char *s_perm = s_perm_all[warp];
+    int *s_bperm = s_bperm_all[warp];
 
+    // ---- one-time setup (the only CTA barriers) ----
     for (int b = tid; b <= p.B; b += NT) s_R[b] = p.frame_raw_base[b];
-    if (canvas_on)
-        for (int t = tid; t < TILE; t += NT) zerobuf[t] = 0.f;
+    if (canvas_on) {
+        for (int t = tid; t < ZC * 32; t += NT) zerobuf[t] = 0.f;
+        for (int t = tid; t < EMIT_WARPS * TILE; t += NT) tiles[t] = 0.f;
+    }
+    if (PFN) {
+        for (int t = tid; t < CIN * C; t += NT) { const int c = t / CIN, k = t - c * CIN; s_W[k * C + c] = __ldg(p.W + t); }
+        for (int c = tid; c < C; c += NT) {
+            float y;
+            if (BN) {
+                const float mu = __ldg(p.bn_m + c), g = __ldg(p.bn_w + c), be = __ldg(p.bn_b + c);
+                const float inv = __frcp_rn(__fsqrt_rn(__fadd_rn(__ldg(p.bn_v + c), p.eps)));
+                s_bn[c] = mu; s_bn[C + c] = inv; s_bn[2 * C + c] = g; s_bn[3 * C + c] = be;
+                // a zero (padded) row still goes through BN + ReLU and joins the max (pillar_vfe.py:37-42)
+                y = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(0.f, mu), inv), g), be);
+            } else {
+                const float be = __ldg(p.bias + c);
+                s_bn[c] = 0.f; s_bn[C + c] = 0.f; s_bn[2 * C + c] = 0.f; s_bn[3 * C + c] = be;
+                y = __fadd_rn(0.f, be);
+            }
+            s_bn[4 * C + c] = (y > 0.f || y != y) ? y : 0.f;
+        }
+    }
     __syncthreads();
     if (tid == 0) {
         int acc = 0;
@@ -337,210 +379,355 @@ __global__ void __launch_bounds__(NWARPS * 32) k_emit(const __grid_constant__ CU
         if (blockIdx.x == 0) p.num_pillars[0] = acc;
     }
     if (canvas_on && TMA) fence_proxy_async_smem();
-
-    // per-lane PFN constants: lane owns channels lane, lane+32, ...
-    Lane pfn;
-    if (PFN) pfn.load(PfnArgs{p.W, p.bias, p.bn_w, p.bn_b, p.bn_m, p.bn_v, p.eps}, lane);
+    __syncthreads();
 
     const int tiles_per_row = (p.nx + 31) >> 5;
     const int rows_per_frame = p.nz * p.ny;
     const int n_rows = p.B * rows_per_frame;
     const int P4 = (p.P >> 2) << 2;
+    const int maxv = p.max_voxels, Pmax = p.P;
+    const float vsx = p.vsize[0], vsy = p.vsize[1], vsz = p.vsize[2], vox = p.voff[0], voy = p.voff[1], voz = p.voff[2];
+    const CellEntry *__restrict__ table = p.table;
+    const float *__restrict__ grows = p.sorted_rows;
+    const unsigned lt = (1u << lane) - 1u;
+
+    // this warp's tile sequence: first tile blockIdx*W + warp, stride gridDim*W; stepping is division free
     TileStep step;
     step.tiles_per_row = tiles_per_row; step.rows_per_frame = rows_per_frame;
-    step.dr = (int)gridDim.x / tiles_per_row; step.dxt = (int)gridDim.x - step.dr * tiles_per_row;
+    {
+        const int stride_tiles = (int)gridDim.x * EMIT_WARPS;
+        step.dr = stride_tiles / tiles_per_row; step.dxt = stride_tiles - step.dr * tiles_per_row;
+    }
+    TilePos cur;
+    {
+        const int t0 = (int)blockIdx.x * EMIT_WARPS + warp;      // the only divisions: where this warp starts
+        cur.r = t0 / tiles_per_row; cur.xt = t0 - cur.r * tiles_per_row;
+        cur.b = cur.r / rows_per_frame; cur.zy = cur.r - cur.b * rows_per_frame;
+    }
+    TilePos nxt = cur;
+    step.advance(nxt);
+    TilePos nxt2 = nxt;
+    step.advance(nxt2);
 
     auto load_entry = [&](const TilePos &t) -> uint4 {
         const int x = t.xt * 32 + lane;
         // row r = (b*nz + z)*ny + y and the table is [b][z][y][x]: the cell index is r*nx + x
-        return (t.r < n_rows && x < p.nx) ? __ldg(reinterpret_cast<const uint4 *>(p.table + (size_t)t.r * p.nx + x))
+        return (t.r < n_rows && x < p.nx) ? __ldg(reinterpret_cast<const uint4 *>(table + (size_t)t.r * p.nx + x))
                                           : make_uint4(0, 0, 0, 0);
     };
-    // warp 0: entries -> plan
-    auto make_plan = [&](TilePlan &q, const uint4 e, const TilePos &t) {
-        const int b = t.r < n_rows ? t.b : 0;
-        const bool occ = (e.x != 0u) && ((int)(e.x - 1u) - s_R[b] < p.max_voxels);
-        const unsigned bal = __ballot_sync(FULL, occ);
-        const int need = (occ && e.y <= 32u) ? (int)e.y : 0;
+    auto make_state = [&](const uint4 e, const TilePos &t) -> CellState {
+        CellState c;
+        const int b = (t.r < n_rows) ? t.b : 0;
+        c.m = (int)(e.x - 1u); c.cnt = (int)e.y; c.start = (int)e.z;
+        c.occ = (e.x != 0u) && (c.m - s_R[b] < maxv);
+        const int need = (c.occ && c.cnt <= 32) ? c.cnt : 0;
         int incl = need;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             const int o = __shfl_up_sync(FULL, incl, d);
             if (lane >= d) incl += o;
         }
-        if (occ) {
-            const int k = __popc(bal & ((1u << lane) - 1u));
-            q.cell[k] = lane; q.m[k] = (int)(e.x - 1u); q.cnt[k] = (int)e.y; q.start[k] = (int)e.z;
-            q.off[k] = (need > 0 && incl <= STAGE_ROWS) ? (incl - need) : -1;
-        }
-        if (lane == 0) q.nocc = __popc(bal);
+        c.off = incl - need;
+        c.staged = need > 0 && incl <= STAGE_W;
+        return c;
     };
-    // all warps: start the gather of a planned tile (warp per pillar, lane per point)
-    auto issue_gather = [&](const TilePlan &q, float *stg) {
-        const int nocc = q.nocc;
-        for (int k = warp; k < nocc; k += NWARPS) {
-            const int off = q.off[k];
-            if (off >= 0 && lane < q.cnt[k]) {
-                const float *src = p.sorted_rows + (size_t)(q.start[k] + lane) * RW;
-                float *dst = stg + (size_t)(off + lane) * RW;
-                for (int v = 0; v < NV; ++v) cp_async16(dst + 4 * v, src + 4 * v);
-            }
+    auto issue_gather = [&](const CellState &c, float *stg) {
+        if (c.staged) {
+            const float *src = grows + (size_t)c.start * RW;
+            float *dst = stg + (size_t)c.off * RW;
+            for (int j = 0; j < c.cnt; ++j)
+                for (int v = 0; v < NV; ++v) cp_async16(dst + j * RW + 4 * v, src + (size_t)j * RW + 4 * v);
         }
         cp_async_commit();
     };
+    // order one unstaged pillar cooperatively: s_bperm[rank] = arrival position of the rank-th smallest index
+    auto coop_order = [&](const float *grow, int cnt) {
+        if (cnt <= 32) {
+            const uint32_t mine = (lane < cnt) ? __float_as_uint(__ldg(grow + (size_t)lane * RW + Fr)) : 0xFFFFFFFFu;
+            int rank = 0;
+            for (int qq = 0; qq < cnt; ++qq) rank += (__shfl_sync(FULL, mine, qq) < mine) ? 1 : 0;
+            if (lane < cnt) s_bperm[rank] = lane;
+        } else {
+            s_bperm[lane] = select_first32(grow + Fr, RW, cnt, lane);
+        }
+        __syncwarp();
+    };
 
-    // the only divisions of the kernel: where this CTA starts
-    TilePos cur;
-    cur.r = (int)blockIdx.x / tiles_per_row; cur.xt = (int)blockIdx.x - cur.r * tiles_per_row;
-    cur.b = cur.r / rows_per_frame; cur.zy = cur.r - cur.b * rows_per_frame;
-    TilePos nxt = cur;
-    step.advance(nxt);
-    TilePos nxt2 = nxt;
-    step.advance(nxt2);
-    uint4 e_next = make_uint4(0, 0, 0, 0);
-    __syncthreads();                                       // s_R / s_K / zerobuf ready
-    if (warp == 0) {
-        make_plan(s_plan[0], load_entry(cur), cur);
-        e_next = load_entry(nxt);
-    }
-    __syncthreads();
-    issue_gather(s_plan[0], stage);
+    CellState st_cur = make_state(load_entry(cur), cur);
+    issue_gather(st_cur, stage);
+    uint4 e_next = load_entry(nxt);
+    unsigned dirty = 0;                  // cells of the tile buffer that hold non-zero columns
+    bool store_pending = false;          // a TMA store from the tile buffer may still be reading it
 
-    int nb = 0;   // non-empty tiles so far (selects the smem tile buffer)
-    for (int it = 0; cur.r < n_rows; ++it, cur = nxt, nxt = nxt2, step.advance(nxt2)) {
+    for (int it = 0; cur.r < n_rows; ++it) {
         const int slot = it & 1;
-        const TilePlan &q = s_plan[slot];
-        const float *stg = stage + (size_t)slot * STAGE_ROWS * RW;
-        const int x0 = cur.xt * 32;
-        const int b = cur.b, zy = cur.zy;
+        const float *stg = stage + (size_t)slot * STAGE_W * RW;
+        // ---- next tile: cell states, gather in flight; entries of the one after it ----
+        const CellState st_nxt = make_state(e_next, nxt);
+        issue_gather(st_nxt, stage + (size_t)(slot ^ 1) * STAGE_W * RW);
+        e_next = load_entry(nxt2);
+
+        const CellState c = st_cur;
+        const int b = cur.b, zy = cur.zy, x0 = cur.xt * 32;
         const int z = (p.nz == 1) ? 0 : zy / p.ny;
         const int y = zy - z * p.ny;
-        // (1) plan the next tile, prefetch the entries of the one after it
-        if (warp == 0) {
-            make_plan(s_plan[slot ^ 1], e_next, nxt);
-            e_next = load_entry(nxt2);
-            if (canvas_on && TMA && lane == 0 && q.nocc > 0) tma_wait_read<1>();   // tile buffer of two tiles ago is free
-        }
-        __syncthreads();   // (A)
-        // (2) start the next tile's gather, clear this tile's buffer
-        issue_gather(s_plan[slot ^ 1], stage + (size_t)(slot ^ 1) * STAGE_ROWS * RW);
-        const int n_occ = q.nocc;
-        float *tb = tilebuf + (nb & 1) * TILE;
-        if (n_occ > 0) {
-            ++nb;
-            if (canvas_on)
-                for (int t = tid * 4; t < TILE; t += NT * 4) *reinterpret_cast<float4 *>(tb + t) = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        cp_async_wait<1>();   // this tile's rows have landed (for this thread's copies)
-        __syncthreads();      // (B) ... and everybody else's; tile buffer cleared
-        if (n_occ == 0) {
+        const unsigned bal_occ = __ballot_sync(FULL, c.occ);
+        if (bal_occ == 0u) {
+            // empty tile: four stores of the shared zero tile
             if (canvas_on) {
                 if (TMA) {
-                    if (tid == 0) { tma_store_3d(&tmap, zerobuf, x0, zy, b * C); tma_commit(); }
-                } else {
-                    for (int c = warp; c < C; c += NWARPS)
-                        if (x0 + lane < p.nx) p.canvas[(((size_t)b * C + c) * p.ny + y) * p.nx + x0 + lane] = 0.f;
-                }
-            }
-            continue;
-        }
-        // (3) compute: warp per pillar
-        for (int k = warp; k < n_occ; k += NWARPS) {
-            const int cell = q.cell[k], m = q.m[k], cnt = q.cnt[k], start = q.start[k], off = q.off[k];
-            const int f = s_K[b] + (m - s_R[b]);          // final pillar id (first-seen order, frames concatenated)
-            const int n_keep = min(cnt, p.P);
-            const bool staged = off >= 0;
-            const float *grow = p.sorted_rows + (size_t)start * RW;   // the pillar's rows in global memory
-            const float *srow = stg + (size_t)(staged ? off : 0) * RW; // ... and in the staging buffer
-            // ---- order the cell's points by input index, keep the first P ----
-            if (cnt == 1) {
-                if (lane == 0) s_perm[warp][0] = 0;
-            } else if (cnt <= 32) {
-                uint32_t mine = 0xFFFFFFFFu;
-                if (lane < cnt) mine = staged ? __float_as_uint(srow[lane * RW + Fr]) : __float_as_uint(__ldg(grow + (size_t)lane * RW + Fr));
-                int rank = 0;
-                for (int qq = 0; qq < cnt; ++qq) rank += (__shfl_sync(FULL, mine, qq) < mine) ? 1 : 0;
-                if (lane < cnt) s_perm[warp][rank] = lane;
-            } else {
-                s_perm[warp][lane] = select_first32(grow + Fr, RW, cnt, lane);
-            }
-            __syncwarp();
-            if (lane == 0) {
-                p.num[f] = n_keep;
-                *reinterpret_cast<int4 *>(p.coords + 4 * (size_t)f) = make_int4(b, z, y, x0 + cell);
-            }
-            if (p.voxels) {
-                float *vo = p.voxels + (size_t)f * p.P * Fr;
-                for (int t = lane; t < p.P * Fr; t += 32) {
-                    const int s = t / Fr, kk = t - s * Fr;
-                    float v = 0.f;
-                    if (s < n_keep) v = staged ? srow[s_perm[warp][s] * RW + kk] : __ldg(grow + (size_t)s_perm[warp][s] * RW + kk);
-                    vo[t] = v;
-                }
-            }
-            if (PFN) {
-                auto load_row = [&](int s, float (&rowf)[RWc]) {
-                    const int pp = s_perm[warp][s];
+                    if (lane == 0) {
 #pragma unroll
-                    for (int v = 0; v < RWc / 4; ++v) {
-                        const float4 t4 = staged ? *reinterpret_cast<const float4 *>(srow + pp * RWc + 4 * v)
-                                                 : __ldg(reinterpret_cast<const float4 *>(grow + (size_t)pp * RWc) + v);
-                        rowf[4 * v] = t4.x; rowf[4 * v + 1] = t4.y; rowf[4 * v + 2] = t4.z; rowf[4 * v + 3] = t4.w;
+                        for (int q4 = 0; q4 < 4; ++q4) tma_store_3d(&zmap, zerobuf, x0, zy, b * C + q4 * ZC);
+                        tma_commit();
                     }
-                };
-                // pillar centre: fl(fl(c*v)+off), two roundings, no FMA (pillar_vfe.py:101-103)
-                const float cx = __fadd_rn(__fmul_rn((float)(x0 + cell), p.vsize[0]), p.voff[0]);
-                const float cy = __fadd_rn(__fmul_rn((float)y, p.vsize[1]), p.voff[1]);
-                const float cz = __fadd_rn(__fmul_rn((float)z, p.vsize[2]), p.voff[2]);
-                float vmax[CPL];
-                pfn.init_max(vmax, n_keep < p.P);
-                float rowf[RWc];
-                if (n_keep == 1) {
-                    // mean of one point is the point (x/1 is exact): skip the slot sum
-                    load_row(0, rowf);
-                    pfn.point(rowf, rowf[0], rowf[1], rowf[2], cx, cy, cz, vmax);
-                } else {
-                    // ---- mean of the kept points (torch CPU sum order, pfn.cuh) ----
-                    SlotSum sum;
-                    for (int s = 0; s < n_keep; ++s) {
-                        const int pp = s_perm[warp][s];
-                        const float4 v = staged ? *reinterpret_cast<const float4 *>(srow + pp * RWc)
-                                                : __ldg(reinterpret_cast<const float4 *>(grow + (size_t)pp * RWc));
-                        sum.add(s, P4, v.x, v.y, v.z);
-                    }
-                    const float fn = (float)n_keep;
-                    const float mx = __fdiv_rn(sum.sx(), fn), my = __fdiv_rn(sum.sy(), fn), mz = __fdiv_rn(sum.sz(), fn);
-                    for (int s = 0; s < n_keep; ++s) {
-                        load_row(s, rowf);
-                        pfn.point(rowf, mx, my, mz, cx, cy, cz, vmax);
-                    }
+                } else if (x0 + lane < p.nx) {
+                    for (int ch = 0; ch < C; ++ch) p.canvas[(((size_t)b * C + ch) * p.ny + y) * p.nx + x0 + lane] = 0.f;
                 }
-#pragma unroll
-                for (int j = 0; j < CPL; ++j) {
-                    const int c = lane + 32 * j;
-                    if (p.feats) p.feats[(size_t)f * C + c] = vmax[j];
-                    if (canvas_on) tb[swz128(c, cell)] = vmax[j];
-                }
-            }
-            __syncwarp();
-        }
-        // (4) the tile goes out in one piece
-        if (canvas_on) {
-            if (TMA) {
-                fence_proxy_async_smem();
-                __syncthreads();   // (C)
-                if (tid == 0) { tma_store_3d(&tmap, tb, x0, zy, b * C); tma_commit(); }
-            } else {
-                __syncthreads();
-                for (int c = warp; c < C; c += NWARPS)
-                    if (x0 + lane < p.nx) p.canvas[(((size_t)b * C + c) * p.ny + y) * p.nx + x0 + lane] = tb[swz128(c, lane)];
             }
         } else {
-            __syncthreads();       // plan / stage buffers are recycled two iterations later
+            const unsigned bal_st = __ballot_sync(FULL, c.staged);
+            const int n_keep = min(c.cnt, Pmax);
+            const int f = c.occ ? s_K[b] + (c.m - s_R[b]) : 0;     // final pillar id (first-seen order, frames concatenated)
+            if (c.occ) {
+                p.num[f] = n_keep;
+                *reinterpret_cast<int4 *>(p.coords + 4 * (size_t)f) = make_int4(b, z, y, x0 + lane);
+            }
+            cp_async_wait<1>();          // this tile's rows have landed (this lane's copies) ...
+            __syncwarp();                // ... and every other lane's
+            // ---- order the points of multi-point pillars by input index ----
+            if (c.staged && c.cnt > 1 && c.cnt <= 4) {            // small: the owning lane ranks them itself
+                const float *ib = stg + (size_t)c.off * RW + Fr;
+                for (int j = 0; j < c.cnt; ++j) {
+                    const uint32_t mine = __float_as_uint(ib[j * RW]);
+                    int rank = 0;
+                    for (int qq = 0; qq < c.cnt; ++qq) rank += (__float_as_uint(ib[qq * RW]) < mine) ? 1 : 0;
+                    s_perm[c.off + rank] = (unsigned char)j;
+                }
+            }
+            unsigned coop = __ballot_sync(FULL, c.staged && c.cnt > 4);   // larger: the warp ranks one pillar at a time
+            while (coop) {
+                const int o = __ffs(coop) - 1;
+                coop &= coop - 1;
+                const int cnt_o = __shfl_sync(FULL, c.cnt, o), off_o = __shfl_sync(FULL, c.off, o);
+                const uint32_t mine = (lane < cnt_o) ? __float_as_uint(stg[(size_t)(off_o + lane) * RW + Fr]) : 0xFFFFFFFFu;
+                int rank = 0;
+                for (int qq = 0; qq < cnt_o; ++qq) rank += (__shfl_sync(FULL, mine, qq) < mine) ? 1 : 0;
+                if (lane < cnt_o) s_perm[off_o + rank] = (unsigned char)lane;
+            }
+            __syncwarp();
+            if (PFN) {
+                // ---- per-pillar record: mean (torch CPU sum order) and bookkeeping, by the owning lane ----
+                if (c.staged) {
+                    const float *srow = stg + (size_t)c.off * RW;
+                    float mx, my, mz;
+                    if (c.cnt == 1) {
+                        mx = srow[0]; my = srow[1]; mz = srow[2];   // mean of one point is the point (x/1 is exact)
+                    } else {
+                        SlotSum sum;
+                        for (int s2 = 0; s2 < n_keep; ++s2) {
+                            const float4 v = *reinterpret_cast<const float4 *>(srow + s_perm[c.off + s2] * RW);
+                            sum.add(s2, P4, v.x, v.y, v.z);
+                        }
+                        const float fn = (float)n_keep;
+                        mx = __fdiv_rn(sum.sx(), fn); my = __fdiv_rn(sum.sy(), fn); mz = __fdiv_rn(sum.sz(), fn);
+                    }
+                    const int k = __popc(bal_st & lt);
+                    rec[2 * k] = make_float4(mx, my, mz, __int_as_float(lane | (n_keep << 8) | (c.cnt == 1 ? 0x10000 : 0)));
+                    rec[2 * k + 1] = make_float4(__int_as_float(c.off), __int_as_float(f), 0.f, 0.f);
+                }
+                // the tile buffer: wait until the previous store has read it, then clear the columns it dirtied
+                if (canvas_on) {
+                    if (TMA && store_pending) {
+                        if (lane == 0) tma_wait_read<0>();
+                        store_pending = false;
+                    }
+                    __syncwarp();
+                    while (dirty) {
+                        const int dc = __ffs(dirty) - 1;
+                        dirty &= dirty - 1;
+                        tile[swz128(lane, dc)] = 0.f; tile[swz128(lane + 32, dc)] = 0.f;
+                    }
+                }
+                __syncwarp();
+                // ---- units: (pillar, 4 channels), dealt round-robin to the lanes ----
+                const float cy = __fadd_rn(__fmul_rn((float)y, vsy), voy);   // pillar centre: fl(fl(c*v)+off), two roundings,
+                const float cz = __fadd_rn(__fmul_rn((float)z, vsz), voz);   // no FMA (pillar_vfe.py:101-103)
+                const int n_units = __popc(bal_st) * 16;
+                for (int u = lane; u < n_units; u += 32) {
+                    const int k = u >> 4, c0 = (u & 15) * 4;
+                    const float4 r0 = rec[2 * k], r1 = rec[2 * k + 1];
+                    const int meta = __float_as_int(r0.w);
+                    const int cell = meta & 31, nk = (meta >> 8) & 63;
+                    const bool single = (meta & 0x10000) != 0;
+                    const int off = __float_as_int(r1.x), fid = __float_as_int(r1.y);
+                    const float cx = __fadd_rn(__fmul_rn((float)(x0 + cell), vsx), vox);
+                    const float *srow = stg + (size_t)off * RWc;
+                    float4 w4[CIN];
+#pragma unroll
+                    for (int kk = 0; kk < CIN; ++kk) w4[kk] = *reinterpret_cast<const float4 *>(s_W + kk * C + c0);
+                    const float4 be = *reinterpret_cast<const float4 *>(s_bn + 3 * C + c0);
+                    float4 mu, iv, ga;
+                    if (BN) {
+                        mu = *reinterpret_cast<const float4 *>(s_bn + c0);
+                        iv = *reinterpret_cast<const float4 *>(s_bn + C + c0);
+                        ga = *reinterpret_cast<const float4 *>(s_bn + 2 * C + c0);
+                    }
+                    // max over slots as an integer max on the float bits: exact for the non-negative post-ReLU values,
+                    // drops negatives and -0 (the ReLU), and lets a NaN (0x7fffffff) win as torch.max does
+                    int v0 = 0, v1 = 0, v2 = 0, v3 = 0;
+                    if (nk < Pmax) {
+                        const float4 pv = *reinterpret_cast<const float4 *>(s_bn + 4 * C + c0);
+                        v0 = __float_as_int(pv.x); v1 = __float_as_int(pv.y); v2 = __float_as_int(pv.z); v3 = __float_as_int(pv.w);
+                    }
+#pragma unroll 1
+                    for (int s2 = 0; s2 < nk; ++s2) {
+                        const float *rp = srow + (single ? 0 : s_perm[off + s2] * RWc);
+                        float row[RWc];
+#pragma unroll
+                        for (int v = 0; v < RWc / 4; ++v) {
+                            const float4 t4 = *reinterpret_cast<const float4 *>(rp + 4 * v);
+                            row[4 * v] = t4.x; row[4 * v + 1] = t4.y; row[4 * v + 2] = t4.z; row[4 * v + 3] = t4.w;
+                        }
+                        float feat[CIN];
+                        {
+                            int kf = 0;
+#pragma unroll
+                            for (int qq = ABS ? 0 : 3; qq < F; ++qq) feat[kf++] = row[qq];
+                            feat[kf++] = __fsub_rn(row[0], r0.x); feat[kf++] = __fsub_rn(row[1], r0.y); feat[kf++] = __fsub_rn(row[2], r0.z);
+                            feat[kf++] = __fsub_rn(row[0], cx); feat[kf++] = __fsub_rn(row[1], cy); feat[kf++] = __fsub_rn(row[2], cz);
+                            // torch.norm(xyz, 2, 2) on the CPU: sqrt(fma(z,z, fma(y,y, x*x)))  (pillar_vfe.py:110-112)
+                            if (DIST) feat[kf++] = __fsqrt_rn(fmaf(row[2], row[2], fmaf(row[1], row[1], __fmul_rn(row[0], row[0]))));
+                        }
+                        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+                        for (int kk = 0; kk < CIN; ++kk) {     // Linear: sequential FMA in k order (pillar_vfe.py:37)
+                            a0 = fmaf(feat[kk], w4[kk].x, a0); a1 = fmaf(feat[kk], w4[kk].y, a1);
+                            a2 = fmaf(feat[kk], w4[kk].z, a2); a3 = fmaf(feat[kk], w4[kk].w, a3);
+                        }
+                        float y0, y1, y2, y3;
+                        if (BN) {                              // BN eval: (((x-mean)*invstd)*gamma)+beta, 4 roundings (:39)
+                            y0 = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(a0, mu.x), iv.x), ga.x), be.x);
+                            y1 = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(a1, mu.y), iv.y), ga.y), be.y);
+                            y2 = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(a2, mu.z), iv.z), ga.z), be.z);
+                            y3 = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(a3, mu.w), iv.w), ga.w), be.w);
+                        } else {
+                            y0 = __fadd_rn(a0, be.x); y1 = __fadd_rn(a1, be.y); y2 = __fadd_rn(a2, be.z); y3 = __fadd_rn(a3, be.w);
+                        }
+                        v0 = max(v0, __float_as_int(y0)); v1 = max(v1, __float_as_int(y1));
+                        v2 = max(v2, __float_as_int(y2)); v3 = max(v3, __float_as_int(y3));
+                    }
+                    const float4 o = make_float4(__int_as_float(v0), __int_as_float(v1), __int_as_float(v2), __int_as_float(v3));
+                    if (p.feats) *reinterpret_cast<float4 *>(p.feats + (size_t)fid * C + c0) = o;
+                    if (canvas_on) {
+                        tile[swz128(c0, cell)] = o.x; tile[swz128(c0 + 1, cell)] = o.y;
+                        tile[swz128(c0 + 2, cell)] = o.z; tile[swz128(c0 + 3, cell)] = o.w;
+                    }
+                }
+            }
+            // ---- unstaged pillars (> 32 arrivals, or staging full): the warp takes them one at a time, lanes = channels ----
+            unsigned big = bal_occ & ~bal_st;
+            while (big) {
+                const int o = __ffs(big) - 1;
+                big &= big - 1;
+                const int cnt_o = __shfl_sync(FULL, c.cnt, o), start_o = __shfl_sync(FULL, c.start, o), f_o = __shfl_sync(FULL, f, o);
+                const int nk = min(cnt_o, Pmax);
+                const float *grow = grows + (size_t)start_o * RW;
+                coop_order(grow, cnt_o);
+                if (p.voxels) {
+                    float *vo = p.voxels + (size_t)f_o * Pmax * Fr;
+                    for (int t = lane; t < Pmax * Fr; t += 32) {
+                        const int s2 = t / Fr, kk = t - s2 * Fr;
+                        vo[t] = (s2 < nk) ? __ldg(grow + (size_t)s_bperm[s2] * RW + kk) : 0.f;
+                    }
+                }
+                if (PFN) {
+                    const float cx = __fadd_rn(__fmul_rn((float)(x0 + o), vsx), vox);
+                    const float cy = __fadd_rn(__fmul_rn((float)y, vsy), voy);
+                    const float cz = __fadd_rn(__fmul_rn((float)z, vsz), voz);
+                    SlotSum sum;
+                    for (int s2 = 0; s2 < nk; ++s2) {
+                        const float4 v = __ldg(reinterpret_cast<const float4 *>(grow + (size_t)s_bperm[s2] * RWc));
+                        sum.add(s2, P4, v.x, v.y, v.z);
+                    }
+                    const float fn = (float)nk;
+                    const float mx = __fdiv_rn(sum.sx(), fn), my = __fdiv_rn(sum.sy(), fn), mz = __fdiv_rn(sum.sz(), fn);
+                    int v0 = (nk < Pmax) ? __float_as_int(s_bn[4 * C + lane]) : 0;
+                    int v1 = (nk < Pmax) ? __float_as_int(s_bn[4 * C + lane + 32]) : 0;
+                    for (int s2 = 0; s2 < nk; ++s2) {
+                        const float4 *r4 = reinterpret_cast<const float4 *>(grow + (size_t)s_bperm[s2] * RWc);
+                        float row[RWc];
+#pragma unroll
+                        for (int v = 0; v < RWc / 4; ++v) {
+                            const float4 t4 = __ldg(r4 + v);
+                            row[4 * v] = t4.x; row[4 * v + 1] = t4.y; row[4 * v + 2] = t4.z; row[4 * v + 3] = t4.w;
+                        }
+                        float feat[CIN];
+                        {
+                            int kf = 0;
+#pragma unroll
+                            for (int qq = ABS ? 0 : 3; qq < F; ++qq) feat[kf++] = row[qq];
+                            feat[kf++] = __fsub_rn(row[0], mx); feat[kf++] = __fsub_rn(row[1], my); feat[kf++] = __fsub_rn(row[2], mz);
+                            feat[kf++] = __fsub_rn(row[0], cx); feat[kf++] = __fsub_rn(row[1], cy); feat[kf++] = __fsub_rn(row[2], cz);
+                            if (DIST) feat[kf++] = __fsqrt_rn(fmaf(row[2], row[2], fmaf(row[1], row[1], __fmul_rn(row[0], row[0]))));
+                        }
+                        float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+                        for (int kk = 0; kk < CIN; ++kk) {
+                            a0 = fmaf(feat[kk], s_W[kk * C + lane], a0);
+                            a1 = fmaf(feat[kk], s_W[kk * C + lane + 32], a1);
+                        }
+                        float y0, y1;
+                        if (BN) {
+                            y0 = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(a0, s_bn[lane]), s_bn[C + lane]), s_bn[2 * C + lane]), s_bn[3 * C + lane]);
+                            y1 = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(a1, s_bn[lane + 32]), s_bn[C + lane + 32]), s_bn[2 * C + lane + 32]), s_bn[3 * C + lane + 32]);
+                        } else {
+                            y0 = __fadd_rn(a0, s_bn[3 * C + lane]); y1 = __fadd_rn(a1, s_bn[3 * C + lane + 32]);
+                        }
+                        v0 = max(v0, __float_as_int(y0)); v1 = max(v1, __float_as_int(y1));
+                    }
+                    if (p.feats) { p.feats[(size_t)f_o * C + lane] = __int_as_float(v0); p.feats[(size_t)f_o * C + lane + 32] = __int_as_float(v1); }
+                    if (canvas_on) { tile[swz128(lane, o)] = __int_as_float(v0); tile[swz128(lane + 32, o)] = __int_as_float(v1); }
+                }
+                __syncwarp();
+            }
+            // ---- optional contract output for the staged pillars: padded voxels [M, P, F], coalesced ----
+            if (p.voxels) {
+                unsigned todo = bal_st;
+                while (todo) {
+                    const int o = __ffs(todo) - 1;
+                    todo &= todo - 1;
+                    const int cnt_o = __shfl_sync(FULL, c.cnt, o), off_o = __shfl_sync(FULL, c.off, o), f_o = __shfl_sync(FULL, f, o);
+                    const int nk = min(cnt_o, Pmax);
+                    float *vo = p.voxels + (size_t)f_o * Pmax * Fr;
+                    const float *srow = stg + (size_t)off_o * RW;
+                    for (int t = lane; t < Pmax * Fr; t += 32) {
+                        const int s2 = t / Fr, kk = t - s2 * Fr;
+                        vo[t] = (s2 < nk) ? srow[((cnt_o == 1) ? 0 : (int)s_perm[off_o + s2]) * RW + kk] : 0.f;
+                    }
+                }
+            }
+            // ---- the tile goes out in one piece ----
+            if (canvas_on) {
+                dirty = bal_occ;
+                if (TMA) {
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) { tma_store_3d(&tmap, tile, x0, zy, b * C); tma_commit(); }
+                    store_pending = true;
+                } else {
+                    __syncwarp();
+                    if (x0 + lane < p.nx)
+                        for (int ch = 0; ch < C; ++ch) p.canvas[(((size_t)b * C + ch) * p.ny + y) * p.nx + x0 + lane] = tile[swz128(ch, lane)];
+                }
+            }
+            __syncwarp();
         }
+        st_cur = st_nxt;
+        cur = nxt; nxt = nxt2; step.advance(nxt2);
     }
     cp_async_wait<0>();
-    if (canvas_on && TMA && tid == 0) tma_wait_read<0>();
+    if (canvas_on && TMA && lane == 0) tma_wait_read<0>();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -563,12 +750,12 @@ static EncodeTiledFn encode_tiled_fn() {
 }
 
 // canvas [B*C, ny, nx] fp32, box = 32 cells x 1 row x C channels, 128-byte swizzle
-int make_canvas_map(CUtensorMap *map, float *canvas, int B, int C, int ny, int nx) {
+int make_canvas_map(CUtensorMap *map, float *canvas, int B, int C, int ny, int nx, int box_c) {
     EncodeTiledFn enc = encode_tiled_fn();
     if (!enc) return HGSF_ERR_DRIVER;
     const cuuint64_t gdim[3] = {(cuuint64_t)nx, (cuuint64_t)ny, (cuuint64_t)B * C};
     const cuuint64_t gstr[2] = {(cuuint64_t)nx * 4, (cuuint64_t)nx * ny * 4};
-    const cuuint32_t box[3] = {32, 1, (cuuint32_t)C};
+    const cuuint32_t box[3] = {32, 1, (cuuint32_t)box_c};
     const cuuint32_t estr[3] = {1, 1, 1};
     const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, canvas, gdim, gstr, box, estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -585,36 +772,41 @@ int sm_count() {
     return n;
 }
 
-constexpr int EMIT_WARPS = 4;
-
 template <int F, bool ABS, bool DIST, int C, bool PFN>
 static int launch_emit_t(const PathParams &p, cudaStream_t stream) {
     const bool canvas_on = PFN && p.canvas;
     const bool tma = canvas_on && (p.nx % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.canvas) & 15) == 0) && C <= 256;
-    CUtensorMap map;
+    CUtensorMap map, zmap;
     memset(&map, 0, sizeof(map));
+    memset(&zmap, 0, sizeof(zmap));
     if (tma) {
-        const int st = make_canvas_map(&map, p.canvas, p.B, C, p.ny, p.nx);
+        int st = make_canvas_map(&map, p.canvas, p.B, C, p.ny, p.nx, C);
+        if (st == HGSF_OK) st = make_canvas_map(&zmap, p.canvas, p.B, C, p.ny, p.nx, C / 4);
         if (st != HGSF_OK) return st;
     }
-    const size_t smem = sizeof(float) * (3 * C * 32 + 2 * STAGE_ROWS * (size_t)p.RW) + sizeof(int) * 2 * (size_t)(p.B + 1);
-    const long long n_tiles = (long long)p.B * p.nz * p.ny * ((p.nx + 31) / 32);
+    const int cin = PFN ? p.Cin : 1;
+    const size_t smem = sizeof(float) * (EMIT_WARPS * C * 32 + (C / 4) * 32 + (size_t)cin * C + 5 * C +
+                                         EMIT_WARPS * 2 * STAGE_W * (size_t)p.RW + EMIT_WARPS * 64 * 4) +
+                        sizeof(int) * 2 * (size_t)(p.B + 1);
+    const long long n_tiles = ((long long)p.B * p.nz * p.ny * ((p.nx + 31) / 32) + EMIT_WARPS - 1) / EMIT_WARPS;   // CTA-loads of tiles
     if (n_tiles == 0) return HGSF_OK;
+    const bool bn = p.bn_w != nullptr;
     auto go = [&](auto kern) -> int {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
         int per_sm = 1;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, EMIT_WARPS * 32, smem);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, EMIT_THREADS, smem);
         if (e != cudaSuccess) return (int)e;
         if (per_sm < 1) per_sm = 1;
         const long long grid = std::min<long long>(n_tiles, (long long)sm_count() * per_sm);
-        kern<<<(unsigned)grid, EMIT_WARPS * 32, smem, stream>>>(map, p);
+        kern<<<(unsigned)grid, EMIT_THREADS, smem, stream>>>(map, zmap, p);
         return (int)cudaGetLastError();
     };
     if constexpr (PFN) {
-        if (tma) return go(k_emit<F, ABS, DIST, C, EMIT_WARPS, PFN, true>);
+        if (tma) return bn ? go(k_emit<F, ABS, DIST, true, C, true, true>) : go(k_emit<F, ABS, DIST, false, C, true, true>);
+        return bn ? go(k_emit<F, ABS, DIST, true, C, true, false>) : go(k_emit<F, ABS, DIST, false, C, true, false>);
     }
-    return go(k_emit<F, ABS, DIST, C, EMIT_WARPS, PFN, false>);
+    return go(k_emit<F, ABS, DIST, true, C, false, false>);
 }
 
 template <int C>
@@ -628,7 +820,7 @@ static int launch_emit_pfn(const PathParams &p, bool abs_xyz, bool dist, cudaStr
 }
 
 static int launch_emit_plain(const PathParams &p, cudaStream_t s) {
-    return launch_emit_t<4, true, false, 32, false>(p, s);   // F / RW are read from the params when PFN is off
+    return launch_emit_t<4, true, false, 64, false>(p, s);   // F / RW are read from the params when PFN is off
 }
 
 int launch_pillar_path(const PathParams &p, bool with_pfn, bool abs_xyz, bool dist, size_t zero_bytes, void *zero_base,
