@@ -1,0 +1,209 @@
+"""Drop-in modules for OpenPCDet / HGSFusion's registries, backed by libhgsfusion_b200.so.
+
+They keep the reference's plugin API (constructor keywords, `forward(batch_dict) -> batch_dict`,
+`get_output_feature_dim`, `num_bev_features`) and parameter names, so reference checkpoints load:
+
+  PillarVFE            <-> pcdet/models/backbones_3d/vfe/pillar_vfe.py:52-123   (VFE.NAME: PillarVFE)
+  PointPillarScatter   <-> pcdet/models/backbones_2d/map_to_bev/pointpillar_scatter.py:5-41
+  FusedPillarVFE       points -> pillars -> PillarVFE -> canvas in one native call; used with
+                       DATA_PROCESSOR `transform_points_to_voxels_placeholder`
+                       (pcdet/datasets/processor/data_processor.py:107-115) so that no CPU voxelizer runs
+  PillarScatterPassthrough   MAP_TO_BEV plugin for FusedPillarVFE: spatial_features already exists
+
+Inference (eval mode) only in this round: the backward pass is SURVEY.md §8(f) rank 1.
+There is no PyTorch fallback: without the CUDA library these modules raise at construction.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .ops import PfnWeights, PillarPath
+
+
+class _PFNLayerParams(nn.Module):
+    """Holds the parameters of the reference's PFNLayer under the same names (pillar_vfe.py:8-27):
+    `linear.weight` (+ `linear.bias` when USE_NORM is False) and `norm.*` (BatchNorm1d eps 1e-3, momentum 0.01)."""
+
+    def __init__(self, in_channels, out_channels, use_norm=True, last_layer=True):
+        super().__init__()
+        self.last_vfe = last_layer
+        self.use_norm = use_norm
+        if not self.last_vfe:
+            out_channels = out_channels // 2
+        if self.use_norm:
+            self.linear = nn.Linear(in_channels, out_channels, bias=False)
+            self.norm = nn.BatchNorm1d(out_channels, eps=1e-3, momentum=0.01)
+        else:
+            self.linear = nn.Linear(in_channels, out_channels, bias=True)
+        self.part = 50000
+
+    def weights(self, use_absolute_xyz: bool, with_distance: bool) -> PfnWeights:
+        if self.use_norm:
+            return PfnWeights(weight=self.linear.weight.detach(), bn_weight=self.norm.weight.detach(),
+                              bn_bias=self.norm.bias.detach(), running_mean=self.norm.running_mean,
+                              running_var=self.norm.running_var, eps=self.norm.eps,
+                              use_absolute_xyz=use_absolute_xyz, with_distance=with_distance)
+        return PfnWeights(weight=self.linear.weight.detach(), bias=self.linear.bias.detach(),
+                          use_absolute_xyz=use_absolute_xyz, with_distance=with_distance)
+
+
+class _VFEBase(nn.Module):
+    def __init__(self, model_cfg, num_point_features, voxel_size, point_cloud_range, **kwargs):
+        super().__init__()
+        _lib.load()                                    # fail loudly here if the CUDA library is missing
+        self.model_cfg = model_cfg
+        self.use_norm = self.model_cfg.USE_NORM
+        self.with_distance = self.model_cfg.WITH_DISTANCE
+        self.use_absolute_xyz = self.model_cfg.USE_ABSLOTE_XYZ      # (sic) the reference's key, pillar_vfe.py:58
+        self.num_raw_features = int(num_point_features)
+        num_point_features += 6 if self.use_absolute_xyz else 3
+        if self.with_distance:
+            num_point_features += 1
+        self.num_filters = list(self.model_cfg.NUM_FILTERS)
+        assert len(self.num_filters) > 0
+        if len(self.num_filters) != 1:
+            raise NotImplementedError("hgsfusion_b200 implements the single-layer PFN every HGSFusion/PointPillars "
+                                      "config uses (NUM_FILTERS: [64]); stacked PFN layers are not built yet")
+        self.pfn_layers = nn.ModuleList([_PFNLayerParams(num_point_features, self.num_filters[0], self.use_norm, True)])
+        self.voxel_size = [float(v) for v in voxel_size]
+        self.point_cloud_range = point_cloud_range
+        self.voxel_x, self.voxel_y, self.voxel_z = self.voxel_size
+        # kept for parity with the reference attributes (pillar_vfe.py:79-81); the native geometry struct
+        # evaluates the same expressions (geometry.make_geometry)
+        self.x_offset = self.voxel_x / 2 + point_cloud_range[0]
+        self.y_offset = self.voxel_y / 2 + point_cloud_range[1]
+        self.z_offset = self.voxel_z / 2 + point_cloud_range[2]
+
+    def get_output_feature_dim(self):
+        return self.num_filters[-1]
+
+    def _check_mode(self):
+        if self.training and torch.is_grad_enabled():
+            raise NotImplementedError("hgsfusion_b200 modules are forward-only this round: call .eval() / no_grad()")
+
+    def _pfn(self) -> PfnWeights:
+        return self.pfn_layers[0].weights(self.use_absolute_xyz, self.with_distance)
+
+
+class PillarVFE(_VFEBase):
+    """batch_dict contract mode: voxels, voxel_num_points, voxel_coords in; pillar_features out."""
+
+    def __init__(self, model_cfg, num_point_features, voxel_size, point_cloud_range, grid_size=None, **kwargs):
+        super().__init__(model_cfg, num_point_features, voxel_size, point_cloud_range)
+        self.path = PillarPath(point_cloud_range, self.voxel_size, max_points_per_voxel=1, max_voxels=1,
+                               num_point_features=self.num_raw_features, grid_size=grid_size)
+
+    def forward(self, batch_dict, **kwargs):
+        self._check_mode()
+        voxels, num, coords = batch_dict['voxels'], batch_dict['voxel_num_points'], batch_dict['voxel_coords']
+        features = self.path.pillar_vfe(voxels, coords, num, self._pfn())
+        batch_dict['pillar_features'] = features.view(-1, 1, features.shape[-1]).squeeze()   # pillar_vfe.py:121
+        return batch_dict
+
+
+class PointPillarScatter(nn.Module):
+    """pillar_features + voxel_coords -> spatial_features [B, C, ny, nx]."""
+
+    def __init__(self, model_cfg, grid_size, point_cloud_range=None, voxel_size=None, **kwargs):
+        super().__init__()
+        _lib.load()
+        self.model_cfg = model_cfg
+        self.num_bev_features = self.model_cfg.NUM_BEV_FEATURES
+        self.nx, self.ny, self.nz = (int(v) for v in grid_size)
+        assert self.nz == 1
+        # the scatter needs only the grid; range / voxel size are placeholders for the geometry struct
+        self.path = PillarPath(np.zeros(6, np.float32) if point_cloud_range is None else point_cloud_range,
+                               [1.0, 1.0, 1.0] if voxel_size is None else voxel_size, 1, 1, 4,
+                               grid_size=[self.nx, self.ny, self.nz])
+        self.batch_size_from_coords = True     # the reference's rule (pointpillar_scatter.py:21); one host sync
+
+    def forward(self, batch_dict, **kwargs):
+        pillar_features, coords = batch_dict['pillar_features'], batch_dict['voxel_coords']
+        if self.batch_size_from_coords or 'batch_size' not in batch_dict:
+            batch_size = coords[:, 0].max().int().item() + 1
+        else:
+            batch_size = int(batch_dict['batch_size'])
+        if pillar_features.dim() == 1:                 # the reference's squeeze() dropped M == 1
+            pillar_features = pillar_features.view(1, -1)
+        batch_dict['spatial_features'] = self.path.pointpillar_scatter(pillar_features, coords, batch_size)
+        return batch_dict
+
+
+class FusedPillarVFE(_VFEBase):
+    """VFE plugin that starts from batch_dict['points'] ([sum N, 1+F], column 0 = batch index,
+    pcdet/datasets/dataset.py:237-244) and produces everything the detector reads downstream:
+    voxel_coords, voxel_num_points, pillar_features and spatial_features (and voxels on request).
+
+    model_cfg keys beyond PillarVFE's: MAX_POINTS_PER_VOXEL, MAX_NUMBER_OF_VOXELS (int or {'train','test'}),
+    optional RETURN_VOXELS (default False), TRIM (default True: slice outputs to [M, ...] like the
+    reference, one host sync; False keeps capacity-sized tensors and batch_dict['num_pillars'] on device)."""
+
+    def __init__(self, model_cfg, num_point_features, voxel_size, point_cloud_range, grid_size=None, **kwargs):
+        super().__init__(model_cfg, num_point_features, voxel_size, point_cloud_range)
+        mv = self.model_cfg.MAX_NUMBER_OF_VOXELS
+        self._max_voxels = mv if isinstance(mv, dict) else {'train': int(mv), 'test': int(mv)}
+        self.max_points = int(self.model_cfg.MAX_POINTS_PER_VOXEL)
+        self.return_voxels = bool(getattr(self.model_cfg, 'RETURN_VOXELS', False))
+        self.trim = bool(getattr(self.model_cfg, 'TRIM', True))
+        self._grid = grid_size
+        self._paths = {}
+
+    def _path(self) -> PillarPath:
+        mode = 'train' if self.training else 'test'
+        if mode not in self._paths:
+            self._paths[mode] = PillarPath(self.point_cloud_range, self.voxel_size, self.max_points,
+                                           int(self._max_voxels[mode]), self.num_raw_features, grid_size=self._grid)
+        return self._paths[mode]
+
+    def forward(self, batch_dict, **kwargs):
+        self._check_mode()
+        points = batch_dict['points']
+        batch_size = int(batch_dict['batch_size'])
+        res = self._path().points_to_bev(points, batch_size, self._pfn(), xyz_col=1, batch_col=0,
+                                         want_voxels=self.return_voxels)
+        if self.trim:
+            out = res.trim()
+            out.pop('num_pillars')
+        else:
+            out = dict(voxel_coords=res.voxel_coords, voxel_num_points=res.voxel_num_points,
+                       pillar_features=res.pillar_features, spatial_features=res.spatial_features,
+                       num_pillars=res.num_pillars)
+            if res.voxels is not None:
+                out['voxels'] = res.voxels
+        batch_dict.update(out)
+        return batch_dict
+
+
+class PillarScatterPassthrough(nn.Module):
+    """MAP_TO_BEV plugin to pair with FusedPillarVFE: the canvas is already in batch_dict."""
+
+    def __init__(self, model_cfg, grid_size, **kwargs):
+        super().__init__()
+        self.model_cfg = model_cfg
+        self.num_bev_features = self.model_cfg.NUM_BEV_FEATURES
+        self.nx, self.ny, self.nz = (int(v) for v in grid_size)
+        assert self.nz == 1
+
+    def forward(self, batch_dict, **kwargs):
+        if 'spatial_features' not in batch_dict:
+            raise KeyError("PillarScatterPassthrough expects FusedPillarVFE upstream (no 'spatial_features')")
+        return batch_dict
+
+
+def register(vfe_all: dict | None = None, map_to_bev_all: dict | None = None, override: bool = False):
+    """Adds the modules to the reference's name -> class registries
+    (pcdet/models/backbones_3d/vfe/__init__.py:13-27, pcdet/models/backbones_2d/map_to_bev/__init__.py:7-14).
+    With override=True the stock 'PillarVFE' / 'PointPillarScatter' names resolve to the native modules."""
+    if vfe_all is not None:
+        vfe_all['FusedPillarVFE'] = FusedPillarVFE
+        vfe_all['PillarVFEB200'] = PillarVFE
+        if override:
+            vfe_all['PillarVFE'] = PillarVFE
+    if map_to_bev_all is not None:
+        map_to_bev_all['PillarScatterPassthrough'] = PillarScatterPassthrough
+        map_to_bev_all['PointPillarScatterB200'] = PointPillarScatter
+        if override:
+            map_to_bev_all['PointPillarScatter'] = PointPillarScatter

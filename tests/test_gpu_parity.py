@@ -8,7 +8,7 @@ import torch
 from hgsfusion_b200 import synthetic
 from hgsfusion_b200.ops import PillarPath
 from oracle import oracle
-from util import bits_equal, device_pfn, geom_for, max_rel_err, oracle_pfn
+from util import bits_equal, device_pfn, geom_for, features_close, oracle_pfn
 
 pytestmark = pytest.mark.gpu
 RTOL = 1e-5   # BASELINE.json north_star: "within 1e-5 relative for fp32 features"
@@ -41,10 +41,10 @@ def check(ref, got, res):
     assert np.array_equal(got["voxel_num_points"].cpu().numpy(), ref["voxel_num_points"])
     assert bits_equal(got["voxels"].cpu().numpy(), ref["voxels"])
     feats = got["pillar_features"].cpu().numpy()
-    assert max_rel_err(feats, ref["pillar_features"]) <= RTOL
+    assert features_close(feats, ref["pillar_features"], RTOL)
     canvas = got["spatial_features"].cpu().numpy()
     assert canvas.shape == ref["spatial_features"].shape
-    assert max_rel_err(canvas, ref["spatial_features"]) <= RTOL
+    assert features_close(canvas, ref["spatial_features"], RTOL)
     # the canvas is an exact copy of pillar_features at the pillar cells and exactly zero elsewhere
     co = ref["voxel_coords"]
     assert bits_equal(canvas[co[:, 0], :, co[:, 2], co[:, 3]], feats)

@@ -31,12 +31,17 @@ def bits_equal(a: np.ndarray, b: np.ndarray) -> bool:
     return a.shape == b.shape and np.array_equal(a.view(np.uint32), b.view(np.uint32))
 
 
-def max_rel_err(got: np.ndarray, ref: np.ndarray) -> float:
-    """max |got-ref| / max(|ref|, 1e-5*max|ref|): the 1e-5 relative bar of BASELINE.json with the
-    atol = 1e-5*max|ref| floor SURVEY.md §7 allows for values near zero."""
+def features_close(got: np.ndarray, ref: np.ndarray, rtol: float = 1e-5, atol_frac: float = 1e-6) -> bool:
+    """|got - ref| <= rtol*|ref| + atol with atol = atol_frac * max|ref|.
+
+    rtol is BASELINE.json's bar ("within 1e-5 relative for fp32 features").  The absolute term only
+    matters for outputs that are themselves the result of cancellation to ~0 in the BatchNorm (a value
+    of 1e-4 produced from O(1) terms): there the reference's own MKL-sqrt invstd, 1 ulp off the IEEE
+    value, already moves the result by ~1e-8.  SURVEY.md section 7 allows atol = 1e-5*max|ref|; this uses a
+    ten times tighter 1e-6."""
     got = got.astype(np.float64)
     ref = ref.astype(np.float64)
     if ref.size == 0:
-        return 0.0
-    floor = 1e-5 * max(np.abs(ref).max(), 1e-30)
-    return float((np.abs(got - ref) / np.maximum(np.abs(ref), floor)).max())
+        return got.size == 0
+    atol = atol_frac * np.abs(ref).max()
+    return bool((np.abs(got - ref) <= rtol * np.abs(ref) + atol).all())
