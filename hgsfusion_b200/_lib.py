@@ -15,7 +15,7 @@ OK, ERR_INVALID_ARG, ERR_UNSUPPORTED, ERR_WORKSPACE, ERR_DRIVER = 0, -1, -2, -3,
 
 EXPORTS = ["hgsf_abi_version", "hgsf_status_string", "hgsf_pillar_capacity", "hgsf_workspace_size",
            "hgsf_pillarize", "hgsf_points_to_bev", "hgsf_pillar_vfe", "hgsf_scatter_workspace_size",
-           "hgsf_pointpillar_scatter", "hgsf_last_launch_count"]
+           "hgsf_pointpillar_scatter", "hgsf_last_launch_count", "hgsf_emit_timing_begin", "hgsf_emit_timing_collect"]
 
 
 class Geometry(C.Structure):
@@ -75,6 +75,8 @@ def load():
     lib.hgsf_scatter_workspace_size.argtypes = [C.POINTER(Geometry), C.c_int32, C.POINTER(C.c_size_t)]
     lib.hgsf_pointpillar_scatter.argtypes = [C.POINTER(Geometry), C.c_void_p, C.c_void_p, C.c_int32, C.c_int64,
                                              C.c_int32, C.c_int32, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
+    lib.hgsf_emit_timing_begin.argtypes = [C.c_int]
+    lib.hgsf_emit_timing_collect.argtypes = [C.POINTER(C.c_float), C.c_int]
     for name in EXPORTS:
         getattr(lib, name)
     if lib.hgsf_abi_version() != 1:

@@ -26,6 +26,10 @@ const char *hgsf_status_string(int status) {
 
 int hgsf_last_launch_count(void) { return g_last_launches; }
 
+int hgsf_emit_timing_begin(int capacity) { return emit_timing_begin(capacity); }
+
+int hgsf_emit_timing_collect(float *ms, int n) { return emit_timing_collect(ms, n); }
+
 static bool geom_ok(const hgsf_geometry *g) {
     if (!g) return false;
     for (int j = 0; j < 3; ++j)

@@ -187,9 +187,8 @@ __global__ void __launch_bounds__(NWARPS * 32) k_scatter_canvas(const __grid_con
 
 int launch_scatter(const ScatterParams &q, cudaStream_t stream, int *launches) {
     int nl = 0;
-    cudaError_t e = cudaMemsetAsync(q.map, 0, sizeof(unsigned) * (size_t)q.B * q.plane, stream);
+    cudaError_t e = cudaMemsetAsync(q.map, 0, sizeof(unsigned) * (size_t)q.B * q.plane, stream);   // not counted as a kernel
     if (e != cudaSuccess) return (int)e;
-    ++nl;
     if (q.M > 0) {
         k_scatter_map<<<(unsigned)((q.M + 255) / 256), 256, 0, stream>>>(q);
         if ((e = cudaGetLastError()) != cudaSuccess) return (int)e;

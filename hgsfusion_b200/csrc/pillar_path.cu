@@ -25,6 +25,7 @@
 
 #include <algorithm>
 #include <cstring>
+#include <vector>
 
 namespace hgsf {
 
@@ -823,12 +824,45 @@ static int launch_emit_plain(const PathParams &p, cudaStream_t s) {
     return launch_emit_t<4, true, false, 64, false>(p, s);   // F / RW are read from the params when PFN is off
 }
 
+// ---- optional per-launch timing of k_emit (bench.py's roofline leg) ---------------------------------
+// A ring of CUDA event pairs recorded on the launching stream around the k_emit launch.  Off by default.
+struct EmitTiming {
+    std::vector<cudaEvent_t> ev;   // 2 * capacity
+    int capacity = 0, count = 0;
+};
+static thread_local EmitTiming g_timing;
+
+int emit_timing_begin(int capacity) {
+    for (cudaEvent_t e : g_timing.ev) cudaEventDestroy(e);
+    g_timing.ev.clear();
+    g_timing.capacity = g_timing.count = 0;
+    if (capacity <= 0) return HGSF_OK;
+    g_timing.ev.resize(2 * (size_t)capacity);
+    for (auto &e : g_timing.ev) {
+        const cudaError_t st = cudaEventCreate(&e);
+        if (st != cudaSuccess) return (int)st;
+    }
+    g_timing.capacity = capacity;
+    return HGSF_OK;
+}
+
+int emit_timing_collect(float *ms, int n) {
+    const int have = g_timing.count < g_timing.capacity ? g_timing.count : g_timing.capacity;
+    int out = 0;
+    for (int i = 0; i < have && out < n; ++i, ++out) {
+        cudaError_t st = cudaEventSynchronize(g_timing.ev[2 * i + 1]);
+        if (st == cudaSuccess) st = cudaEventElapsedTime(ms + out, g_timing.ev[2 * i], g_timing.ev[2 * i + 1]);
+        if (st != cudaSuccess) return -(int)st;
+    }
+    g_timing.count = 0;
+    return out;
+}
+
 int launch_pillar_path(const PathParams &p, bool with_pfn, bool abs_xyz, bool dist, size_t zero_bytes, void *zero_base,
                        cudaStream_t stream, int *launches) {
-    int nl = 0;
+    int nl = 0;   // kernels only; the workspace memset below is not counted
     cudaError_t e = cudaMemsetAsync(zero_base, 0, zero_bytes, stream);
     if (e != cudaSuccess) return (int)e;
-    ++nl;
     if (p.n > 0) {
         const unsigned g = (unsigned)((p.n + 255) / 256);
         k_count<<<g, 256, 0, stream>>>(p);
@@ -839,6 +873,8 @@ int launch_pillar_path(const PathParams &p, bool with_pfn, bool abs_xyz, bool di
         if ((e = cudaGetLastError()) != cudaSuccess) return (int)e;
         nl += 3;
     }
+    const bool timed = g_timing.capacity > 0 && g_timing.count < g_timing.capacity;
+    if (timed) cudaEventRecord(g_timing.ev[2 * g_timing.count], stream);
     int st;
     if (with_pfn) {
         if (p.C == 64) st = launch_emit_pfn<64>(p, abs_xyz, dist, stream);
@@ -847,6 +883,7 @@ int launch_pillar_path(const PathParams &p, bool with_pfn, bool abs_xyz, bool di
         st = launch_emit_plain(p, stream);
     }
     if (st != HGSF_OK) return st;
+    if (timed) cudaEventRecord(g_timing.ev[2 * g_timing.count++ + 1], stream);
     ++nl;
     if (launches) *launches = nl;
     return HGSF_OK;

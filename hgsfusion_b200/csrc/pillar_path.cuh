@@ -66,4 +66,7 @@ inline WorkspaceLayout workspace_layout(int64_t n, int B, int64_t cells, int F) 
 int launch_pillar_path(const PathParams &p, bool with_pfn, bool abs_xyz, bool dist, size_t zero_bytes, void *zero_base,
                        cudaStream_t stream, int *launches);
 
+int emit_timing_begin(int capacity);
+int emit_timing_collect(float *ms, int n);
+
 }  // namespace hgsf
