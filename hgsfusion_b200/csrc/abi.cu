@@ -66,6 +66,7 @@ static int run_path(const hgsf_geometry *g, const hgsf_points *pt, const hgsf_pf
     if (P > 32) return HGSF_ERR_UNSUPPORTED;           // one warp orders a pillar: at most 32 slots
     const int64_t cells = (int64_t)g->grid[0] * g->grid[1] * g->grid[2];
     if (cells * pt->batch_size > INT_MAX || pt->n > INT_MAX) return HGSF_ERR_UNSUPPORTED;
+    if (pt->batch_size > 32767 || g->grid[0] > 65535 || g->grid[1] > 65535 || g->grid[2] > 65535) return HGSF_ERR_UNSUPPORTED;
     if (out->pillar_capacity < hgsf_pillar_capacity(g, pt->n, pt->batch_size, max_voxels)) return HGSF_ERR_INVALID_ARG;
     const WorkspaceLayout w = workspace_layout(pt->n, pt->batch_size, cells, pt->num_features);
     if (ws_bytes < w.total || (reinterpret_cast<uintptr_t>(ws) & 255)) return HGSF_ERR_WORKSPACE;
@@ -86,6 +87,7 @@ static int run_path(const hgsf_geometry *g, const hgsf_points *pt, const hgsf_pf
     p.key = reinterpret_cast<int32_t *>(base + w.off_key);
     p.arrival = reinterpret_cast<uint32_t *>(base + w.off_arrival);
     p.sorted_rows = reinterpret_cast<float *>(base + w.off_sorted_rows);
+    p.prec = reinterpret_cast<int4 *>(base + w.off_prec);
     p.RW = w.RW;
     p.coords = out->voxel_coords; p.num = out->voxel_num_points; p.num_pillars = out->num_pillars;
     p.voxels = out->voxels;
@@ -99,6 +101,7 @@ static int run_path(const hgsf_geometry *g, const hgsf_points *pt, const hgsf_pf
         const int cin = (abs_xyz ? p.F : p.F - 3) + 6 + (dist ? 1 : 0);
         if (cin != pfn->in_channels) return HGSF_ERR_INVALID_ARG;
         if (out->spatial_features && g->grid[2] != 1) return HGSF_ERR_INVALID_ARG;   // PointPillarScatter asserts nz == 1
+        if (!out->pillar_features) return HGSF_ERR_INVALID_ARG;                       // the canvas is built from the pillar rows
         p.W = pfn->weight; p.bias = pfn->bias; p.bn_w = pfn->bn_weight; p.bn_b = pfn->bn_bias;
         p.bn_m = pfn->bn_mean; p.bn_v = pfn->bn_var; p.eps = pfn->bn_eps;
         p.Cin = cin; p.C = pfn->out_channels;

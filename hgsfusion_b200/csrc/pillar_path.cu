@@ -1,17 +1,19 @@
 // pillar_path.cu -- points -> pillars (first-seen order) -> decorate + PFN + max -> BEV canvas.
 //
-// Four kernels on one stream, no host sync, no allocation:
+// Five kernels on one stream, no host sync, no allocation:
 //   k_count  (1 thread / point)  cell key; per cell: min point index + count (warp-aggregated atomics
 //                                into the direct-address cell table)
 //   k_scan   (1024 points / CTA) single-pass decoupled look-back scan over points: a point that is the
 //                                first of its cell gets (raw pillar id, CSR start) = exclusive prefix of
-//                                (first-flags, cell counts) -> pillar ids come out in first-seen order
+//                                (first-flags, cell counts) -> pillar ids come out in first-seen order;
+//                                it also writes the pillar's record {start, cnt, b, z, y, x}
 //   k_fill   (1 thread / point)  copies each point's features (+ its index) to its pillar's CSR segment
-//   k_emit   (persistent CTAs, one 32-cell x C-channel canvas tile at a time) orders each pillar's
-//                                points by index, keeps the first P, decorates, runs the PFN with the
-//                                weights in registers, takes the max, writes pillar_features /
-//                                voxel_coords / voxel_num_points rows and the canvas tile (zeros
-//                                included) with one TMA tensor store per tile.
+//   k_pfn    (pillar major)      a warp takes 32 consecutive pillars (their CSR rows are contiguous): orders each
+//                                pillar's points by index, keeps the first P, decorates, runs the PFN with the
+//                                weights in registers, takes the max; writes voxel_coords / voxel_num_points /
+//                                pillar_features rows (and the padded voxels tensor on request)
+//   k_canvas (tile major)        warps walk the canvas in tiles of 32 cells x C channels: cell table -> pillar row
+//                                -> tile in shared memory -> one TMA tensor store per tile, zeros included
 //
 // What it reproduces (file:line under the reference):
 //   spconv Point2VoxelCPU3d.point_to_voxel as called by pcdet/datasets/processor/data_processor.py:55
@@ -181,6 +183,13 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan(const PathParams p) {
             CellEntry *e = p.table + keys[j];
             e->tag = pillars + 1u;     // raw pillar id + 1 (disjoint from the 0xFFFFFFFF-i range other threads compare against)
             e->start = points;
+            // the pillar's record, in first-seen order (one thread per pillar pays the divisions)
+            const int key = keys[j];
+            const int b = key / p.cells, rem = key - b * p.cells;
+            const int plane = p.ny * p.nx;
+            const int z = rem / plane, rem2 = rem - z * plane;
+            const int y = rem2 / p.nx, x = rem2 - y * p.nx;
+            p.prec[pillars] = make_int4((int)points, (int)cnt[j], (b << 16) | z, (y << 16) | x);
         }
         run += pack2(flag[j], cnt[j]);
     }
@@ -281,92 +290,38 @@ struct TileStep {
     }
 };
 
-// ---- k_emit -------------------------------------------------------------------------------------
-// Every WARP is an autonomous worker: it walks its own sequence of canvas tiles (a tile = 32 cells of
-// one BEV row x all C channels = C rows of 128 B) with its own tile buffer, staging buffers and
-// software pipeline; there is no CTA barrier inside the loop, so a warp that waits (gather, TMA
-// read-out) never holds up another.  The CTA only shares the PFN weights (k-major in shared memory,
-// read as broadcast float4s) and a small zero tile.
-//
-// Lane l owns cell l of the tile for the bookkeeping (table entry, ordering, mean: all in registers).
-// The arithmetic is cut into UNITS of (pillar, 4 output channels) dealt round-robin to the 32 lanes, so
-// lanes stay busy whatever the number of pillars in the tile.
-//
-// Pipeline of one warp, iteration i:  prefetch table entries of tile i+2  |  cp.async gather of tile
-// i+1's point rows  |  order + mean + units of tile i  |  one TMA tensor store of tile i.
-constexpr int EMIT_WARPS = 4;
-constexpr int EMIT_THREADS = EMIT_WARPS * 32;
-constexpr int STAGE_W = 64;           // staged point rows per tile (a typical tile holds ~10; the rest is read from L2)
+// ---- k_pfn --------------------------------------------------------------------------------------
+// Pillar major.  A warp takes a chunk of 32 consecutive pillars (raw first-seen ids m0 .. m0+31); because the CSR
+// start is the prefix sum over that same order, the chunk's point rows are one contiguous span of sorted_rows and
+// stream through L1.  Lane j OWNS pillar m0+j for the bookkeeping (ordering by point index, first P kept, mean in
+// torch's summation order, voxel_coords / voxel_num_points).  The arithmetic is cut into UNITS of (pillar, 4 output
+// channels): lane l always computes channels 4*(l&15) .. +3 -- so its 13/14 Linear weight float4s and BatchNorm
+// constants stay in REGISTERS for the whole kernel -- for pillars (l>>4) + 2*it, it = 0..15.  CUDA-core FMA: a
+// 13x64 contraction is far below a tensor-core tile.
+constexpr int PFN_WARPS = 4;
+constexpr int PFN_THREADS = PFN_WARPS * 32;
+constexpr int SMALL_CNT = 6;          // up to this many arrivals the owning lane ranks them itself
 
-__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)
-                 : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-// what a lane knows about its cell of a tile
-struct CellState {
-    int m, cnt, start, off;     // raw pillar id, arrivals, CSR start, staging offset
-    bool occ, staged;           // holds a kept pillar / its rows are (being) staged
-};
-
-template <int F, bool ABS, bool DIST, bool BN, int C, bool PFN, bool TMA>
-__global__ void __launch_bounds__(EMIT_THREADS, 4)
-k_emit(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap zmap, const PathParams p) {
+template <int F, bool ABS, bool DIST, bool BN, bool PFN>
+__global__ void __launch_bounds__(PFN_THREADS, 4) k_pfn(const PathParams p) {
+    constexpr int C = 64;
     constexpr int CIN = PFN ? ((ABS ? F : F - 3) + 6 + (DIST ? 1 : 0)) : 1;
     constexpr int RWc = (F + 1 + 3) / 4 * 4;   // F features + the point index, padded to float4
-    constexpr int TILE = C * 32;               // floats per tile
-    constexpr int ZC = C / 4;                  // channels of the shared zero tile (an empty tile = 4 stores of it)
-    constexpr int NT = EMIT_THREADS;
-    static_assert(C == 64, "units are 4 of 64 channels; the fallback path maps 2 channels per lane");
-    const int Fr = PFN ? F : p.F, RW = PFN ? RWc : p.RW, NV = RW >> 2;
+    const int Fr = PFN ? F : p.F, RW = PFN ? RWc : p.RW;
 
-    extern __shared__ __align__(1024) uint8_t smem_raw[];
-    float *tiles = reinterpret_cast<float *>(smem_raw);                    // [EMIT_WARPS][TILE]
-    float *zerobuf = tiles + EMIT_WARPS * TILE;                            // [ZC*32]
-    float *s_W = zerobuf + ZC * 32;                                        // [CIN][C]  k-major Linear weight
-    float *s_bn = s_W + CIN * C;                                           // [5][C]    mean, invstd, gamma, beta(bias), pad value
-    float *stage_all = s_bn + 5 * C;                                       // [EMIT_WARPS][2][STAGE_W * RW]
-    float4 *rec_all = reinterpret_cast<float4 *>(stage_all + EMIT_WARPS * 2 * STAGE_W * RW);   // [EMIT_WARPS][32][2]
-    int *s_R = reinterpret_cast<int *>(rec_all + EMIT_WARPS * 64);         // [B+1] raw pillar base per frame
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    int *s_R = reinterpret_cast<int *>(smem_raw);                          // [B+1] raw pillar base per frame
     int *s_K = s_R + (p.B + 1);                                            // [B+1] kept (final) pillar base per frame
-    __shared__ unsigned char s_perm_all[EMIT_WARPS][STAGE_W];              // per pillar: arrival position of its rank-th point
-    __shared__ int s_bperm_all[EMIT_WARPS][32];                            // warp-per-pillar path
+    __shared__ float4 s_rec_all[PFN_WARPS][32][2];                         // per pillar of the chunk: mean + bookkeeping
+    __shared__ unsigned char s_perm_all[PFN_WARPS][32][32];                // arrival position of the pillar's rank-th point
+    __shared__ int s_bperm_all[PFN_WARPS][32];                             // same for a pillar with > 32 arrivals
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const bool canvas_on = PFN && (p.canvas != nullptr);
-    float *tile = tiles + warp * TILE;
-    float *stage = stage_all + (size_t)warp * 2 * STAGE_W * RW;
-    float4 *rec = rec_all + warp * 64;
-    unsigned char *s_perm = s_perm_all[warp];
-    int *s_bperm = s_bperm_all[warp];
+    float4(*rec)[2] = s_rec_all[warp];
+    unsigned char(*perm)[32] = s_perm_all[warp];
+    int *bperm = s_bperm_all[warp];
 
-    // ---- one-time setup (the only CTA barriers) ----
-    for (int b = tid; b <= p.B; b += NT) s_R[b] = p.frame_raw_base[b];
-    if (canvas_on) {
-        for (int t = tid; t < ZC * 32; t += NT) zerobuf[t] = 0.f;
-        for (int t = tid; t < EMIT_WARPS * TILE; t += NT) tiles[t] = 0.f;
-    }
-    if (PFN) {
-        for (int t = tid; t < CIN * C; t += NT) { const int c = t / CIN, k = t - c * CIN; s_W[k * C + c] = __ldg(p.W + t); }
-        for (int c = tid; c < C; c += NT) {
-            float y;
-            if (BN) {
-                const float mu = __ldg(p.bn_m + c), g = __ldg(p.bn_w + c), be = __ldg(p.bn_b + c);
-                const float inv = __frcp_rn(__fsqrt_rn(__fadd_rn(__ldg(p.bn_v + c), p.eps)));
-                s_bn[c] = mu; s_bn[C + c] = inv; s_bn[2 * C + c] = g; s_bn[3 * C + c] = be;
-                // a zero (padded) row still goes through BN + ReLU and joins the max (pillar_vfe.py:37-42)
-                y = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(0.f, mu), inv), g), be);
-            } else {
-                const float be = __ldg(p.bias + c);
-                s_bn[c] = 0.f; s_bn[C + c] = 0.f; s_bn[2 * C + c] = 0.f; s_bn[3 * C + c] = be;
-                y = __fadd_rn(0.f, be);
-            }
-            s_bn[4 * C + c] = (y > 0.f || y != y) ? y : 0.f;
-        }
-    }
+    for (int b = tid; b <= p.B; b += PFN_THREADS) s_R[b] = p.frame_raw_base[b];
     __syncthreads();
     if (tid == 0) {
         int acc = 0;
@@ -379,356 +334,395 @@ k_emit(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtenso
         s_K[p.B] = acc;
         if (blockIdx.x == 0) p.num_pillars[0] = acc;
     }
-    if (canvas_on && TMA) fence_proxy_async_smem();
     __syncthreads();
 
-    const int tiles_per_row = (p.nx + 31) >> 5;
-    const int rows_per_frame = p.nz * p.ny;
-    const int n_rows = p.B * rows_per_frame;
+    // this lane's 4 channels: Linear rows and BatchNorm constants, in registers for the whole kernel
+    const int c0 = 4 * (lane & 15);
+    float4 w4[CIN];
+    float4 mu = make_float4(0.f, 0.f, 0.f, 0.f), iv = mu, ga = mu, be = mu, pv = mu;
+    if (PFN) {
+#pragma unroll
+        for (int k = 0; k < CIN; ++k)
+            w4[k] = make_float4(__ldg(p.W + (c0 + 0) * CIN + k), __ldg(p.W + (c0 + 1) * CIN + k),
+                                __ldg(p.W + (c0 + 2) * CIN + k), __ldg(p.W + (c0 + 3) * CIN + k));
+        float bnv[5][4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int c = c0 + j;
+            float y;
+            if (BN) {
+                bnv[0][j] = __ldg(p.bn_m + c);
+                bnv[1][j] = __frcp_rn(__fsqrt_rn(__fadd_rn(__ldg(p.bn_v + c), p.eps)));
+                bnv[2][j] = __ldg(p.bn_w + c);
+                bnv[3][j] = __ldg(p.bn_b + c);
+                // a zero (padded) row still goes through BN + ReLU and joins the max (pillar_vfe.py:37-42)
+                y = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(0.f, bnv[0][j]), bnv[1][j]), bnv[2][j]), bnv[3][j]);
+            } else {
+                bnv[0][j] = bnv[1][j] = bnv[2][j] = 0.f;
+                bnv[3][j] = __ldg(p.bias + c);
+                y = __fadd_rn(0.f, bnv[3][j]);
+            }
+            bnv[4][j] = (y > 0.f || y != y) ? y : 0.f;
+        }
+        mu = make_float4(bnv[0][0], bnv[0][1], bnv[0][2], bnv[0][3]); iv = make_float4(bnv[1][0], bnv[1][1], bnv[1][2], bnv[1][3]);
+        ga = make_float4(bnv[2][0], bnv[2][1], bnv[2][2], bnv[2][3]); be = make_float4(bnv[3][0], bnv[3][1], bnv[3][2], bnv[3][3]);
+        pv = make_float4(bnv[4][0], bnv[4][1], bnv[4][2], bnv[4][3]);
+    }
+
     const int P4 = (p.P >> 2) << 2;
     const int maxv = p.max_voxels, Pmax = p.P;
     const float vsx = p.vsize[0], vsy = p.vsize[1], vsz = p.vsize[2], vox = p.voff[0], voy = p.voff[1], voz = p.voff[2];
-    const CellEntry *__restrict__ table = p.table;
     const float *__restrict__ grows = p.sorted_rows;
-    const unsigned lt = (1u << lane) - 1u;
+    const int m_raw = s_R[p.B];
+    const int n_chunks = (m_raw + 31) >> 5;
+    const int half = lane >> 4;
 
-    // this warp's tile sequence: first tile blockIdx*W + warp, stride gridDim*W; stepping is division free
+    for (int ch = blockIdx.x * PFN_WARPS + warp; ch < n_chunks; ch += gridDim.x * PFN_WARPS) {
+        // ---- owner phase: lane j looks after pillar m0 + j ----
+        const int m = ch * 32 + lane;
+        int4 pr = make_int4(0, 0, 0, 0);
+        if (m < m_raw) pr = __ldg(p.prec + m);
+        const int start = pr.x, cnt = pr.y, pb = pr.z >> 16, pz = pr.z & 0xFFFF, py = pr.w >> 16, px = pr.w & 0xFFFF;
+        const int local = m - s_R[pb];
+        const bool kept = (m < m_raw) && (local < maxv);      // pillars beyond max_voxels were never created
+        const int f = s_K[pb] + local;                          // final pillar id (first-seen order, frames concatenated)
+        const int n_keep = min(cnt, Pmax);
+        const float *grow = grows + (size_t)start * RW;
+        if (kept) {
+            p.num[f] = n_keep;
+            *reinterpret_cast<int4 *>(p.coords + 4 * (size_t)f) = make_int4(pb, pz, py, px);
+        }
+        // order the pillar's points by input index
+        if (kept && cnt > 1 && cnt <= SMALL_CNT) {
+            uint32_t idx[SMALL_CNT];
+#pragma unroll
+            for (int j = 0; j < SMALL_CNT; ++j) idx[j] = (j < cnt) ? __float_as_uint(__ldg(grow + (size_t)j * RW + Fr)) : 0xFFFFFFFFu;
+#pragma unroll
+            for (int j = 0; j < SMALL_CNT; ++j) {
+                int rank = 0;
+#pragma unroll
+                for (int q = 0; q < SMALL_CNT; ++q) rank += (idx[q] < idx[j]) ? 1 : 0;
+                if (j < cnt) perm[lane][rank] = (unsigned char)j;
+            }
+        }
+        unsigned coop = __ballot_sync(FULL, kept && cnt > SMALL_CNT && cnt <= 32);   // the warp ranks these one at a time
+        while (coop) {
+            const int o = __ffs(coop) - 1;
+            coop &= coop - 1;
+            const int cnt_o = __shfl_sync(FULL, cnt, o), start_o = __shfl_sync(FULL, start, o);
+            const uint32_t mine = (lane < cnt_o) ? __float_as_uint(__ldg(grows + (size_t)(start_o + lane) * RW + Fr)) : 0xFFFFFFFFu;
+            int rank = 0;
+            for (int q = 0; q < cnt_o; ++q) rank += (__shfl_sync(FULL, mine, q) < mine) ? 1 : 0;
+            if (lane < cnt_o) perm[o][rank] = (unsigned char)lane;
+        }
+        __syncwarp();
+        const unsigned huge = __ballot_sync(FULL, kept && cnt > 32);
+        if (PFN) {
+            // mean of the kept points (torch CPU sum order) and the record the unit lanes read
+            float mx = 0.f, my = 0.f, mz = 0.f;
+            if (kept && cnt <= 32) {
+                if (cnt == 1) {
+                    const float4 v = __ldg(reinterpret_cast<const float4 *>(grow));
+                    mx = v.x; my = v.y; mz = v.z;               // mean of one point is the point (x/1 is exact)
+                } else {
+                    SlotSum sum;
+                    for (int s2 = 0; s2 < n_keep; ++s2) {
+                        const float4 v = __ldg(reinterpret_cast<const float4 *>(grow + (size_t)perm[lane][s2] * RW));
+                        sum.add(s2, P4, v.x, v.y, v.z);
+                    }
+                    const float fn = (float)n_keep;
+                    mx = __fdiv_rn(sum.sx(), fn); my = __fdiv_rn(sum.sy(), fn); mz = __fdiv_rn(sum.sz(), fn);
+                }
+            }
+            const int live = (kept && cnt <= 32) ? 1 : 0;
+            rec[lane][0] = make_float4(mx, my, mz, __int_as_float(n_keep | (live << 8) | (cnt == 1 ? 0x200 : 0)));
+            rec[lane][1] = make_float4(__int_as_float(start), __int_as_float(f), __int_as_float(pr.z), __int_as_float(pr.w));
+            __syncwarp();
+            // ---- unit phase: lane l = channels c0..c0+3 of pillar (l>>4) + 2*it ----
+#pragma unroll 1
+            for (int it = 0; it < 16; ++it) {
+                const int ps = half + 2 * it;
+                const float4 r0 = rec[ps][0], r1 = rec[ps][1];
+                const int meta = __float_as_int(r0.w);
+                if (!(meta & 0x100)) continue;
+                const int nk = meta & 0xFF;
+                const bool single = (meta & 0x200) != 0;
+                const int zz = __float_as_int(r1.z) & 0xFFFF, yx = __float_as_int(r1.w);
+                // pillar centre: fl(fl(c*v)+off), two roundings, no FMA (pillar_vfe.py:101-103)
+                const float cx = __fadd_rn(__fmul_rn((float)(yx & 0xFFFF), vsx), vox);
+                const float cy = __fadd_rn(__fmul_rn((float)(yx >> 16), vsy), voy);
+                const float cz = __fadd_rn(__fmul_rn((float)zz, vsz), voz);
+                const float *rowb = grows + (size_t)__float_as_int(r1.x) * RWc;
+                // max over slots as an integer max on the float bits: exact for the non-negative post-ReLU values,
+                // drops negatives and -0 (the ReLU), and lets a NaN (0x7fffffff) win as torch.max does
+                int v0 = 0, v1 = 0, v2 = 0, v3 = 0;
+                if (nk < Pmax) { v0 = __float_as_int(pv.x); v1 = __float_as_int(pv.y); v2 = __float_as_int(pv.z); v3 = __float_as_int(pv.w); }
+#pragma unroll 1
+                for (int s2 = 0; s2 < nk; ++s2) {
+                    const float4 *r4 = reinterpret_cast<const float4 *>(rowb + (single ? 0 : (int)perm[ps][s2] * RWc));
+                    float row[RWc];
+#pragma unroll
+                    for (int v = 0; v < RWc / 4; ++v) {
+                        const float4 t4 = __ldg(r4 + v);
+                        row[4 * v] = t4.x; row[4 * v + 1] = t4.y; row[4 * v + 2] = t4.z; row[4 * v + 3] = t4.w;
+                    }
+                    float feat[CIN];
+                    {
+                        int kf = 0;
+#pragma unroll
+                        for (int q = ABS ? 0 : 3; q < F; ++q) feat[kf++] = row[q];
+                        feat[kf++] = __fsub_rn(row[0], r0.x); feat[kf++] = __fsub_rn(row[1], r0.y); feat[kf++] = __fsub_rn(row[2], r0.z);
+                        feat[kf++] = __fsub_rn(row[0], cx); feat[kf++] = __fsub_rn(row[1], cy); feat[kf++] = __fsub_rn(row[2], cz);
+                        // torch.norm(xyz, 2, 2) on the CPU: sqrt(fma(z,z, fma(y,y, x*x)))  (pillar_vfe.py:110-112)
+                        if (DIST) feat[kf++] = __fsqrt_rn(fmaf(row[2], row[2], fmaf(row[1], row[1], __fmul_rn(row[0], row[0]))));
+                    }
+                    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+                    for (int kk = 0; kk < CIN; ++kk) {     // Linear: sequential FMA in k order (pillar_vfe.py:37)
+                        a0 = fmaf(feat[kk], w4[kk].x, a0); a1 = fmaf(feat[kk], w4[kk].y, a1);
+                        a2 = fmaf(feat[kk], w4[kk].z, a2); a3 = fmaf(feat[kk], w4[kk].w, a3);
+                    }
+                    float y0, y1, y2, y3;
+                    if (BN) {                              // BN eval: (((x-mean)*invstd)*gamma)+beta, 4 roundings (:39)
+                        y0 = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(a0, mu.x), iv.x), ga.x), be.x);
+                        y1 = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(a1, mu.y), iv.y), ga.y), be.y);
+                        y2 = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(a2, mu.z), iv.z), ga.z), be.z);
+                        y3 = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(a3, mu.w), iv.w), ga.w), be.w);
+                    } else {
+                        y0 = __fadd_rn(a0, be.x); y1 = __fadd_rn(a1, be.y); y2 = __fadd_rn(a2, be.z); y3 = __fadd_rn(a3, be.w);
+                    }
+                    v0 = max(v0, __float_as_int(y0)); v1 = max(v1, __float_as_int(y1));
+                    v2 = max(v2, __float_as_int(y2)); v3 = max(v3, __float_as_int(y3));
+                }
+                *reinterpret_cast<float4 *>(p.feats + (size_t)__float_as_int(r1.y) * C + c0) =
+                    make_float4(__int_as_float(v0), __int_as_float(v1), __int_as_float(v2), __int_as_float(v3));
+            }
+        }
+        // ---- pillars with more than 32 arrivals: the warp selects the 32 smallest point indices, then as above ----
+        unsigned hm = huge;
+        while (hm) {
+            const int o = __ffs(hm) - 1;
+            hm &= hm - 1;
+            const int cnt_o = __shfl_sync(FULL, cnt, o), start_o = __shfl_sync(FULL, start, o), f_o = __shfl_sync(FULL, f, o);
+            const int prz = __shfl_sync(FULL, pr.z, o), prw = __shfl_sync(FULL, pr.w, o);
+            const int nk = min(cnt_o, Pmax);
+            const float *grow_o = grows + (size_t)start_o * RW;
+            bperm[lane] = select_first32(grow_o + Fr, RW, cnt_o, lane);
+            __syncwarp();
+            if (p.voxels) {
+                float *vo = p.voxels + (size_t)f_o * Pmax * Fr;
+                for (int t = lane; t < Pmax * Fr; t += 32) {
+                    const int s2 = t / Fr, kk = t - s2 * Fr;
+                    vo[t] = (s2 < nk) ? __ldg(grow_o + (size_t)bperm[s2] * RW + kk) : 0.f;
+                }
+            }
+            if (PFN) {
+                SlotSum sum;
+                for (int s2 = 0; s2 < nk; ++s2) {
+                    const float4 v = __ldg(reinterpret_cast<const float4 *>(grow_o + (size_t)bperm[s2] * RWc));
+                    sum.add(s2, P4, v.x, v.y, v.z);
+                }
+                const float fn = (float)nk;
+                const float mx = __fdiv_rn(sum.sx(), fn), my = __fdiv_rn(sum.sy(), fn), mz = __fdiv_rn(sum.sz(), fn);
+                const float cx = __fadd_rn(__fmul_rn((float)(prw & 0xFFFF), vsx), vox);
+                const float cy = __fadd_rn(__fmul_rn((float)(prw >> 16), vsy), voy);
+                const float cz = __fadd_rn(__fmul_rn((float)(prz & 0xFFFF), vsz), voz);
+                int v0 = 0, v1 = 0, v2 = 0, v3 = 0;
+                if (nk < Pmax) { v0 = __float_as_int(pv.x); v1 = __float_as_int(pv.y); v2 = __float_as_int(pv.z); v3 = __float_as_int(pv.w); }
+                for (int s2 = 0; s2 < nk; ++s2) {
+                    const float4 *r4 = reinterpret_cast<const float4 *>(grow_o + (size_t)bperm[s2] * RWc);
+                    float row[RWc];
+#pragma unroll
+                    for (int v = 0; v < RWc / 4; ++v) {
+                        const float4 t4 = __ldg(r4 + v);
+                        row[4 * v] = t4.x; row[4 * v + 1] = t4.y; row[4 * v + 2] = t4.z; row[4 * v + 3] = t4.w;
+                    }
+                    float feat[CIN];
+                    {
+                        int kf = 0;
+#pragma unroll
+                        for (int q = ABS ? 0 : 3; q < F; ++q) feat[kf++] = row[q];
+                        feat[kf++] = __fsub_rn(row[0], mx); feat[kf++] = __fsub_rn(row[1], my); feat[kf++] = __fsub_rn(row[2], mz);
+                        feat[kf++] = __fsub_rn(row[0], cx); feat[kf++] = __fsub_rn(row[1], cy); feat[kf++] = __fsub_rn(row[2], cz);
+                        if (DIST) feat[kf++] = __fsqrt_rn(fmaf(row[2], row[2], fmaf(row[1], row[1], __fmul_rn(row[0], row[0]))));
+                    }
+                    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+                    for (int kk = 0; kk < CIN; ++kk) {
+                        a0 = fmaf(feat[kk], w4[kk].x, a0); a1 = fmaf(feat[kk], w4[kk].y, a1);
+                        a2 = fmaf(feat[kk], w4[kk].z, a2); a3 = fmaf(feat[kk], w4[kk].w, a3);
+                    }
+                    float y0, y1, y2, y3;
+                    if (BN) {
+                        y0 = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(a0, mu.x), iv.x), ga.x), be.x);
+                        y1 = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(a1, mu.y), iv.y), ga.y), be.y);
+                        y2 = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(a2, mu.z), iv.z), ga.z), be.z);
+                        y3 = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(a3, mu.w), iv.w), ga.w), be.w);
+                    } else {
+                        y0 = __fadd_rn(a0, be.x); y1 = __fadd_rn(a1, be.y); y2 = __fadd_rn(a2, be.z); y3 = __fadd_rn(a3, be.w);
+                    }
+                    v0 = max(v0, __float_as_int(y0)); v1 = max(v1, __float_as_int(y1));
+                    v2 = max(v2, __float_as_int(y2)); v3 = max(v3, __float_as_int(y3));
+                }
+                if (half == 0)     // both half-warps computed the same 64 channels; one writes
+                    *reinterpret_cast<float4 *>(p.feats + (size_t)f_o * C + c0) =
+                        make_float4(__int_as_float(v0), __int_as_float(v1), __int_as_float(v2), __int_as_float(v3));
+            }
+            __syncwarp();
+        }
+        // ---- optional contract output: the padded voxels tensor [M, P, F], coalesced, one pillar at a time ----
+        if (p.voxels) {
+            unsigned todo = __ballot_sync(FULL, kept && cnt <= 32);
+            while (todo) {
+                const int o = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const int cnt_o = __shfl_sync(FULL, cnt, o), start_o = __shfl_sync(FULL, start, o), f_o = __shfl_sync(FULL, f, o);
+                const int nk = min(cnt_o, Pmax);
+                float *vo = p.voxels + (size_t)f_o * Pmax * Fr;
+                const float *grow_o = grows + (size_t)start_o * RW;
+                for (int t = lane; t < Pmax * Fr; t += 32) {
+                    const int s2 = t / Fr, kk = t - s2 * Fr;
+                    vo[t] = (s2 < nk) ? __ldg(grow_o + (size_t)((cnt_o == 1) ? 0 : (int)perm[o][s2]) * RW + kk) : 0.f;
+                }
+            }
+        }
+        __syncwarp();   // rec / perm are rewritten by the next chunk
+    }
+}
+
+// ---- k_canvas -----------------------------------------------------------------------------------
+// Tile major.  Every warp is an autonomous worker walking its own sequence of canvas tiles (a tile = 32 cells of
+// one BEV row x all C channels = C rows of 128 B) with its own 8 KB tile buffer: cell table entries (prefetched one
+// tile ahead) -> final pillar ids -> pillar_features rows (256 B each, straight from L2) -> tile columns -> ONE TMA
+// tensor store per tile (128-byte swizzle, so the column writes spread over banks).  Empty tiles are four stores
+// of a shared 2 KB zero tile and cost the SM nothing.  The canvas is written exactly once, zeros included.
+constexpr int CANVAS_WARPS = 4;
+constexpr int CANVAS_THREADS = CANVAS_WARPS * 32;
+
+template <int C, bool TMA>
+__global__ void __launch_bounds__(CANVAS_THREADS)
+k_canvas(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap zmap, const PathParams p) {
+    constexpr int TILE = C * 32;
+    constexpr int ZC = C / 4;
+    static_assert(C == 64, "a unit is 4 of 64 channels");
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    float *tiles = reinterpret_cast<float *>(smem_raw);                    // [CANVAS_WARPS][TILE]
+    float *zerobuf = tiles + CANVAS_WARPS * TILE;                          // [ZC*32]
+    int *s_R = reinterpret_cast<int *>(zerobuf + ZC * 32);                 // [B+1]
+    int *s_K = s_R + (p.B + 1);                                            // [B+1]
+    __shared__ int2 s_list_all[CANVAS_WARPS][32];                          // (cell, final pillar id) of the tile's pillars
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float *tile = tiles + warp * TILE;
+    int2 *list = s_list_all[warp];
+    for (int b = tid; b <= p.B; b += CANVAS_THREADS) s_R[b] = p.frame_raw_base[b];
+    for (int t = tid; t < ZC * 32; t += CANVAS_THREADS) zerobuf[t] = 0.f;
+    for (int t = tid; t < CANVAS_WARPS * TILE; t += CANVAS_THREADS) tiles[t] = 0.f;
+    __syncthreads();
+    if (tid == 0) {
+        int acc = 0;
+        for (int b = 0; b < p.B; ++b) { s_K[b] = acc; acc += min(s_R[b + 1] - s_R[b], p.max_voxels); }
+        s_K[p.B] = acc;
+    }
+    if (TMA) fence_proxy_async_smem();
+    __syncthreads();
+
+    const int tiles_per_row = (p.nx + 31) >> 5;
+    const int rows_per_frame = p.ny;                       // nz == 1 (PointPillarScatter asserts it)
+    const int n_rows = p.B * rows_per_frame;
+    const int maxv = p.max_voxels;
+    const CellEntry *__restrict__ table = p.table;
+    const unsigned lt = (1u << lane) - 1u;
+    // lane-constant part of the swizzled tile address of channel c0+j, cell x:
+    //   (c0+j)*32 + ((( x>>2 ) ^ ((c0+j)&7)) << 2 | (x&3))
+    const int c0 = 4 * (lane & 15);
+    const int half = lane >> 4;
+
     TileStep step;
     step.tiles_per_row = tiles_per_row; step.rows_per_frame = rows_per_frame;
     {
-        const int stride_tiles = (int)gridDim.x * EMIT_WARPS;
+        const int stride_tiles = (int)gridDim.x * CANVAS_WARPS;
         step.dr = stride_tiles / tiles_per_row; step.dxt = stride_tiles - step.dr * tiles_per_row;
     }
     TilePos cur;
     {
-        const int t0 = (int)blockIdx.x * EMIT_WARPS + warp;      // the only divisions: where this warp starts
+        const int t0 = (int)blockIdx.x * CANVAS_WARPS + warp;     // the only divisions: where this warp starts
         cur.r = t0 / tiles_per_row; cur.xt = t0 - cur.r * tiles_per_row;
         cur.b = cur.r / rows_per_frame; cur.zy = cur.r - cur.b * rows_per_frame;
     }
     TilePos nxt = cur;
     step.advance(nxt);
-    TilePos nxt2 = nxt;
-    step.advance(nxt2);
-
-    auto load_entry = [&](const TilePos &t) -> uint4 {
+    auto load_entry = [&](const TilePos &t) -> uint2 {
         const int x = t.xt * 32 + lane;
-        // row r = (b*nz + z)*ny + y and the table is [b][z][y][x]: the cell index is r*nx + x
-        return (t.r < n_rows && x < p.nx) ? __ldg(reinterpret_cast<const uint4 *>(table + (size_t)t.r * p.nx + x))
-                                          : make_uint4(0, 0, 0, 0);
+        return (t.r < n_rows && x < p.nx) ? __ldg(reinterpret_cast<const uint2 *>(table + (size_t)t.r * p.nx + x)) : make_uint2(0, 0);
     };
-    auto make_state = [&](const uint4 e, const TilePos &t) -> CellState {
-        CellState c;
-        const int b = (t.r < n_rows) ? t.b : 0;
-        c.m = (int)(e.x - 1u); c.cnt = (int)e.y; c.start = (int)e.z;
-        c.occ = (e.x != 0u) && (c.m - s_R[b] < maxv);
-        const int need = (c.occ && c.cnt <= 32) ? c.cnt : 0;
-        int incl = need;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const int o = __shfl_up_sync(FULL, incl, d);
-            if (lane >= d) incl += o;
-        }
-        c.off = incl - need;
-        c.staged = need > 0 && incl <= STAGE_W;
-        return c;
-    };
-    auto issue_gather = [&](const CellState &c, float *stg) {
-        if (c.staged) {
-            const float *src = grows + (size_t)c.start * RW;
-            float *dst = stg + (size_t)c.off * RW;
-            for (int j = 0; j < c.cnt; ++j)
-                for (int v = 0; v < NV; ++v) cp_async16(dst + j * RW + 4 * v, src + (size_t)j * RW + 4 * v);
-        }
-        cp_async_commit();
-    };
-    // order one unstaged pillar cooperatively: s_bperm[rank] = arrival position of the rank-th smallest index
-    auto coop_order = [&](const float *grow, int cnt) {
-        if (cnt <= 32) {
-            const uint32_t mine = (lane < cnt) ? __float_as_uint(__ldg(grow + (size_t)lane * RW + Fr)) : 0xFFFFFFFFu;
-            int rank = 0;
-            for (int qq = 0; qq < cnt; ++qq) rank += (__shfl_sync(FULL, mine, qq) < mine) ? 1 : 0;
-            if (lane < cnt) s_bperm[rank] = lane;
-        } else {
-            s_bperm[lane] = select_first32(grow + Fr, RW, cnt, lane);
-        }
-        __syncwarp();
-    };
-
-    CellState st_cur = make_state(load_entry(cur), cur);
-    issue_gather(st_cur, stage);
-    uint4 e_next = load_entry(nxt);
+    uint2 e = load_entry(cur);
     unsigned dirty = 0;                  // cells of the tile buffer that hold non-zero columns
     bool store_pending = false;          // a TMA store from the tile buffer may still be reading it
 
-    for (int it = 0; cur.r < n_rows; ++it) {
-        const int slot = it & 1;
-        const float *stg = stage + (size_t)slot * STAGE_W * RW;
-        // ---- next tile: cell states, gather in flight; entries of the one after it ----
-        const CellState st_nxt = make_state(e_next, nxt);
-        issue_gather(st_nxt, stage + (size_t)(slot ^ 1) * STAGE_W * RW);
-        e_next = load_entry(nxt2);
-
-        const CellState c = st_cur;
-        const int b = cur.b, zy = cur.zy, x0 = cur.xt * 32;
-        const int z = (p.nz == 1) ? 0 : zy / p.ny;
-        const int y = zy - z * p.ny;
-        const unsigned bal_occ = __ballot_sync(FULL, c.occ);
-        if (bal_occ == 0u) {
-            // empty tile: four stores of the shared zero tile
-            if (canvas_on) {
-                if (TMA) {
-                    if (lane == 0) {
+    for (; cur.r < n_rows; cur = nxt, step.advance(nxt)) {
+        const uint2 e_next = load_entry(nxt);              // prefetch the next tile's entries
+        const int b = cur.b, y = cur.zy, x0 = cur.xt * 32;
+        const int local = (int)(e.x - 1u) - s_R[b];
+        const bool occ = (e.x != 0u) && (local < maxv);
+        const unsigned bal = __ballot_sync(FULL, occ);
+        if (bal == 0u) {
+            if (TMA) {
+                if (lane == 0) {
 #pragma unroll
-                        for (int q4 = 0; q4 < 4; ++q4) tma_store_3d(&zmap, zerobuf, x0, zy, b * C + q4 * ZC);
-                        tma_commit();
-                    }
-                } else if (x0 + lane < p.nx) {
-                    for (int ch = 0; ch < C; ++ch) p.canvas[(((size_t)b * C + ch) * p.ny + y) * p.nx + x0 + lane] = 0.f;
+                    for (int q4 = 0; q4 < 4; ++q4) tma_store_3d(&zmap, zerobuf, x0, y, b * C + q4 * ZC);
+                    tma_commit();
                 }
+            } else if (x0 + lane < p.nx) {
+                for (int ch = 0; ch < C; ++ch) p.canvas[(((size_t)b * C + ch) * p.ny + y) * p.nx + x0 + lane] = 0.f;
             }
         } else {
-            const unsigned bal_st = __ballot_sync(FULL, c.staged);
-            const int n_keep = min(c.cnt, Pmax);
-            const int f = c.occ ? s_K[b] + (c.m - s_R[b]) : 0;     // final pillar id (first-seen order, frames concatenated)
-            if (c.occ) {
-                p.num[f] = n_keep;
-                *reinterpret_cast<int4 *>(p.coords + 4 * (size_t)f) = make_int4(b, z, y, x0 + lane);
-            }
-            cp_async_wait<1>();          // this tile's rows have landed (this lane's copies) ...
-            __syncwarp();                // ... and every other lane's
-            // ---- order the points of multi-point pillars by input index ----
-            if (c.staged && c.cnt > 1 && c.cnt <= 4) {            // small: the owning lane ranks them itself
-                const float *ib = stg + (size_t)c.off * RW + Fr;
-                for (int j = 0; j < c.cnt; ++j) {
-                    const uint32_t mine = __float_as_uint(ib[j * RW]);
-                    int rank = 0;
-                    for (int qq = 0; qq < c.cnt; ++qq) rank += (__float_as_uint(ib[qq * RW]) < mine) ? 1 : 0;
-                    s_perm[c.off + rank] = (unsigned char)j;
-                }
-            }
-            unsigned coop = __ballot_sync(FULL, c.staged && c.cnt > 4);   // larger: the warp ranks one pillar at a time
-            while (coop) {
-                const int o = __ffs(coop) - 1;
-                coop &= coop - 1;
-                const int cnt_o = __shfl_sync(FULL, c.cnt, o), off_o = __shfl_sync(FULL, c.off, o);
-                const uint32_t mine = (lane < cnt_o) ? __float_as_uint(stg[(size_t)(off_o + lane) * RW + Fr]) : 0xFFFFFFFFu;
-                int rank = 0;
-                for (int qq = 0; qq < cnt_o; ++qq) rank += (__shfl_sync(FULL, mine, qq) < mine) ? 1 : 0;
-                if (lane < cnt_o) s_perm[off_o + rank] = (unsigned char)lane;
+            if (occ) list[__popc(bal & lt)] = make_int2(lane, s_K[b] + local);
+            // the tile buffer: wait until the previous store has read it, then clear what it dirtied
+            if (TMA && store_pending) {
+                if (lane == 0) tma_wait_read<0>();
+                store_pending = false;
             }
             __syncwarp();
-            if (PFN) {
-                // ---- per-pillar record: mean (torch CPU sum order) and bookkeeping, by the owning lane ----
-                if (c.staged) {
-                    const float *srow = stg + (size_t)c.off * RW;
-                    float mx, my, mz;
-                    if (c.cnt == 1) {
-                        mx = srow[0]; my = srow[1]; mz = srow[2];   // mean of one point is the point (x/1 is exact)
-                    } else {
-                        SlotSum sum;
-                        for (int s2 = 0; s2 < n_keep; ++s2) {
-                            const float4 v = *reinterpret_cast<const float4 *>(srow + s_perm[c.off + s2] * RW);
-                            sum.add(s2, P4, v.x, v.y, v.z);
-                        }
-                        const float fn = (float)n_keep;
-                        mx = __fdiv_rn(sum.sx(), fn); my = __fdiv_rn(sum.sy(), fn); mz = __fdiv_rn(sum.sz(), fn);
-                    }
-                    const int k = __popc(bal_st & lt);
-                    rec[2 * k] = make_float4(mx, my, mz, __int_as_float(lane | (n_keep << 8) | (c.cnt == 1 ? 0x10000 : 0)));
-                    rec[2 * k + 1] = make_float4(__int_as_float(c.off), __int_as_float(f), 0.f, 0.f);
+            if (__popc(dirty) > 2) {
+#pragma unroll
+                for (int t = 0; t < TILE / 128; ++t) *reinterpret_cast<float4 *>(tile + t * 128 + lane * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+            } else {
+                while (dirty) {
+                    const int dc = __ffs(dirty) - 1;
+                    dirty &= dirty - 1;
+                    tile[swz128(lane, dc)] = 0.f; tile[swz128(lane + 32, dc)] = 0.f;
                 }
-                // the tile buffer: wait until the previous store has read it, then clear the columns it dirtied
-                if (canvas_on) {
-                    if (TMA && store_pending) {
-                        if (lane == 0) tma_wait_read<0>();
-                        store_pending = false;
-                    }
-                    __syncwarp();
-                    while (dirty) {
-                        const int dc = __ffs(dirty) - 1;
-                        dirty &= dirty - 1;
-                        tile[swz128(lane, dc)] = 0.f; tile[swz128(lane + 32, dc)] = 0.f;
-                    }
-                }
+            }
+            dirty = bal;
+            __syncwarp();
+            // units: (pillar, 4 channels): lane l moves channels c0..c0+3 of the tile's pillar (l>>4) + 2*it
+            const int n_p = __popc(bal);
+            for (int k = half; k < n_p; k += 2) {
+                const int2 cf = list[k];
+                const float4 v = __ldg(reinterpret_cast<const float4 *>(p.feats + (size_t)cf.y * C + c0));
+                const int xq = cf.x >> 2, xr = cf.x & 3;
+                float *t0 = tile + c0 * 32 + xr;
+                t0[0 * 32 + ((xq ^ ((c0 + 0) & 7)) << 2)] = v.x;
+                t0[1 * 32 + ((xq ^ ((c0 + 1) & 7)) << 2)] = v.y;
+                t0[2 * 32 + ((xq ^ ((c0 + 2) & 7)) << 2)] = v.z;
+                t0[3 * 32 + ((xq ^ ((c0 + 3) & 7)) << 2)] = v.w;
+            }
+            if (TMA) {
+                fence_proxy_async_smem();
                 __syncwarp();
-                // ---- units: (pillar, 4 channels), dealt round-robin to the lanes ----
-                const float cy = __fadd_rn(__fmul_rn((float)y, vsy), voy);   // pillar centre: fl(fl(c*v)+off), two roundings,
-                const float cz = __fadd_rn(__fmul_rn((float)z, vsz), voz);   // no FMA (pillar_vfe.py:101-103)
-                const int n_units = __popc(bal_st) * 16;
-                for (int u = lane; u < n_units; u += 32) {
-                    const int k = u >> 4, c0 = (u & 15) * 4;
-                    const float4 r0 = rec[2 * k], r1 = rec[2 * k + 1];
-                    const int meta = __float_as_int(r0.w);
-                    const int cell = meta & 31, nk = (meta >> 8) & 63;
-                    const bool single = (meta & 0x10000) != 0;
-                    const int off = __float_as_int(r1.x), fid = __float_as_int(r1.y);
-                    const float cx = __fadd_rn(__fmul_rn((float)(x0 + cell), vsx), vox);
-                    const float *srow = stg + (size_t)off * RWc;
-                    float4 w4[CIN];
-#pragma unroll
-                    for (int kk = 0; kk < CIN; ++kk) w4[kk] = *reinterpret_cast<const float4 *>(s_W + kk * C + c0);
-                    const float4 be = *reinterpret_cast<const float4 *>(s_bn + 3 * C + c0);
-                    float4 mu, iv, ga;
-                    if (BN) {
-                        mu = *reinterpret_cast<const float4 *>(s_bn + c0);
-                        iv = *reinterpret_cast<const float4 *>(s_bn + C + c0);
-                        ga = *reinterpret_cast<const float4 *>(s_bn + 2 * C + c0);
-                    }
-                    // max over slots as an integer max on the float bits: exact for the non-negative post-ReLU values,
-                    // drops negatives and -0 (the ReLU), and lets a NaN (0x7fffffff) win as torch.max does
-                    int v0 = 0, v1 = 0, v2 = 0, v3 = 0;
-                    if (nk < Pmax) {
-                        const float4 pv = *reinterpret_cast<const float4 *>(s_bn + 4 * C + c0);
-                        v0 = __float_as_int(pv.x); v1 = __float_as_int(pv.y); v2 = __float_as_int(pv.z); v3 = __float_as_int(pv.w);
-                    }
-#pragma unroll 1
-                    for (int s2 = 0; s2 < nk; ++s2) {
-                        const float *rp = srow + (single ? 0 : s_perm[off + s2] * RWc);
-                        float row[RWc];
-#pragma unroll
-                        for (int v = 0; v < RWc / 4; ++v) {
-                            const float4 t4 = *reinterpret_cast<const float4 *>(rp + 4 * v);
-                            row[4 * v] = t4.x; row[4 * v + 1] = t4.y; row[4 * v + 2] = t4.z; row[4 * v + 3] = t4.w;
-                        }
-                        float feat[CIN];
-                        {
-                            int kf = 0;
-#pragma unroll
-                            for (int qq = ABS ? 0 : 3; qq < F; ++qq) feat[kf++] = row[qq];
-                            feat[kf++] = __fsub_rn(row[0], r0.x); feat[kf++] = __fsub_rn(row[1], r0.y); feat[kf++] = __fsub_rn(row[2], r0.z);
-                            feat[kf++] = __fsub_rn(row[0], cx); feat[kf++] = __fsub_rn(row[1], cy); feat[kf++] = __fsub_rn(row[2], cz);
-                            // torch.norm(xyz, 2, 2) on the CPU: sqrt(fma(z,z, fma(y,y, x*x)))  (pillar_vfe.py:110-112)
-                            if (DIST) feat[kf++] = __fsqrt_rn(fmaf(row[2], row[2], fmaf(row[1], row[1], __fmul_rn(row[0], row[0]))));
-                        }
-                        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll
-                        for (int kk = 0; kk < CIN; ++kk) {     // Linear: sequential FMA in k order (pillar_vfe.py:37)
-                            a0 = fmaf(feat[kk], w4[kk].x, a0); a1 = fmaf(feat[kk], w4[kk].y, a1);
-                            a2 = fmaf(feat[kk], w4[kk].z, a2); a3 = fmaf(feat[kk], w4[kk].w, a3);
-                        }
-                        float y0, y1, y2, y3;
-                        if (BN) {                              // BN eval: (((x-mean)*invstd)*gamma)+beta, 4 roundings (:39)
-                            y0 = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(a0, mu.x), iv.x), ga.x), be.x);
-                            y1 = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(a1, mu.y), iv.y), ga.y), be.y);
-                            y2 = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(a2, mu.z), iv.z), ga.z), be.z);
-                            y3 = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(a3, mu.w), iv.w), ga.w), be.w);
-                        } else {
-                            y0 = __fadd_rn(a0, be.x); y1 = __fadd_rn(a1, be.y); y2 = __fadd_rn(a2, be.z); y3 = __fadd_rn(a3, be.w);
-                        }
-                        v0 = max(v0, __float_as_int(y0)); v1 = max(v1, __float_as_int(y1));
-                        v2 = max(v2, __float_as_int(y2)); v3 = max(v3, __float_as_int(y3));
-                    }
-                    const float4 o = make_float4(__int_as_float(v0), __int_as_float(v1), __int_as_float(v2), __int_as_float(v3));
-                    if (p.feats) *reinterpret_cast<float4 *>(p.feats + (size_t)fid * C + c0) = o;
-                    if (canvas_on) {
-                        tile[swz128(c0, cell)] = o.x; tile[swz128(c0 + 1, cell)] = o.y;
-                        tile[swz128(c0 + 2, cell)] = o.z; tile[swz128(c0 + 3, cell)] = o.w;
-                    }
-                }
-            }
-            // ---- unstaged pillars (> 32 arrivals, or staging full): the warp takes them one at a time, lanes = channels ----
-            unsigned big = bal_occ & ~bal_st;
-            while (big) {
-                const int o = __ffs(big) - 1;
-                big &= big - 1;
-                const int cnt_o = __shfl_sync(FULL, c.cnt, o), start_o = __shfl_sync(FULL, c.start, o), f_o = __shfl_sync(FULL, f, o);
-                const int nk = min(cnt_o, Pmax);
-                const float *grow = grows + (size_t)start_o * RW;
-                coop_order(grow, cnt_o);
-                if (p.voxels) {
-                    float *vo = p.voxels + (size_t)f_o * Pmax * Fr;
-                    for (int t = lane; t < Pmax * Fr; t += 32) {
-                        const int s2 = t / Fr, kk = t - s2 * Fr;
-                        vo[t] = (s2 < nk) ? __ldg(grow + (size_t)s_bperm[s2] * RW + kk) : 0.f;
-                    }
-                }
-                if (PFN) {
-                    const float cx = __fadd_rn(__fmul_rn((float)(x0 + o), vsx), vox);
-                    const float cy = __fadd_rn(__fmul_rn((float)y, vsy), voy);
-                    const float cz = __fadd_rn(__fmul_rn((float)z, vsz), voz);
-                    SlotSum sum;
-                    for (int s2 = 0; s2 < nk; ++s2) {
-                        const float4 v = __ldg(reinterpret_cast<const float4 *>(grow + (size_t)s_bperm[s2] * RWc));
-                        sum.add(s2, P4, v.x, v.y, v.z);
-                    }
-                    const float fn = (float)nk;
-                    const float mx = __fdiv_rn(sum.sx(), fn), my = __fdiv_rn(sum.sy(), fn), mz = __fdiv_rn(sum.sz(), fn);
-                    int v0 = (nk < Pmax) ? __float_as_int(s_bn[4 * C + lane]) : 0;
-                    int v1 = (nk < Pmax) ? __float_as_int(s_bn[4 * C + lane + 32]) : 0;
-                    for (int s2 = 0; s2 < nk; ++s2) {
-                        const float4 *r4 = reinterpret_cast<const float4 *>(grow + (size_t)s_bperm[s2] * RWc);
-                        float row[RWc];
-#pragma unroll
-                        for (int v = 0; v < RWc / 4; ++v) {
-                            const float4 t4 = __ldg(r4 + v);
-                            row[4 * v] = t4.x; row[4 * v + 1] = t4.y; row[4 * v + 2] = t4.z; row[4 * v + 3] = t4.w;
-                        }
-                        float feat[CIN];
-                        {
-                            int kf = 0;
-#pragma unroll
-                            for (int qq = ABS ? 0 : 3; qq < F; ++qq) feat[kf++] = row[qq];
-                            feat[kf++] = __fsub_rn(row[0], mx); feat[kf++] = __fsub_rn(row[1], my); feat[kf++] = __fsub_rn(row[2], mz);
-                            feat[kf++] = __fsub_rn(row[0], cx); feat[kf++] = __fsub_rn(row[1], cy); feat[kf++] = __fsub_rn(row[2], cz);
-                            if (DIST) feat[kf++] = __fsqrt_rn(fmaf(row[2], row[2], fmaf(row[1], row[1], __fmul_rn(row[0], row[0]))));
-                        }
-                        float a0 = 0.f, a1 = 0.f;
-#pragma unroll
-                        for (int kk = 0; kk < CIN; ++kk) {
-                            a0 = fmaf(feat[kk], s_W[kk * C + lane], a0);
-                            a1 = fmaf(feat[kk], s_W[kk * C + lane + 32], a1);
-                        }
-                        float y0, y1;
-                        if (BN) {
-                            y0 = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(a0, s_bn[lane]), s_bn[C + lane]), s_bn[2 * C + lane]), s_bn[3 * C + lane]);
-                            y1 = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(a1, s_bn[lane + 32]), s_bn[C + lane + 32]), s_bn[2 * C + lane + 32]), s_bn[3 * C + lane + 32]);
-                        } else {
-                            y0 = __fadd_rn(a0, s_bn[3 * C + lane]); y1 = __fadd_rn(a1, s_bn[3 * C + lane + 32]);
-                        }
-                        v0 = max(v0, __float_as_int(y0)); v1 = max(v1, __float_as_int(y1));
-                    }
-                    if (p.feats) { p.feats[(size_t)f_o * C + lane] = __int_as_float(v0); p.feats[(size_t)f_o * C + lane + 32] = __int_as_float(v1); }
-                    if (canvas_on) { tile[swz128(lane, o)] = __int_as_float(v0); tile[swz128(lane + 32, o)] = __int_as_float(v1); }
-                }
+                if (lane == 0) { tma_store_3d(&tmap, tile, x0, y, b * C); tma_commit(); }
+                store_pending = true;
+            } else {
                 __syncwarp();
-            }
-            // ---- optional contract output for the staged pillars: padded voxels [M, P, F], coalesced ----
-            if (p.voxels) {
-                unsigned todo = bal_st;
-                while (todo) {
-                    const int o = __ffs(todo) - 1;
-                    todo &= todo - 1;
-                    const int cnt_o = __shfl_sync(FULL, c.cnt, o), off_o = __shfl_sync(FULL, c.off, o), f_o = __shfl_sync(FULL, f, o);
-                    const int nk = min(cnt_o, Pmax);
-                    float *vo = p.voxels + (size_t)f_o * Pmax * Fr;
-                    const float *srow = stg + (size_t)off_o * RW;
-                    for (int t = lane; t < Pmax * Fr; t += 32) {
-                        const int s2 = t / Fr, kk = t - s2 * Fr;
-                        vo[t] = (s2 < nk) ? srow[((cnt_o == 1) ? 0 : (int)s_perm[off_o + s2]) * RW + kk] : 0.f;
-                    }
-                }
-            }
-            // ---- the tile goes out in one piece ----
-            if (canvas_on) {
-                dirty = bal_occ;
-                if (TMA) {
-                    fence_proxy_async_smem();
-                    __syncwarp();
-                    if (lane == 0) { tma_store_3d(&tmap, tile, x0, zy, b * C); tma_commit(); }
-                    store_pending = true;
-                } else {
-                    __syncwarp();
-                    if (x0 + lane < p.nx)
-                        for (int ch = 0; ch < C; ++ch) p.canvas[(((size_t)b * C + ch) * p.ny + y) * p.nx + x0 + lane] = tile[swz128(ch, lane)];
-                }
+                if (x0 + lane < p.nx)
+                    for (int ch = 0; ch < C; ++ch) p.canvas[(((size_t)b * C + ch) * p.ny + y) * p.nx + x0 + lane] = tile[swz128(ch, lane)];
             }
             __syncwarp();
         }
-        st_cur = st_nxt;
-        cur = nxt; nxt = nxt2; step.advance(nxt2);
+        e = e_next;
     }
-    cp_async_wait<0>();
-    if (canvas_on && TMA && lane == 0) tma_wait_read<0>();
+    if (TMA && lane == 0) tma_wait_read<0>();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -773,10 +767,48 @@ int sm_count() {
     return n;
 }
 
-template <int F, bool ABS, bool DIST, int C, bool PFN>
-static int launch_emit_t(const PathParams &p, cudaStream_t stream) {
-    const bool canvas_on = PFN && p.canvas;
-    const bool tma = canvas_on && (p.nx % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.canvas) & 15) == 0) && C <= 256;
+template <typename K>
+static int launch_persistent(K kern, int threads, size_t smem, long long work_ctas, cudaStream_t stream, int *grid_out) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    int per_sm = 1;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem);
+    if (e != cudaSuccess) return (int)e;
+    if (per_sm < 1) per_sm = 1;
+    *grid_out = (int)std::max<long long>(1, std::min<long long>(work_ctas, (long long)sm_count() * per_sm));
+    return HGSF_OK;
+}
+
+template <int F, bool ABS, bool DIST, bool PFN>
+static int launch_pfn_t(const PathParams &p, cudaStream_t stream) {
+    const size_t smem = sizeof(int) * 2 * (size_t)(p.B + 1);
+    const long long chunks = ((long long)p.n + 31) / 32;          // upper bound on pillar chunks
+    const bool bn = p.bn_w != nullptr;
+    auto go = [&](auto kern) -> int {
+        int grid = 1;
+        const int st = launch_persistent(kern, PFN_THREADS, smem, (chunks + PFN_WARPS - 1) / PFN_WARPS, stream, &grid);
+        if (st != HGSF_OK) return st;
+        kern<<<(unsigned)grid, PFN_THREADS, smem, stream>>>(p);
+        return (int)cudaGetLastError();
+    };
+    if constexpr (PFN) return bn ? go(k_pfn<F, ABS, DIST, true, true>) : go(k_pfn<F, ABS, DIST, false, true>);
+    return go(k_pfn<F, ABS, DIST, true, false>);
+}
+
+static int launch_pfn(const PathParams &p, bool with_pfn, bool abs_xyz, bool dist, cudaStream_t s) {
+    if (!with_pfn) return launch_pfn_t<4, true, false, false>(p, s);   // F / RW are read from the params when PFN is off
+    if (p.C != 64) return HGSF_ERR_UNSUPPORTED;
+#define HGSF_CASE(FV, A, D) if (p.F == FV && abs_xyz == A && dist == D) return launch_pfn_t<FV, A, D, true>(p, s);
+    HGSF_CASE(4, true, false) HGSF_CASE(5, true, false) HGSF_CASE(6, true, false) HGSF_CASE(7, true, false)
+    HGSF_CASE(8, true, false) HGSF_CASE(7, false, false) HGSF_CASE(8, false, false)
+    HGSF_CASE(7, true, true) HGSF_CASE(8, true, true)
+#undef HGSF_CASE
+    return HGSF_ERR_UNSUPPORTED;
+}
+
+static int launch_canvas(const PathParams &p, cudaStream_t stream) {
+    constexpr int C = 64;
+    const bool tma = (p.nx % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.canvas) & 15) == 0);
     CUtensorMap map, zmap;
     memset(&map, 0, sizeof(map));
     memset(&zmap, 0, sizeof(zmap));
@@ -785,47 +817,21 @@ static int launch_emit_t(const PathParams &p, cudaStream_t stream) {
         if (st == HGSF_OK) st = make_canvas_map(&zmap, p.canvas, p.B, C, p.ny, p.nx, C / 4);
         if (st != HGSF_OK) return st;
     }
-    const int cin = PFN ? p.Cin : 1;
-    const size_t smem = sizeof(float) * (EMIT_WARPS * C * 32 + (C / 4) * 32 + (size_t)cin * C + 5 * C +
-                                         EMIT_WARPS * 2 * STAGE_W * (size_t)p.RW + EMIT_WARPS * 64 * 4) +
-                        sizeof(int) * 2 * (size_t)(p.B + 1);
-    const long long n_tiles = ((long long)p.B * p.nz * p.ny * ((p.nx + 31) / 32) + EMIT_WARPS - 1) / EMIT_WARPS;   // CTA-loads of tiles
+    const size_t smem = sizeof(float) * (CANVAS_WARPS * C * 32 + (C / 4) * 32) + sizeof(int) * 2 * (size_t)(p.B + 1);
+    const long long n_tiles = (long long)p.B * p.ny * ((p.nx + 31) / 32);
     if (n_tiles == 0) return HGSF_OK;
-    const bool bn = p.bn_w != nullptr;
     auto go = [&](auto kern) -> int {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-        int per_sm = 1;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, EMIT_THREADS, smem);
-        if (e != cudaSuccess) return (int)e;
-        if (per_sm < 1) per_sm = 1;
-        const long long grid = std::min<long long>(n_tiles, (long long)sm_count() * per_sm);
-        kern<<<(unsigned)grid, EMIT_THREADS, smem, stream>>>(map, zmap, p);
+        int grid = 1;
+        const int st = launch_persistent(kern, CANVAS_THREADS, smem, (n_tiles + CANVAS_WARPS - 1) / CANVAS_WARPS, stream, &grid);
+        if (st != HGSF_OK) return st;
+        kern<<<(unsigned)grid, CANVAS_THREADS, smem, stream>>>(map, zmap, p);
         return (int)cudaGetLastError();
     };
-    if constexpr (PFN) {
-        if (tma) return bn ? go(k_emit<F, ABS, DIST, true, C, true, true>) : go(k_emit<F, ABS, DIST, false, C, true, true>);
-        return bn ? go(k_emit<F, ABS, DIST, true, C, true, false>) : go(k_emit<F, ABS, DIST, false, C, true, false>);
-    }
-    return go(k_emit<F, ABS, DIST, true, C, false, false>);
+    return tma ? go(k_canvas<C, true>) : go(k_canvas<C, false>);
 }
 
-template <int C>
-static int launch_emit_pfn(const PathParams &p, bool abs_xyz, bool dist, cudaStream_t s) {
-#define HGSF_CASE(FV, A, D) if (p.F == FV && abs_xyz == A && dist == D) return launch_emit_t<FV, A, D, C, true>(p, s);
-    HGSF_CASE(4, true, false) HGSF_CASE(5, true, false) HGSF_CASE(6, true, false) HGSF_CASE(7, true, false)
-    HGSF_CASE(8, true, false) HGSF_CASE(7, false, false) HGSF_CASE(8, false, false)
-    HGSF_CASE(7, true, true) HGSF_CASE(8, true, true)
-#undef HGSF_CASE
-    return HGSF_ERR_UNSUPPORTED;
-}
-
-static int launch_emit_plain(const PathParams &p, cudaStream_t s) {
-    return launch_emit_t<4, true, false, 64, false>(p, s);   // F / RW are read from the params when PFN is off
-}
-
-// ---- optional per-launch timing of k_emit (bench.py's roofline leg) ---------------------------------
-// A ring of CUDA event pairs recorded on the launching stream around the k_emit launch.  Off by default.
+// ---- optional per-launch timing of the dominant kernel, k_canvas (bench.py's roofline leg) ---------------------------------
+// A ring of CUDA event pairs recorded on the launching stream around that launch.  Off by default.
 struct EmitTiming {
     std::vector<cudaEvent_t> ev;   // 2 * capacity
     int capacity = 0, count = 0;
@@ -873,18 +879,17 @@ int launch_pillar_path(const PathParams &p, bool with_pfn, bool abs_xyz, bool di
         if ((e = cudaGetLastError()) != cudaSuccess) return (int)e;
         nl += 3;
     }
-    const bool timed = g_timing.capacity > 0 && g_timing.count < g_timing.capacity;
-    if (timed) cudaEventRecord(g_timing.ev[2 * g_timing.count], stream);
-    int st;
-    if (with_pfn) {
-        if (p.C == 64) st = launch_emit_pfn<64>(p, abs_xyz, dist, stream);
-        else st = HGSF_ERR_UNSUPPORTED;
-    } else {
-        st = launch_emit_plain(p, stream);
-    }
+    int st = launch_pfn(p, with_pfn, abs_xyz, dist, stream);
     if (st != HGSF_OK) return st;
-    if (timed) cudaEventRecord(g_timing.ev[2 * g_timing.count++ + 1], stream);
     ++nl;
+    if (with_pfn && p.canvas) {
+        const bool timed = g_timing.capacity > 0 && g_timing.count < g_timing.capacity;
+        if (timed) cudaEventRecord(g_timing.ev[2 * g_timing.count], stream);
+        st = launch_canvas(p, stream);
+        if (st != HGSF_OK) return st;
+        if (timed) cudaEventRecord(g_timing.ev[2 * g_timing.count++ + 1], stream);
+        ++nl;
+    }
     if (launches) *launches = nl;
     return HGSF_OK;
 }

@@ -24,6 +24,7 @@ struct PathParams {
     int32_t *key;                      // [n] cell key of each point, -1 = outside the grid
     uint32_t *arrival;                 // [n] unordered arrival rank of the point inside its cell
     float *sorted_rows;                // [n, RW] F features + point index of each point, grouped by pillar (CSR order)
+    int4 *prec;                        // [n] per raw pillar id: {CSR start, arrivals, b<<16|z, y<<16|x}
     int RW;
     // ---- PFN ----
     const float *W, *bias, *bn_w, *bn_b, *bn_m, *bn_v;
@@ -37,7 +38,7 @@ struct PathParams {
 struct WorkspaceLayout {
     size_t zero_bytes;     // leading region that must be zero at the start of every call
     size_t off_ticket, off_desc, off_raw_base, off_table;
-    size_t off_frame_offsets, off_key, off_arrival, off_sorted_rows;
+    size_t off_frame_offsets, off_key, off_arrival, off_sorted_rows, off_prec;
     size_t total;
     int scan_tiles, RW;
 };
@@ -58,6 +59,7 @@ inline WorkspaceLayout workspace_layout(int64_t n, int B, int64_t cells, int F) 
     w.off_key = o;         o = align_up(o + sizeof(int32_t) * (size_t)n, 256);
     w.off_arrival = o;     o = align_up(o + sizeof(uint32_t) * (size_t)n, 256);
     w.off_sorted_rows = o; o = align_up(o + sizeof(float) * (size_t)n * (size_t)w.RW, 256);
+    w.off_prec = o;        o = align_up(o + sizeof(int4) * (size_t)n, 256);
     w.total = o;
     return w;
 }
