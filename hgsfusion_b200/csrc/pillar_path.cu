@@ -26,6 +26,7 @@
 #include "contract_ops.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -373,6 +374,7 @@ __global__ void __launch_bounds__(PFN_THREADS, 4) k_pfn(const PathParams p) {
     const int maxv = p.max_voxels, Pmax = p.P;
     const float vsx = p.vsize[0], vsy = p.vsize[1], vsz = p.vsize[2], vox = p.voff[0], voy = p.voff[1], voz = p.voff[2];
     const float *__restrict__ grows = p.sorted_rows;
+    const uint64_t keep_policy = l2_policy_evict_last();      // pillar rows: k_canvas re-reads them from L2
     const int m_raw = s_R[p.B];
     const int n_chunks = (m_raw + 31) >> 5;
     const int half = lane >> 4;
@@ -494,8 +496,8 @@ __global__ void __launch_bounds__(PFN_THREADS, 4) k_pfn(const PathParams p) {
                     v0 = max(v0, __float_as_int(y0)); v1 = max(v1, __float_as_int(y1));
                     v2 = max(v2, __float_as_int(y2)); v3 = max(v3, __float_as_int(y3));
                 }
-                *reinterpret_cast<float4 *>(p.feats + (size_t)__float_as_int(r1.y) * C + c0) =
-                    make_float4(__int_as_float(v0), __int_as_float(v1), __int_as_float(v2), __int_as_float(v3));
+                st_f4_hint(p.feats + (size_t)__float_as_int(r1.y) * C + c0,
+                           make_float4(__int_as_float(v0), __int_as_float(v1), __int_as_float(v2), __int_as_float(v3)), keep_policy);
             }
         }
         // ---- pillars with more than 32 arrivals: the warp selects the 32 smallest point indices, then as above ----
@@ -599,25 +601,27 @@ __global__ void __launch_bounds__(PFN_THREADS, 4) k_pfn(const PathParams p) {
 constexpr int CANVAS_WARPS = 4;
 constexpr int CANVAS_THREADS = CANVAS_WARPS * 32;
 
-template <int C, bool TMA>
+// STORE selects how a finished tile leaves the SM: 0 = one TMA tensor store, 1 = coalesced 16-byte global stores
+// (4 channel rows x 128 B per warp instruction), 2 = 4-byte stores (row pitch not a multiple of 16 bytes)
+template <int C, int STORE>
 __global__ void __launch_bounds__(CANVAS_THREADS)
 k_canvas(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap zmap, const PathParams p) {
     constexpr int TILE = C * 32;
     constexpr int ZC = C / 4;
     static_assert(C == 64, "a unit is 4 of 64 channels");
+    constexpr bool TMA = (STORE == 0);
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    float *tiles = reinterpret_cast<float *>(smem_raw);                    // [CANVAS_WARPS][TILE]
-    float *zerobuf = tiles + CANVAS_WARPS * TILE;                          // [ZC*32]
+    float *tiles = reinterpret_cast<float *>(smem_raw);                    // [CANVAS_WARPS][2][TILE] double buffered
+    float *zerobuf = tiles + CANVAS_WARPS * 2 * TILE;                          // [ZC*32]
     int *s_R = reinterpret_cast<int *>(zerobuf + ZC * 32);                 // [B+1]
     int *s_K = s_R + (p.B + 1);                                            // [B+1]
-    __shared__ int2 s_list_all[CANVAS_WARPS][32];                          // (cell, final pillar id) of the tile's pillars
+    __shared__ int2 s_list_all[CANVAS_WARPS][64];                          // (cell, final pillar id) of this / the next tile's pillars
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    float *tile = tiles + warp * TILE;
-    int2 *list = s_list_all[warp];
+    float *tile_base = tiles + warp * 2 * TILE;
     for (int b = tid; b <= p.B; b += CANVAS_THREADS) s_R[b] = p.frame_raw_base[b];
     for (int t = tid; t < ZC * 32; t += CANVAS_THREADS) zerobuf[t] = 0.f;
-    for (int t = tid; t < CANVAS_WARPS * TILE; t += CANVAS_THREADS) tiles[t] = 0.f;
+    for (int t = tid; t < CANVAS_WARPS * 2 * TILE; t += CANVAS_THREADS) tiles[t] = 0.f;
     __syncthreads();
     if (tid == 0) {
         int acc = 0;
@@ -652,38 +656,77 @@ k_canvas(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUten
     }
     TilePos nxt = cur;
     step.advance(nxt);
+    TilePos nxt2 = nxt;
+    step.advance(nxt2);
     auto load_entry = [&](const TilePos &t) -> uint2 {
         const int x = t.xt * 32 + lane;
         return (t.r < n_rows && x < p.nx) ? __ldg(reinterpret_cast<const uint2 *>(table + (size_t)t.r * p.nx + x)) : make_uint2(0, 0);
     };
-    uint2 e = load_entry(cur);
-    unsigned dirty = 0;                  // cells of the tile buffer that hold non-zero columns
-    bool store_pending = false;          // a TMA store from the tile buffer may still be reading it
-
-    for (; cur.r < n_rows; cur = nxt, step.advance(nxt)) {
-        const uint2 e_next = load_entry(nxt);              // prefetch the next tile's entries
-        const int b = cur.b, y = cur.zy, x0 = cur.xt * 32;
-        const int local = (int)(e.x - 1u) - s_R[b];
-        const bool occ = (e.x != 0u) && (local < maxv);
+    const uint64_t stream_policy = l2_policy_evict_first();   // canvas: written once, never re-read here
+    // a tile's pillar list (cell, final id) from its table entries; returns the occupancy mask
+    auto make_list = [&](const uint2 ent, const TilePos &t, int2 *lst) -> unsigned {
+        const int bb = (t.r < n_rows) ? t.b : 0;
+        const int local = (int)(ent.x - 1u) - s_R[bb];
+        const bool occ = (ent.x != 0u) && (local < maxv);
         const unsigned bal = __ballot_sync(FULL, occ);
+        if (occ) lst[__popc(bal & lt)] = make_int2(lane, s_K[bb] + local);
+        __syncwarp();
+        return bal;
+    };
+    constexpr int PRE = 4;              // pillar rows prefetched per half-warp for the next tile (covers 8 pillars)
+    auto prefetch_rows = [&](const int2 *lst, int n_p, float4 (&pre)[PRE]) {
+#pragma unroll
+        for (int j = 0; j < PRE; ++j) {
+            const int k = half + 2 * j;
+            if (k < n_p) pre[j] = ld_f4_hint(p.feats + (size_t)lst[k].y * C + c0, stream_policy);
+        }
+    };
+
+    int2 *list0 = s_list_all[warp], *list1 = s_list_all[warp] + 32;
+    unsigned bal = make_list(load_entry(cur), cur, list0);
+    float4 pre[PRE];
+    prefetch_rows(list0, __popc(bal), pre);
+    uint2 e_next = load_entry(nxt);
+    unsigned dirty0 = 0u, dirty1 = 0u;   // cells of each tile buffer that hold non-zero columns
+    int nb = 0;                          // non-empty tiles so far: selects the tile buffer
+
+    for (int it = 0; cur.r < n_rows; ++it, cur = nxt, nxt = nxt2, step.advance(nxt2)) {
+        int2 *list = (it & 1) ? list1 : list0, *list_n = (it & 1) ? list0 : list1;
+        // ---- next tile: pillar list, its first rows on their way; entries of the tile after it ----
+        const unsigned bal_n = make_list(e_next, nxt, list_n);
+        float4 pre_n[PRE];
+        prefetch_rows(list_n, __popc(bal_n), pre_n);
+        e_next = load_entry(nxt2);
+
+        const int b = cur.b, y = cur.zy, x0 = cur.xt * 32;
         if (bal == 0u) {
             if (TMA) {
                 if (lane == 0) {
 #pragma unroll
-                    for (int q4 = 0; q4 < 4; ++q4) tma_store_3d(&zmap, zerobuf, x0, y, b * C + q4 * ZC);
+                    for (int q4 = 0; q4 < 4; ++q4) tma_store_3d_hint(&zmap, zerobuf, x0, y, b * C + q4 * ZC, stream_policy);
                     tma_commit();
+                }
+            } else if (STORE == 1) {
+                // lane l: 16-byte chunk (l & 7) of channel rows (l >> 3) + 4*i
+                const int xc = x0 + 4 * (lane & 7);
+                if (xc < p.nx) {
+                    float *dst = p.canvas + (((size_t)b * C + (lane >> 3)) * p.ny + y) * p.nx + xc;
+                    const size_t plane4 = (size_t)4 * p.ny * p.nx;
+#pragma unroll
+                    for (int i = 0; i < C / 4; ++i) __stcs(reinterpret_cast<float4 *>(dst + i * plane4), make_float4(0.f, 0.f, 0.f, 0.f));
                 }
             } else if (x0 + lane < p.nx) {
                 for (int ch = 0; ch < C; ++ch) p.canvas[(((size_t)b * C + ch) * p.ny + y) * p.nx + x0 + lane] = 0.f;
             }
         } else {
-            if (occ) list[__popc(bal & lt)] = make_int2(lane, s_K[b] + local);
-            // the tile buffer: wait until the previous store has read it, then clear what it dirtied
-            if (TMA && store_pending) {
-                if (lane == 0) tma_wait_read<0>();
-                store_pending = false;
+            // this tile's buffer: wait until the store issued from it two tiles ago has read it (the most recent
+            // store, from the other buffer, may still be in flight), then clear what that tile dirtied
+            float *tile = tile_base + (nb & 1) * TILE;
+            unsigned dirty = (nb & 1) ? dirty1 : dirty0;
+            if (TMA) {
+                if (lane == 0) tma_wait_read<1>();
+                __syncwarp();
             }
-            __syncwarp();
             if (__popc(dirty) > 2) {
 #pragma unroll
                 for (int t = 0; t < TILE / 128; ++t) *reinterpret_cast<float4 *>(tile + t * 128 + lane * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -694,25 +737,43 @@ k_canvas(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUten
                     tile[swz128(lane, dc)] = 0.f; tile[swz128(lane + 32, dc)] = 0.f;
                 }
             }
-            dirty = bal;
+            if (nb & 1) dirty1 = bal; else dirty0 = bal;
+            ++nb;
             __syncwarp();
-            // units: (pillar, 4 channels): lane l moves channels c0..c0+3 of the tile's pillar (l>>4) + 2*it
+            // units: (pillar, 4 channels): lane l moves channels c0..c0+3 of the tile's pillar (l>>4) + 2*j
             const int n_p = __popc(bal);
-            for (int k = half; k < n_p; k += 2) {
-                const int2 cf = list[k];
-                const float4 v = __ldg(reinterpret_cast<const float4 *>(p.feats + (size_t)cf.y * C + c0));
-                const int xq = cf.x >> 2, xr = cf.x & 3;
+            auto put = [&](int cell, const float4 v) {
+                const int xq = cell >> 2, xr = cell & 3;
                 float *t0 = tile + c0 * 32 + xr;
                 t0[0 * 32 + ((xq ^ ((c0 + 0) & 7)) << 2)] = v.x;
                 t0[1 * 32 + ((xq ^ ((c0 + 1) & 7)) << 2)] = v.y;
                 t0[2 * 32 + ((xq ^ ((c0 + 2) & 7)) << 2)] = v.z;
                 t0[3 * 32 + ((xq ^ ((c0 + 3) & 7)) << 2)] = v.w;
+            };
+#pragma unroll
+            for (int j = 0; j < PRE; ++j) {
+                const int k = half + 2 * j;
+                if (k < n_p) put(list[k].x, pre[j]);
             }
+            for (int k = half + 2 * PRE; k < n_p; k += 2)
+                put(list[k].x, ld_f4_hint(p.feats + (size_t)list[k].y * C + c0, stream_policy));
             if (TMA) {
                 fence_proxy_async_smem();
                 __syncwarp();
-                if (lane == 0) { tma_store_3d(&tmap, tile, x0, y, b * C); tma_commit(); }
-                store_pending = true;
+                if (lane == 0) { tma_store_3d_hint(&tmap, tile, x0, y, b * C, stream_policy); tma_commit(); }
+            } else if (STORE == 1) {
+                __syncwarp();
+                const int xc = x0 + 4 * (lane & 7);
+                if (xc < p.nx) {
+                    float *dst = p.canvas + (((size_t)b * C + (lane >> 3)) * p.ny + y) * p.nx + xc;
+                    const size_t plane4 = (size_t)4 * p.ny * p.nx;
+#pragma unroll
+                    for (int i = 0; i < C / 4; ++i) {
+                        const int row = (lane >> 3) + 4 * i;
+                        const float4 v = *reinterpret_cast<const float4 *>(tile + row * 32 + (((lane & 7) ^ (row & 7)) << 2));
+                        __stcs(reinterpret_cast<float4 *>(dst + i * plane4), v);
+                    }
+                }
             } else {
                 __syncwarp();
                 if (x0 + lane < p.nx)
@@ -720,7 +781,9 @@ k_canvas(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUten
             }
             __syncwarp();
         }
-        e = e_next;
+        bal = bal_n;
+#pragma unroll
+        for (int j = 0; j < PRE; ++j) pre[j] = pre_n[j];
     }
     if (TMA && lane == 0) tma_wait_read<0>();
 }
@@ -808,7 +871,10 @@ static int launch_pfn(const PathParams &p, bool with_pfn, bool abs_xyz, bool dis
 
 static int launch_canvas(const PathParams &p, cudaStream_t stream) {
     constexpr int C = 64;
-    const bool tma = (p.nx % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.canvas) & 15) == 0);
+    const bool vec_ok = (p.nx % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.canvas) & 15) == 0);
+    // HGSF_CANVAS_STORE=tma|vec picks the tile store for experiments; default below
+    const char *env = getenv("HGSF_CANVAS_STORE");
+    const bool tma = vec_ok && !(env && env[0] == 'v');
     CUtensorMap map, zmap;
     memset(&map, 0, sizeof(map));
     memset(&zmap, 0, sizeof(zmap));
@@ -817,7 +883,7 @@ static int launch_canvas(const PathParams &p, cudaStream_t stream) {
         if (st == HGSF_OK) st = make_canvas_map(&zmap, p.canvas, p.B, C, p.ny, p.nx, C / 4);
         if (st != HGSF_OK) return st;
     }
-    const size_t smem = sizeof(float) * (CANVAS_WARPS * C * 32 + (C / 4) * 32) + sizeof(int) * 2 * (size_t)(p.B + 1);
+    const size_t smem = sizeof(float) * (CANVAS_WARPS * 2 * C * 32 + (C / 4) * 32) + sizeof(int) * 2 * (size_t)(p.B + 1);
     const long long n_tiles = (long long)p.B * p.ny * ((p.nx + 31) / 32);
     if (n_tiles == 0) return HGSF_OK;
     auto go = [&](auto kern) -> int {
@@ -827,7 +893,8 @@ static int launch_canvas(const PathParams &p, cudaStream_t stream) {
         kern<<<(unsigned)grid, CANVAS_THREADS, smem, stream>>>(map, zmap, p);
         return (int)cudaGetLastError();
     };
-    return tma ? go(k_canvas<C, true>) : go(k_canvas<C, false>);
+    if (tma) return go(k_canvas<C, 0>);
+    return vec_ok ? go(k_canvas<C, 1>) : go(k_canvas<C, 2>);
 }
 
 // ---- optional per-launch timing of the dominant kernel, k_canvas (bench.py's roofline leg) ---------------------------------
