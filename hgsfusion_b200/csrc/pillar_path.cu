@@ -21,6 +21,8 @@
 //   PillarVFE.forward + PFNLayer.forward          pcdet/models/backbones_3d/vfe/pillar_vfe.py:29-49,94-123
 //   PointPillarScatter.forward                    pcdet/models/backbones_2d/map_to_bev/pointpillar_scatter.py:14-41
 // The fp32 operation order is the one the CPU reference was measured to use (oracle/pillar_oracle.c).
+#include <cooperative_groups.h>
+
 #include "pillar_path.cuh"
 #include "pfn.cuh"
 #include "contract_ops.cuh"
@@ -30,10 +32,19 @@
 #include <cstring>
 #include <vector>
 
+namespace cg = cooperative_groups;
+
 namespace hgsf {
 
 // ------------------------------------------------------------------------------------------------
-// k_count
+// k_front : ONE cooperative kernel for the whole front end (grid barriers instead of launches)
+//   phase 0  zero the cell table
+//   phase 1  count : 1 thread / point.  cell key; per cell min point index + count through warp-aggregated atomics
+//   phase 2  scan  : exclusive prefix over POINTS of (is-first-of-its-cell, that cell's count).  At a first point the
+//                    prefix is (raw pillar id, CSR start): pillar ids come out in first-seen order without a sort.
+//                    Two level: every CTA reduces its contiguous slice, barrier, then scans it with the sum of the
+//                    slices before it as carry-in.  Also writes the pillar records and the raw id at each frame start.
+//   phase 3  fill  : 1 thread / point: copies the point's features (+ its index) to its pillar's CSR segment
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ int find_frame(const int32_t *__restrict__ off, int B, int i) {
     // largest b in [0, B) with off[b] <= i  (frames are contiguous; empty frames are skipped)
@@ -45,9 +56,8 @@ __device__ __forceinline__ int find_frame(const int32_t *__restrict__ off, int B
     return lo;
 }
 
-__global__ void __launch_bounds__(256) k_count(const PathParams p) {
-    const int i = blockIdx.x * 256 + threadIdx.x;
-    const int lane = threadIdx.x & 31;
+// phase 1 body for point i (every lane of the warp calls it, i >= n for the padding lanes)
+__device__ __forceinline__ void count_point(const PathParams &p, int i, int lane) {
     int key = -1;
     if (i < p.n) {
         const float *row = p.pts + (size_t)i * p.stride;
@@ -95,135 +105,20 @@ __global__ void __launch_bounds__(256) k_count(const PathParams p) {
     }
 }
 
-// ------------------------------------------------------------------------------------------------
-// k_scan : exclusive prefix over points of (is-first-of-its-cell, that cell's count)
-// descriptor word: [63:62] status (0 none, 1 aggregate, 2 inclusive prefix) [61:31] pillars [30:0] points
-// ------------------------------------------------------------------------------------------------
-constexpr int SCAN_THREADS = 256;
-constexpr int SCAN_ITEMS = SCAN_TILE / SCAN_THREADS;   // 4
-__device__ __forceinline__ uint64_t pack2(uint32_t pillars, uint32_t points) { return ((uint64_t)pillars << 31) | points; }
-constexpr uint64_t VAL_MASK = (1ull << 62) - 1;
-
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan(const PathParams p) {
-    __shared__ uint32_t s_tile;
-    __shared__ uint64_t s_warp[SCAN_THREADS / 32];
-    __shared__ uint64_t s_prefix;
-    __shared__ uint32_t s_excl[SCAN_TILE];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) s_tile = atomicAdd(p.ticket, 1u);   // dynamic tile id: look-back never waits on an unscheduled CTA
-    __syncthreads();
-    const int tile = (int)s_tile;
-    const int base = tile * SCAN_TILE + tid * SCAN_ITEMS;
-
-    int keys[SCAN_ITEMS];
-    uint32_t flag[SCAN_ITEMS], cnt[SCAN_ITEMS];
-    uint64_t local = 0;
-#pragma unroll
-    for (int j = 0; j < SCAN_ITEMS; ++j) {
-        const int i = base + j;
-        keys[j] = (i < p.n) ? p.key[i] : -1;
-    }
-#pragma unroll
-    for (int j = 0; j < SCAN_ITEMS; ++j) {
-        flag[j] = 0; cnt[j] = 0;
-        if (keys[j] >= 0) {
-            const uint2 e = *reinterpret_cast<const uint2 *>(p.table + keys[j]);   // tag, cnt
-            flag[j] = (e.x == 0xFFFFFFFFu - (uint32_t)(base + j)) ? 1u : 0u;
-            cnt[j] = flag[j] ? e.y : 0u;
-        }
-        local += pack2(flag[j], cnt[j]);
-    }
-    // block-wide exclusive scan of `local`
-    uint64_t incl = local;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const uint64_t o = __shfl_up_sync(FULL, incl, d);
-        if (lane >= d) incl += o;
-    }
-    if (lane == 31) s_warp[warp] = incl;
-    __syncthreads();
-    uint64_t warp_off = 0, block_total = 0;
-#pragma unroll
-    for (int w = 0; w < SCAN_THREADS / 32; ++w) {
-        const uint64_t v = s_warp[w];
-        if (w < warp) warp_off += v;
-        block_total += v;
-    }
-    // decoupled look-back (warp 0)
-    if (warp == 0) {
-        if (lane == 0) st_volatile_u64(p.scan_desc + tile, (tile == 0 ? (2ull << 62) : (1ull << 62)) | block_total);
-        uint64_t excl = 0;
-        int look = tile - 1;
-        while (look >= 0) {
-            const int idx = look - lane;
-            uint64_t d;
-            do {
-                d = (idx >= 0) ? ld_volatile_u64(p.scan_desc + idx) : (2ull << 62);
-            } while (__any_sync(FULL, (d >> 62) == 0));
-            const unsigned pm = __ballot_sync(FULL, (d >> 62) == 2);
-            const int first = pm ? (__ffs(pm) - 1) : 32;
-            uint64_t v = (lane <= first) ? (d & VAL_MASK) : 0ull;
-#pragma unroll
-            for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(FULL, v, s);
-            excl += v;
-            if (pm) break;
-            look -= 32;
-        }
-        if (lane == 0) {
-            if (tile > 0) st_volatile_u64(p.scan_desc + tile, (2ull << 62) | (excl + block_total));
-            s_prefix = excl;
-        }
-    }
-    __syncthreads();
-    uint64_t run = s_prefix + warp_off + (incl - local);
-#pragma unroll
-    for (int j = 0; j < SCAN_ITEMS; ++j) {
-        const uint32_t pillars = (uint32_t)(run >> 31), points = (uint32_t)(run & 0x7FFFFFFFu);
-        s_excl[tid * SCAN_ITEMS + j] = pillars;
-        if (flag[j]) {
-            CellEntry *e = p.table + keys[j];
-            e->tag = pillars + 1u;     // raw pillar id + 1 (disjoint from the 0xFFFFFFFF-i range other threads compare against)
-            e->start = points;
-            // the pillar's record, in first-seen order (one thread per pillar pays the divisions)
-            const int key = keys[j];
-            const int b = key / p.cells, rem = key - b * p.cells;
-            const int plane = p.ny * p.nx;
-            const int z = rem / plane, rem2 = rem - z * plane;
-            const int y = rem2 / p.nx, x = rem2 - y * p.nx;
-            p.prec[pillars] = make_int4((int)points, (int)cnt[j], (b << 16) | z, (y << 16) | x);
-        }
-        run += pack2(flag[j], cnt[j]);
-    }
-    __syncthreads();
-    // raw pillar id at each frame start
-    const int lo = tile * SCAN_TILE, hi = lo + SCAN_TILE;
-    const bool last = (hi >= p.n);
-    const uint32_t total = (uint32_t)((s_prefix + block_total) >> 31);
-    for (int b = tid; b <= p.B; b += SCAN_THREADS) {
-        const int o = p.frame_offsets[b];
-        if (o >= lo && o < hi && o < p.n) p.frame_raw_base[b] = (int32_t)s_excl[o - lo];
-        else if (last && o >= p.n) p.frame_raw_base[b] = (int32_t)total;
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// k_fill : point features -> CSR segment of the point's pillar
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_fill(const PathParams p) {
-    const int i = blockIdx.x * 256 + threadIdx.x;
-    if (i >= p.n) return;
+// phase 3 body
+__device__ __forceinline__ void fill_point(const PathParams &p, int i) {
     const int key = p.key[i];
     if (key < 0) return;
-    const uint4 e = __ldg(reinterpret_cast<const uint4 *>(p.table + key));
+    const uint4 e = *reinterpret_cast<const uint4 *>(p.table + key);
     const int b = key / p.cells;
-    const int local = (int)(e.x - 1u) - __ldg(p.frame_raw_base + b);
+    const int local = (int)(e.x - 1u) - p.frame_raw_base[b];
     if (local >= p.max_voxels) return;            // pillar beyond max_voxels: never created
     const size_t pos = (size_t)e.z + p.arrival[i];
     const float *src = p.pts + (size_t)i * p.stride + p.xyz_col;
     float4 *dst = reinterpret_cast<float4 *>(p.sorted_rows + pos * p.RW);
     for (int k = 0; k < p.RW; k += 4) {
         float4 v;
-        // F features, then the point index (slot F) that k_emit orders the pillar by
+        // F features, then the point index (slot F) that k_pfn orders the pillar by
         const float fi = __int_as_float(i);
         v.x = (k + 0 < p.F) ? __ldg(src + k + 0) : (k + 0 == p.F ? fi : 0.f);
         v.y = (k + 1 < p.F) ? __ldg(src + k + 1) : (k + 1 == p.F ? fi : 0.f);
@@ -231,6 +126,151 @@ __global__ void __launch_bounds__(256) k_fill(const PathParams p) {
         v.w = (k + 3 < p.F) ? __ldg(src + k + 3) : (k + 3 == p.F ? fi : 0.f);
         dst[k >> 2] = v;
     }
+}
+
+constexpr int FRONT_THREADS = 256;
+constexpr int SCAN_ITEMS = SCAN_TILE / FRONT_THREADS;   // 4
+__device__ __forceinline__ uint64_t pack2(uint32_t pillars, uint32_t points) { return ((uint64_t)pillars << 32) | points; }
+
+// block-wide sum of a 64-bit value; every thread gets the total
+__device__ __forceinline__ uint64_t block_sum(uint64_t v, uint64_t *s_warp, int lane, int warp) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(FULL, v, d);
+    __syncthreads();
+    if (lane == 0) s_warp[warp] = v;
+    __syncthreads();
+    uint64_t t = 0;
+#pragma unroll
+    for (int w = 0; w < FRONT_THREADS / 32; ++w) t += s_warp[w];
+    return t;
+}
+
+__global__ void __launch_bounds__(FRONT_THREADS) k_front(const PathParams p) {
+    cg::grid_group grid = cg::this_grid();
+#ifdef HGSF_PHASE_TIMES
+    auto stamp = [&](int k) { if (blockIdx.x == 0 && threadIdx.x == 0) { uint64_t t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); p.scan_desc[4000 + k] = t; } };
+#else
+    auto stamp = [&](int) {};
+#endif
+    stamp(0);
+    __shared__ uint64_t s_warp[FRONT_THREADS / 32];
+    __shared__ uint32_t s_excl[SCAN_TILE];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long gtid = (long long)blockIdx.x * FRONT_THREADS + tid, nthr = (long long)gridDim.x * FRONT_THREADS;
+
+    // ---- phase 0: zero the cell table (and k_pfn's chunk ticket) ----
+    if (gtid == 0) *p.ticket = 0u;
+    {
+        uint4 *t4 = reinterpret_cast<uint4 *>(p.table);
+        const long long n4 = (long long)p.B * p.cells;      // one uint4 per entry
+        for (long long i = gtid; i < n4; i += nthr) t4[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    grid.sync();
+    stamp(1);
+    // ---- phase 1: count ----
+    {
+        const long long n_pad = ((long long)p.n + 31) & ~31ll;
+        for (long long i = gtid; i < n_pad; i += nthr) count_point(p, (int)i, lane);
+    }
+    grid.sync();
+    stamp(2);
+    // ---- phase 2: scan.  CTA c owns points [lo, hi), a whole number of 1024-point tiles ----
+    const int tiles_total = (p.n + SCAN_TILE - 1) / SCAN_TILE;
+    const int tiles_per_cta = (tiles_total + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int lo = min((int)blockIdx.x * tiles_per_cta, tiles_total) * SCAN_TILE;
+    const int hi = min(((int)blockIdx.x + 1) * tiles_per_cta, tiles_total) * SCAN_TILE;
+    auto flags_of = [&](int base, int (&keys)[SCAN_ITEMS], uint32_t (&flag)[SCAN_ITEMS], uint32_t (&cnt)[SCAN_ITEMS]) -> uint64_t {
+        uint64_t local = 0;
+#pragma unroll
+        for (int j = 0; j < SCAN_ITEMS; ++j) keys[j] = (base + j < p.n) ? p.key[base + j] : -1;
+#pragma unroll
+        for (int j = 0; j < SCAN_ITEMS; ++j) {
+            flag[j] = 0; cnt[j] = 0;
+            if (keys[j] >= 0) {
+                const uint2 e = *reinterpret_cast<const uint2 *>(p.table + keys[j]);   // tag, cnt
+                flag[j] = (e.x == 0xFFFFFFFFu - (uint32_t)(base + j)) ? 1u : 0u;
+                cnt[j] = flag[j] ? e.y : 0u;
+            }
+            local += pack2(flag[j], cnt[j]);
+        }
+        return local;
+    };
+    {
+        uint64_t mine = 0;
+        for (int t0 = lo; t0 < hi; t0 += SCAN_TILE) {
+            int keys[SCAN_ITEMS];
+            uint32_t flag[SCAN_ITEMS], cnt[SCAN_ITEMS];
+            mine += flags_of(t0 + tid * SCAN_ITEMS, keys, flag, cnt);
+        }
+        const uint64_t total = block_sum(mine, s_warp, lane, warp);
+        if (tid == 0) p.scan_desc[blockIdx.x] = total;
+    }
+    grid.sync();
+    stamp(3);
+    {
+        uint64_t before = 0;
+        for (int c = tid; c < (int)blockIdx.x; c += FRONT_THREADS) before += p.scan_desc[c];
+        uint64_t carry = block_sum(before, s_warp, lane, warp);     // (pillars, points) of all slices before this one
+        for (int t0 = lo; t0 < hi; t0 += SCAN_TILE) {
+            const int base = t0 + tid * SCAN_ITEMS;
+            int keys[SCAN_ITEMS];
+            uint32_t flag[SCAN_ITEMS], cnt[SCAN_ITEMS];
+            const uint64_t local = flags_of(base, keys, flag, cnt);
+            // block-wide exclusive scan of `local`
+            uint64_t incl = local;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint64_t o = __shfl_up_sync(FULL, incl, d);
+                if (lane >= d) incl += o;
+            }
+            __syncthreads();
+            if (lane == 31) s_warp[warp] = incl;
+            __syncthreads();
+            uint64_t warp_off = 0, tile_total = 0;
+#pragma unroll
+            for (int w = 0; w < FRONT_THREADS / 32; ++w) {
+                const uint64_t v = s_warp[w];
+                if (w < warp) warp_off += v;
+                tile_total += v;
+            }
+            uint64_t run = carry + warp_off + (incl - local);
+#pragma unroll
+            for (int j = 0; j < SCAN_ITEMS; ++j) {
+                const uint32_t pillars = (uint32_t)(run >> 32), points = (uint32_t)run;
+                s_excl[tid * SCAN_ITEMS + j] = pillars;
+                if (flag[j]) {
+                    CellEntry *e = p.table + keys[j];
+                    e->tag = pillars + 1u;     // raw pillar id + 1 (disjoint from the 0xFFFFFFFF-i values phase 1 left)
+                    e->start = points;
+                    // the pillar's record, in first-seen order (one thread per pillar pays the divisions)
+                    const int key = keys[j];
+                    const int b = key / p.cells, rem = key - b * p.cells;
+                    const int plane = p.ny * p.nx;
+                    const int z = rem / plane, rem2 = rem - z * plane;
+                    const int y = rem2 / p.nx, x = rem2 - y * p.nx;
+                    p.prec[pillars] = make_int4((int)points, (int)cnt[j], (b << 16) | z, (y << 16) | x);
+                }
+                run += pack2(flag[j], cnt[j]);
+            }
+            __syncthreads();
+            // raw pillar id at each frame start
+            const bool last = (t0 + SCAN_TILE >= p.n);
+            const uint32_t total = (uint32_t)((carry + tile_total) >> 32);
+            for (int b = tid; b <= p.B; b += FRONT_THREADS) {
+                const int o = p.frame_offsets[b];
+                if (o >= t0 && o < t0 + SCAN_TILE && o < p.n) p.frame_raw_base[b] = (int32_t)s_excl[o - t0];
+                else if (last && o >= p.n) p.frame_raw_base[b] = (int32_t)total;
+            }
+            carry += tile_total;
+        }
+        if (p.n == 0 && blockIdx.x == 0)
+            for (int b = tid; b <= p.B; b += FRONT_THREADS) p.frame_raw_base[b] = 0;
+    }
+    grid.sync();
+    stamp(4);
+    // ---- phase 3: fill ----
+    for (long long i = gtid; i < p.n; i += nthr) fill_point(p, (int)i);
+    stamp(5);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -378,8 +418,54 @@ __global__ void __launch_bounds__(PFN_THREADS, 4) k_pfn(const PathParams p) {
     const int m_raw = s_R[p.B];
     const int n_chunks = (m_raw + 31) >> 5;
     const int half = lane >> 4;
+    const unsigned lt = (1u << lane) - 1u;
 
-    for (int ch = blockIdx.x * PFN_WARPS + warp; ch < n_chunks; ch += gridDim.x * PFN_WARPS) {
+    // one point through decorate + Linear + BN, folded into the running max (integer max on the float bits: exact for
+    // the non-negative post-ReLU values, drops negatives and -0 = the ReLU, lets a NaN 0x7fffffff win as torch.max does)
+    auto eval_point = [&](const float *rowp, float mx, float my, float mz, float cx, float cy, float cz,
+                          int &v0, int &v1, int &v2, int &v3) {
+        const float4 *r4 = reinterpret_cast<const float4 *>(rowp);
+        float row[RWc];
+#pragma unroll
+        for (int v = 0; v < RWc / 4; ++v) {
+            const float4 t4 = __ldg(r4 + v);
+            row[4 * v] = t4.x; row[4 * v + 1] = t4.y; row[4 * v + 2] = t4.z; row[4 * v + 3] = t4.w;
+        }
+        float feat[CIN];
+        {
+            int kf = 0;
+#pragma unroll
+            for (int q = ABS ? 0 : 3; q < F; ++q) feat[kf++] = row[q];
+            feat[kf++] = __fsub_rn(row[0], mx); feat[kf++] = __fsub_rn(row[1], my); feat[kf++] = __fsub_rn(row[2], mz);
+            feat[kf++] = __fsub_rn(row[0], cx); feat[kf++] = __fsub_rn(row[1], cy); feat[kf++] = __fsub_rn(row[2], cz);
+            // torch.norm(xyz, 2, 2) on the CPU: sqrt(fma(z,z, fma(y,y, x*x)))  (pillar_vfe.py:110-112)
+            if (DIST) feat[kf++] = __fsqrt_rn(fmaf(row[2], row[2], fmaf(row[1], row[1], __fmul_rn(row[0], row[0]))));
+        }
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+        for (int kk = 0; kk < CIN; ++kk) {     // Linear: sequential FMA in k order (pillar_vfe.py:37)
+            a0 = fmaf(feat[kk], w4[kk].x, a0); a1 = fmaf(feat[kk], w4[kk].y, a1);
+            a2 = fmaf(feat[kk], w4[kk].z, a2); a3 = fmaf(feat[kk], w4[kk].w, a3);
+        }
+        float y0, y1, y2, y3;
+        if (BN) {                              // BN eval: (((x-mean)*invstd)*gamma)+beta, 4 roundings (:39)
+            y0 = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(a0, mu.x), iv.x), ga.x), be.x);
+            y1 = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(a1, mu.y), iv.y), ga.y), be.y);
+            y2 = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(a2, mu.z), iv.z), ga.z), be.z);
+            y3 = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(a3, mu.w), iv.w), ga.w), be.w);
+        } else {
+            y0 = __fadd_rn(a0, be.x); y1 = __fadd_rn(a1, be.y); y2 = __fadd_rn(a2, be.z); y3 = __fadd_rn(a3, be.w);
+        }
+        v0 = max(v0, __float_as_int(y0)); v1 = max(v1, __float_as_int(y1));
+        v2 = max(v2, __float_as_int(y2)); v3 = max(v3, __float_as_int(y3));
+    };
+
+    for (;;) {
+        // chunks are handed out dynamically: dense chunks (many points per pillar) cost several times a sparse one
+        int ch = 0;
+        if (lane == 0) ch = (int)atomicAdd(p.ticket, 1u);
+        ch = __shfl_sync(FULL, ch, 0);
+        if (ch >= n_chunks) break;
         // ---- owner phase: lane j looks after pillar m0 + j ----
         const int m = ch * 32 + lane;
         int4 pr = make_int4(0, 0, 0, 0);
@@ -421,8 +507,9 @@ __global__ void __launch_bounds__(PFN_THREADS, 4) k_pfn(const PathParams p) {
         const unsigned huge = __ballot_sync(FULL, kept && cnt > 32);
         if (PFN) {
             // mean of the kept points (torch CPU sum order) and the record the unit lanes read
+            const bool live = kept && cnt <= 32;
             float mx = 0.f, my = 0.f, mz = 0.f;
-            if (kept && cnt <= 32) {
+            if (live) {
                 if (cnt == 1) {
                     const float4 v = __ldg(reinterpret_cast<const float4 *>(grow));
                     mx = v.x; my = v.y; mz = v.z;               // mean of one point is the point (x/1 is exact)
@@ -436,71 +523,63 @@ __global__ void __launch_bounds__(PFN_THREADS, 4) k_pfn(const PathParams p) {
                     mx = __fdiv_rn(sum.sx(), fn); my = __fdiv_rn(sum.sy(), fn); mz = __fdiv_rn(sum.sz(), fn);
                 }
             }
-            const int live = (kept && cnt <= 32) ? 1 : 0;
-            rec[lane][0] = make_float4(mx, my, mz, __int_as_float(n_keep | (live << 8) | (cnt == 1 ? 0x200 : 0)));
-            rec[lane][1] = make_float4(__int_as_float(start), __int_as_float(f), __int_as_float(pr.z), __int_as_float(pr.w));
+            // two work lists: pillars with ONE point to evaluate (paired across the half-warps) and pillars with several
+            // (taken one at a time, the half-warps splitting the points)
+            const unsigned sbal = __ballot_sync(FULL, live && n_keep == 1);
+            const unsigned mbal = __ballot_sync(FULL, live && n_keep > 1);
+            const int n_s = __popc(sbal), n_m = __popc(mbal);
+            if (live) {
+                const int slot = (n_keep == 1) ? __popc(sbal & lt) : 31 - __popc(mbal & lt);   // singles from the front, multis from the back
+                // position of the single evaluated point: 0, or the rank-0 arrival when P == 1 truncated a larger pillar
+                const int pos0 = (cnt == 1) ? 0 : (int)perm[lane][0];
+                rec[slot][0] = make_float4(mx, my, mz, __int_as_float(n_keep | (lane << 8) | (pos0 << 16)));
+                rec[slot][1] = make_float4(__int_as_float(start), __int_as_float(f), __int_as_float(pr.z), __int_as_float(pr.w));
+            }
             __syncwarp();
-            // ---- unit phase: lane l = channels c0..c0+3 of pillar (l>>4) + 2*it ----
+            // ---- unit phase.  lane l always computes channels c0..c0+3 ----
+            // (a) single-point pillars: half-warp h takes list entries 2*it + h
 #pragma unroll 1
-            for (int it = 0; it < 16; ++it) {
-                const int ps = half + 2 * it;
-                const float4 r0 = rec[ps][0], r1 = rec[ps][1];
+            for (int it = 0; 2 * it < n_s; ++it) {
+                const int e = 2 * it + half;
+                if (e < n_s) {
+                    const float4 r0 = rec[e][0], r1 = rec[e][1];
+                    const int meta = __float_as_int(r0.w);
+                    const int zz = __float_as_int(r1.z) & 0xFFFF, yx = __float_as_int(r1.w);
+                    // pillar centre: fl(fl(c*v)+off), two roundings, no FMA (pillar_vfe.py:101-103)
+                    const float cx = __fadd_rn(__fmul_rn((float)(yx & 0xFFFF), vsx), vox);
+                    const float cy = __fadd_rn(__fmul_rn((float)(yx >> 16), vsy), voy);
+                    const float cz = __fadd_rn(__fmul_rn((float)zz, vsz), voz);
+                    int v0 = 0, v1 = 0, v2 = 0, v3 = 0;
+                    if (1 < Pmax) { v0 = __float_as_int(pv.x); v1 = __float_as_int(pv.y); v2 = __float_as_int(pv.z); v3 = __float_as_int(pv.w); }
+                    eval_point(grows + ((size_t)__float_as_int(r1.x) + (meta >> 16)) * RWc, r0.x, r0.y, r0.z, cx, cy, cz, v0, v1, v2, v3);
+                    st_f4_hint(p.feats + (size_t)__float_as_int(r1.y) * C + c0,
+                               make_float4(__int_as_float(v0), __int_as_float(v1), __int_as_float(v2), __int_as_float(v3)), keep_policy);
+                }
+            }
+            // (b) multi-point pillars: both half-warps on the same pillar, half h takes slots h, h+2, ...; max-combined
+#pragma unroll 1
+            for (int it = 0; it < n_m; ++it) {
+                const float4 r0 = rec[31 - it][0], r1 = rec[31 - it][1];
                 const int meta = __float_as_int(r0.w);
-                if (!(meta & 0x100)) continue;
-                const int nk = meta & 0xFF;
-                const bool single = (meta & 0x200) != 0;
+                const int nk = meta & 0xFF, owner = (meta >> 8) & 0xFF;
                 const int zz = __float_as_int(r1.z) & 0xFFFF, yx = __float_as_int(r1.w);
-                // pillar centre: fl(fl(c*v)+off), two roundings, no FMA (pillar_vfe.py:101-103)
                 const float cx = __fadd_rn(__fmul_rn((float)(yx & 0xFFFF), vsx), vox);
                 const float cy = __fadd_rn(__fmul_rn((float)(yx >> 16), vsy), voy);
                 const float cz = __fadd_rn(__fmul_rn((float)zz, vsz), voz);
                 const float *rowb = grows + (size_t)__float_as_int(r1.x) * RWc;
-                // max over slots as an integer max on the float bits: exact for the non-negative post-ReLU values,
-                // drops negatives and -0 (the ReLU), and lets a NaN (0x7fffffff) win as torch.max does
                 int v0 = 0, v1 = 0, v2 = 0, v3 = 0;
                 if (nk < Pmax) { v0 = __float_as_int(pv.x); v1 = __float_as_int(pv.y); v2 = __float_as_int(pv.z); v3 = __float_as_int(pv.w); }
 #pragma unroll 1
-                for (int s2 = 0; s2 < nk; ++s2) {
-                    const float4 *r4 = reinterpret_cast<const float4 *>(rowb + (single ? 0 : (int)perm[ps][s2] * RWc));
-                    float row[RWc];
-#pragma unroll
-                    for (int v = 0; v < RWc / 4; ++v) {
-                        const float4 t4 = __ldg(r4 + v);
-                        row[4 * v] = t4.x; row[4 * v + 1] = t4.y; row[4 * v + 2] = t4.z; row[4 * v + 3] = t4.w;
-                    }
-                    float feat[CIN];
-                    {
-                        int kf = 0;
-#pragma unroll
-                        for (int q = ABS ? 0 : 3; q < F; ++q) feat[kf++] = row[q];
-                        feat[kf++] = __fsub_rn(row[0], r0.x); feat[kf++] = __fsub_rn(row[1], r0.y); feat[kf++] = __fsub_rn(row[2], r0.z);
-                        feat[kf++] = __fsub_rn(row[0], cx); feat[kf++] = __fsub_rn(row[1], cy); feat[kf++] = __fsub_rn(row[2], cz);
-                        // torch.norm(xyz, 2, 2) on the CPU: sqrt(fma(z,z, fma(y,y, x*x)))  (pillar_vfe.py:110-112)
-                        if (DIST) feat[kf++] = __fsqrt_rn(fmaf(row[2], row[2], fmaf(row[1], row[1], __fmul_rn(row[0], row[0]))));
-                    }
-                    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll
-                    for (int kk = 0; kk < CIN; ++kk) {     // Linear: sequential FMA in k order (pillar_vfe.py:37)
-                        a0 = fmaf(feat[kk], w4[kk].x, a0); a1 = fmaf(feat[kk], w4[kk].y, a1);
-                        a2 = fmaf(feat[kk], w4[kk].z, a2); a3 = fmaf(feat[kk], w4[kk].w, a3);
-                    }
-                    float y0, y1, y2, y3;
-                    if (BN) {                              // BN eval: (((x-mean)*invstd)*gamma)+beta, 4 roundings (:39)
-                        y0 = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(a0, mu.x), iv.x), ga.x), be.x);
-                        y1 = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(a1, mu.y), iv.y), ga.y), be.y);
-                        y2 = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(a2, mu.z), iv.z), ga.z), be.z);
-                        y3 = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(a3, mu.w), iv.w), ga.w), be.w);
-                    } else {
-                        y0 = __fadd_rn(a0, be.x); y1 = __fadd_rn(a1, be.y); y2 = __fadd_rn(a2, be.z); y3 = __fadd_rn(a3, be.w);
-                    }
-                    v0 = max(v0, __float_as_int(y0)); v1 = max(v1, __float_as_int(y1));
-                    v2 = max(v2, __float_as_int(y2)); v3 = max(v3, __float_as_int(y3));
-                }
-                st_f4_hint(p.feats + (size_t)__float_as_int(r1.y) * C + c0,
-                           make_float4(__int_as_float(v0), __int_as_float(v1), __int_as_float(v2), __int_as_float(v3)), keep_policy);
+                for (int s2 = half; s2 < nk; s2 += 2)
+                    eval_point(rowb + (size_t)perm[owner][s2] * RWc, r0.x, r0.y, r0.z, cx, cy, cz, v0, v1, v2, v3);
+                v0 = max(v0, __shfl_xor_sync(FULL, v0, 16)); v1 = max(v1, __shfl_xor_sync(FULL, v1, 16));
+                v2 = max(v2, __shfl_xor_sync(FULL, v2, 16)); v3 = max(v3, __shfl_xor_sync(FULL, v3, 16));
+                if (half == 0)
+                    st_f4_hint(p.feats + (size_t)__float_as_int(r1.y) * C + c0,
+                               make_float4(__int_as_float(v0), __int_as_float(v1), __int_as_float(v2), __int_as_float(v3)), keep_policy);
             }
         }
-        // ---- pillars with more than 32 arrivals: the warp selects the 32 smallest point indices, then as above ----
+        // ---- pillars with more than 32 arrivals: the warp selects the 32 smallest point indices, then as (b) ----
         unsigned hm = huge;
         while (hm) {
             const int o = __ffs(hm) - 1;
@@ -531,44 +610,14 @@ __global__ void __launch_bounds__(PFN_THREADS, 4) k_pfn(const PathParams p) {
                 const float cz = __fadd_rn(__fmul_rn((float)(prz & 0xFFFF), vsz), voz);
                 int v0 = 0, v1 = 0, v2 = 0, v3 = 0;
                 if (nk < Pmax) { v0 = __float_as_int(pv.x); v1 = __float_as_int(pv.y); v2 = __float_as_int(pv.z); v3 = __float_as_int(pv.w); }
-                for (int s2 = 0; s2 < nk; ++s2) {
-                    const float4 *r4 = reinterpret_cast<const float4 *>(grow_o + (size_t)bperm[s2] * RWc);
-                    float row[RWc];
-#pragma unroll
-                    for (int v = 0; v < RWc / 4; ++v) {
-                        const float4 t4 = __ldg(r4 + v);
-                        row[4 * v] = t4.x; row[4 * v + 1] = t4.y; row[4 * v + 2] = t4.z; row[4 * v + 3] = t4.w;
-                    }
-                    float feat[CIN];
-                    {
-                        int kf = 0;
-#pragma unroll
-                        for (int q = ABS ? 0 : 3; q < F; ++q) feat[kf++] = row[q];
-                        feat[kf++] = __fsub_rn(row[0], mx); feat[kf++] = __fsub_rn(row[1], my); feat[kf++] = __fsub_rn(row[2], mz);
-                        feat[kf++] = __fsub_rn(row[0], cx); feat[kf++] = __fsub_rn(row[1], cy); feat[kf++] = __fsub_rn(row[2], cz);
-                        if (DIST) feat[kf++] = __fsqrt_rn(fmaf(row[2], row[2], fmaf(row[1], row[1], __fmul_rn(row[0], row[0]))));
-                    }
-                    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll
-                    for (int kk = 0; kk < CIN; ++kk) {
-                        a0 = fmaf(feat[kk], w4[kk].x, a0); a1 = fmaf(feat[kk], w4[kk].y, a1);
-                        a2 = fmaf(feat[kk], w4[kk].z, a2); a3 = fmaf(feat[kk], w4[kk].w, a3);
-                    }
-                    float y0, y1, y2, y3;
-                    if (BN) {
-                        y0 = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(a0, mu.x), iv.x), ga.x), be.x);
-                        y1 = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(a1, mu.y), iv.y), ga.y), be.y);
-                        y2 = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(a2, mu.z), iv.z), ga.z), be.z);
-                        y3 = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(a3, mu.w), iv.w), ga.w), be.w);
-                    } else {
-                        y0 = __fadd_rn(a0, be.x); y1 = __fadd_rn(a1, be.y); y2 = __fadd_rn(a2, be.z); y3 = __fadd_rn(a3, be.w);
-                    }
-                    v0 = max(v0, __float_as_int(y0)); v1 = max(v1, __float_as_int(y1));
-                    v2 = max(v2, __float_as_int(y2)); v3 = max(v3, __float_as_int(y3));
-                }
-                if (half == 0)     // both half-warps computed the same 64 channels; one writes
-                    *reinterpret_cast<float4 *>(p.feats + (size_t)f_o * C + c0) =
-                        make_float4(__int_as_float(v0), __int_as_float(v1), __int_as_float(v2), __int_as_float(v3));
+#pragma unroll 1
+                for (int s2 = half; s2 < nk; s2 += 2)
+                    eval_point(grow_o + (size_t)bperm[s2] * RWc, mx, my, mz, cx, cy, cz, v0, v1, v2, v3);
+                v0 = max(v0, __shfl_xor_sync(FULL, v0, 16)); v1 = max(v1, __shfl_xor_sync(FULL, v1, 16));
+                v2 = max(v2, __shfl_xor_sync(FULL, v2, 16)); v3 = max(v3, __shfl_xor_sync(FULL, v3, 16));
+                if (half == 0)
+                    st_f4_hint(p.feats + (size_t)f_o * C + c0,
+                               make_float4(__int_as_float(v0), __int_as_float(v1), __int_as_float(v2), __int_as_float(v3)), keep_policy);
             }
             __syncwarp();
         }
@@ -755,8 +804,16 @@ k_canvas(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUten
                 const int k = half + 2 * j;
                 if (k < n_p) put(list[k].x, pre[j]);
             }
-            for (int k = half + 2 * PRE; k < n_p; k += 2)
-                put(list[k].x, ld_f4_hint(p.feats + (size_t)list[k].y * C + c0, stream_policy));
+            // more than 2*PRE pillars in the tile: the rest in batches of PRE loads, then PRE column writes
+            for (int k0 = half + 2 * PRE; k0 < n_p; k0 += 2 * PRE) {
+                float4 more[PRE];
+#pragma unroll
+                for (int j = 0; j < PRE; ++j)
+                    if (k0 + 2 * j < n_p) more[j] = ld_f4_hint(p.feats + (size_t)list[k0 + 2 * j].y * C + c0, stream_policy);
+#pragma unroll
+                for (int j = 0; j < PRE; ++j)
+                    if (k0 + 2 * j < n_p) put(list[k0 + 2 * j].x, more[j]);
+            }
             if (TMA) {
                 fence_proxy_async_smem();
                 __syncwarp();
@@ -933,18 +990,26 @@ int emit_timing_collect(float *ms, int n) {
 
 int launch_pillar_path(const PathParams &p, bool with_pfn, bool abs_xyz, bool dist, size_t zero_bytes, void *zero_base,
                        cudaStream_t stream, int *launches) {
-    int nl = 0;   // kernels only; the workspace memset below is not counted
-    cudaError_t e = cudaMemsetAsync(zero_base, 0, zero_bytes, stream);
-    if (e != cudaSuccess) return (int)e;
-    if (p.n > 0) {
-        const unsigned g = (unsigned)((p.n + 255) / 256);
-        k_count<<<g, 256, 0, stream>>>(p);
-        if ((e = cudaGetLastError()) != cudaSuccess) return (int)e;
-        k_scan<<<(unsigned)((p.n + SCAN_TILE - 1) / SCAN_TILE), SCAN_THREADS, 0, stream>>>(p);
-        if ((e = cudaGetLastError()) != cudaSuccess) return (int)e;
-        k_fill<<<g, 256, 0, stream>>>(p);
-        if ((e = cudaGetLastError()) != cudaSuccess) return (int)e;
-        nl += 3;
+    int nl = 0;
+    (void)zero_bytes; (void)zero_base;      // the cell table is zeroed by k_front itself
+    {
+        // cooperative launch: every CTA must be resident, so the grid is the occupancy limit (capped: ~4 CTAs/SM is
+        // plenty of parallelism for a latency-bound front end and keeps the grid barriers cheap)
+        static int max_ctas = []() {
+            int per_sm = 1;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_front, FRONT_THREADS, 0);
+            const char *env = getenv("HGSF_FRONT_CTAS");
+            const int cap = env ? atoi(env) : 4;
+            return sm_count() * std::max(1, std::min(per_sm, cap));
+        }();
+        const long long want = std::max<long long>(((long long)p.B * p.cells + FRONT_THREADS * 8 - 1) / (FRONT_THREADS * 8),
+                                                   ((long long)p.n + FRONT_THREADS - 1) / FRONT_THREADS);
+        const int grid = (int)std::max<long long>(1, std::min<long long>(want, max_ctas));
+        PathParams pp = p;
+        void *args[] = {&pp};
+        cudaError_t e = cudaLaunchCooperativeKernel((const void *)k_front, dim3(grid), dim3(FRONT_THREADS), args, 0, stream);
+        if (e != cudaSuccess) return (int)e;
+        ++nl;
     }
     int st = launch_pfn(p, with_pfn, abs_xyz, dist, stream);
     if (st != HGSF_OK) return st;

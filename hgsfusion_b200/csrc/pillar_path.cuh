@@ -51,7 +51,7 @@ inline WorkspaceLayout workspace_layout(int64_t n, int B, int64_t cells, int F) 
     w.scan_tiles = (int)((n + SCAN_TILE - 1) / SCAN_TILE);
     w.RW = (F + 1 + 3) / 4 * 4;   // F features + the point index
     w.off_ticket = o;      o = align_up(o + 16, 256);
-    w.off_desc = o;        o = align_up(o + sizeof(uint64_t) * (size_t)(w.scan_tiles > 0 ? w.scan_tiles : 1), 256);
+    w.off_desc = o;        o = align_up(o + sizeof(uint64_t) * 4096, 256);          // per-CTA slice totals of k_front's scan
     w.off_raw_base = o;    o = align_up(o + sizeof(int32_t) * (size_t)(B + 1), 256);
     w.off_table = o;       o = align_up(o + sizeof(CellEntry) * (size_t)B * (size_t)cells, 256);
     w.zero_bytes = o;
