@@ -744,18 +744,18 @@ k_canvas(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUten
         // ---- next tile: pillar list, its first rows on their way; entries of the tile after it ----
         const unsigned bal_n = make_list(e_next, nxt, list_n);
         float4 pre_n[PRE];
-        prefetch_rows(list_n, __popc(bal_n), pre_n);
+        if (!(p.dbg & 4)) prefetch_rows(list_n, __popc(bal_n), pre_n);
         e_next = load_entry(nxt2);
 
         const int b = cur.b, y = cur.zy, x0 = cur.xt * 32;
         if (bal == 0u) {
-            if (TMA) {
+            if (TMA && !(p.dbg & 1)) {
                 if (lane == 0) {
 #pragma unroll
                     for (int q4 = 0; q4 < 4; ++q4) tma_store_3d_hint(&zmap, zerobuf, x0, y, b * C + q4 * ZC, stream_policy);
                     tma_commit();
                 }
-            } else if (STORE == 1) {
+            } else if (STORE == 1 || (TMA && (p.dbg & 1))) {
                 // lane l: 16-byte chunk (l & 7) of channel rows (l >> 3) + 4*i
                 const int xc = x0 + 4 * (lane & 7);
                 if (xc < p.nx) {
@@ -772,11 +772,12 @@ k_canvas(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUten
             // store, from the other buffer, may still be in flight), then clear what that tile dirtied
             float *tile = tile_base + (nb & 1) * TILE;
             unsigned dirty = (nb & 1) ? dirty1 : dirty0;
-            if (TMA) {
+            if (TMA && !(p.dbg & 16)) {
                 if (lane == 0) tma_wait_read<1>();
                 __syncwarp();
             }
-            if (__popc(dirty) > 2) {
+            if (p.dbg & 16) {
+            } else if (__popc(dirty) > 2) {
 #pragma unroll
                 for (int t = 0; t < TILE / 128; ++t) *reinterpret_cast<float4 *>(tile + t * 128 + lane * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
             } else {
@@ -799,13 +800,15 @@ k_canvas(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUten
                 t0[2 * 32 + ((xq ^ ((c0 + 2) & 7)) << 2)] = v.z;
                 t0[3 * 32 + ((xq ^ ((c0 + 3) & 7)) << 2)] = v.w;
             };
+            if (!(p.dbg & 2)) {
 #pragma unroll
             for (int j = 0; j < PRE; ++j) {
                 const int k = half + 2 * j;
                 if (k < n_p) put(list[k].x, pre[j]);
             }
+            }
             // more than 2*PRE pillars in the tile: the rest in batches of PRE loads, then PRE column writes
-            for (int k0 = half + 2 * PRE; k0 < n_p; k0 += 2 * PRE) {
+            for (int k0 = half + 2 * PRE; k0 < n_p && !(p.dbg & 2); k0 += 2 * PRE) {
                 float4 more[PRE];
 #pragma unroll
                 for (int j = 0; j < PRE; ++j)
@@ -817,7 +820,15 @@ k_canvas(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUten
             if (TMA) {
                 fence_proxy_async_smem();
                 __syncwarp();
-                if (lane == 0) { tma_store_3d_hint(&tmap, tile, x0, y, b * C, stream_policy); tma_commit(); }
+                if (lane == 0) {
+                    if (p.dbg & 8) {
+#pragma unroll
+                        for (int q4 = 0; q4 < 4; ++q4) tma_store_3d_hint(&zmap, tile + q4 * ZC * 32, x0, y, b * C + q4 * ZC, stream_policy);
+                    } else {
+                        tma_store_3d_hint(&tmap, tile, x0, y, b * C, stream_policy);
+                    }
+                    tma_commit();
+                }
             } else if (STORE == 1) {
                 __syncwarp();
                 const int xc = x0 + 4 * (lane & 7);
@@ -928,6 +939,7 @@ static int launch_pfn(const PathParams &p, bool with_pfn, bool abs_xyz, bool dis
 
 static int launch_canvas(const PathParams &p, cudaStream_t stream) {
     constexpr int C = 64;
+    const_cast<PathParams &>(p).dbg = getenv("HGSF_DBG") ? atoi(getenv("HGSF_DBG")) : 0;
     const bool vec_ok = (p.nx % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.canvas) & 15) == 0);
     // HGSF_CANVAS_STORE=tma|vec picks the tile store for experiments; default below
     const char *env = getenv("HGSF_CANVAS_STORE");

@@ -26,6 +26,7 @@ struct PathParams {
     float *sorted_rows;                // [n, RW] F features + point index of each point, grouped by pillar (CSR order)
     int4 *prec;                        // [n] per raw pillar id: {CSR start, arrivals, b<<16|z, y<<16|x}
     int RW;
+    int dbg;                           // experiment switches (HGSF_DBG), 0 in normal use
     // ---- PFN ----
     const float *W, *bias, *bn_w, *bn_b, *bn_m, *bn_v;
     float eps;
