@@ -101,7 +101,6 @@ static int run_path(const hgsf_geometry *g, const hgsf_points *pt, const hgsf_pf
         const int cin = (abs_xyz ? p.F : p.F - 3) + 6 + (dist ? 1 : 0);
         if (cin != pfn->in_channels) return HGSF_ERR_INVALID_ARG;
         if (out->spatial_features && g->grid[2] != 1) return HGSF_ERR_INVALID_ARG;   // PointPillarScatter asserts nz == 1
-        if (!out->pillar_features) return HGSF_ERR_INVALID_ARG;                       // the canvas is built from the pillar rows
         p.W = pfn->weight; p.bias = pfn->bias; p.bn_w = pfn->bn_weight; p.bn_b = pfn->bn_bias;
         p.bn_m = pfn->bn_mean; p.bn_v = pfn->bn_var; p.eps = pfn->bn_eps;
         p.Cin = cin; p.C = pfn->out_channels;

@@ -115,7 +115,9 @@ template <int NWARPS, bool TMA>
 __global__ void __launch_bounds__(NWARPS * 32) k_scatter_canvas(const __grid_constant__ CUtensorMap tmap, const ScatterParams q) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const int C = q.C, TILE = C * 32, NT = NWARPS * 32;
-    float *tilebuf = reinterpret_cast<float *>(smem_raw);   // [2][TILE]
+    // the TMA swizzle works on absolute shared-memory address bits: start the tiles on a 1024-byte boundary
+    uint8_t *smem_al = smem_raw + ((1024u - ((uint32_t)__cvta_generic_to_shared(smem_raw) & 1023u)) & 1023u);
+    float *tilebuf = reinterpret_cast<float *>(smem_al);    // [2][TILE]
     float *zerobuf = tilebuf + 2 * TILE;
     __shared__ int s_nocc[2], s_cell[2][32], s_m[2][32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -202,7 +204,7 @@ int launch_scatter(const ScatterParams &q, cudaStream_t stream, int *launches) {
         const int st = make_canvas_map(&map, q.canvas, q.B, q.C, q.ny, q.nx, q.C);
         if (st != HGSF_OK) return st;
     }
-    const size_t smem = sizeof(float) * 3 * (size_t)q.C * 32;
+    const size_t smem = 1024 + sizeof(float) * 3 * (size_t)q.C * 32;
     const long long n_tiles = (long long)q.B * q.ny * ((q.nx + 31) / 32);
     if (n_tiles > 0) {
         auto go = [&](auto kern) -> int {

@@ -40,11 +40,14 @@ namespace hgsf {
 // k_front : ONE cooperative kernel for the whole front end (grid barriers instead of launches)
 //   phase 0  zero the cell table
 //   phase 1  count : 1 thread / point.  cell key; per cell min point index + count through warp-aggregated atomics
-//   phase 2  scan  : exclusive prefix over POINTS of (is-first-of-its-cell, that cell's count).  At a first point the
-//                    prefix is (raw pillar id, CSR start): pillar ids come out in first-seen order without a sort.
-//                    Two level: every CTA reduces its contiguous slice, barrier, then scans it with the sum of the
-//                    slices before it as carry-in.  Also writes the pillar records and the raw id at each frame start.
-//   phase 3  fill  : 1 thread / point: copies the point's features (+ its index) to its pillar's CSR segment
+//   phase 2  two scans, each two level (every CTA reduces its contiguous slice, barrier, then scans it with the sum of
+//            the slices before it as carry-in):
+//            (a) over POINTS, of "is the first point of its cell": the exclusive prefix at a first point is the raw
+//                pillar id -> pillar ids come out in first-seen order without a sort.  Also writes the pillar records
+//                and the raw id at each frame start.
+//            (b) over CELLS in table order (b, z, y, x), of the cell counts: the exclusive prefix is the cell's CSR
+//                start -> the point rows of a 32-cell canvas tile are CONTIGUOUS in sorted_rows.
+//   phase 3  fill  : 1 thread / point: copies the point's features (+ its index) to its cell's CSR segment
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ int find_frame(const int32_t *__restrict__ off, int B, int i) {
     // largest b in [0, B) with off[b] <= i  (frames are contiguous; empty frames are skipped)
@@ -205,6 +208,23 @@ __global__ void __launch_bounds__(FRONT_THREADS) k_front(const PathParams p) {
         const uint64_t total = block_sum(mine, s_warp, lane, warp);
         if (tid == 0) p.scan_desc[blockIdx.x] = total;
     }
+    // (b) cells: CTA c owns cells [clo, chi), a whole number of 1024-cell tiles
+    const long long n_cells = (long long)p.B * p.cells;
+    const long long ctiles_total = (n_cells + SCAN_TILE - 1) / SCAN_TILE;
+    const long long ctiles_per_cta = (ctiles_total + gridDim.x - 1) / gridDim.x;
+    const long long clo = min((long long)blockIdx.x * ctiles_per_cta, ctiles_total) * SCAN_TILE;
+    const long long chi = min(((long long)blockIdx.x + 1) * ctiles_per_cta, ctiles_total) * SCAN_TILE;
+    {
+        uint64_t mine = 0;
+        for (long long t0 = clo; t0 < chi; t0 += SCAN_TILE)
+#pragma unroll
+            for (int j = 0; j < SCAN_ITEMS; ++j) {
+                const long long c = t0 + tid * SCAN_ITEMS + j;
+                if (c < n_cells) mine += p.table[c].cnt;
+            }
+        const uint64_t total = block_sum(mine, s_warp, lane, warp);
+        if (tid == 0) p.scan_desc[2048 + blockIdx.x] = total;
+    }
     grid.sync();
     stamp(3);
     {
@@ -236,19 +256,18 @@ __global__ void __launch_bounds__(FRONT_THREADS) k_front(const PathParams p) {
             uint64_t run = carry + warp_off + (incl - local);
 #pragma unroll
             for (int j = 0; j < SCAN_ITEMS; ++j) {
-                const uint32_t pillars = (uint32_t)(run >> 32), points = (uint32_t)run;
+                const uint32_t pillars = (uint32_t)(run >> 32);
                 s_excl[tid * SCAN_ITEMS + j] = pillars;
                 if (flag[j]) {
                     CellEntry *e = p.table + keys[j];
                     e->tag = pillars + 1u;     // raw pillar id + 1 (disjoint from the 0xFFFFFFFF-i values phase 1 left)
-                    e->start = points;
                     // the pillar's record, in first-seen order (one thread per pillar pays the divisions)
                     const int key = keys[j];
                     const int b = key / p.cells, rem = key - b * p.cells;
                     const int plane = p.ny * p.nx;
                     const int z = rem / plane, rem2 = rem - z * plane;
                     const int y = rem2 / p.nx, x = rem2 - y * p.nx;
-                    p.prec[pillars] = make_int4((int)points, (int)cnt[j], (b << 16) | z, (y << 16) | x);
+                    p.prec[pillars] = make_int4(key, (int)cnt[j], (b << 16) | z, (y << 16) | x);
                 }
                 run += pack2(flag[j], cnt[j]);
             }
@@ -265,6 +284,41 @@ __global__ void __launch_bounds__(FRONT_THREADS) k_front(const PathParams p) {
         }
         if (p.n == 0 && blockIdx.x == 0)
             for (int b = tid; b <= p.B; b += FRONT_THREADS) p.frame_raw_base[b] = 0;
+    }
+    {
+        // (b) cells: CSR start of every cell (empty ones too: a tile's row span is start[first cell] .. start[last]+cnt)
+        uint64_t before = 0;
+        for (int c = tid; c < (int)blockIdx.x; c += FRONT_THREADS) before += p.scan_desc[2048 + c];
+        uint32_t carry = (uint32_t)block_sum(before, s_warp, lane, warp);
+        for (long long t0 = clo; t0 < chi; t0 += SCAN_TILE) {
+            const long long c0 = t0 + tid * SCAN_ITEMS;
+            uint32_t cn[SCAN_ITEMS], local = 0;
+#pragma unroll
+            for (int j = 0; j < SCAN_ITEMS; ++j) { cn[j] = (c0 + j < n_cells) ? p.table[c0 + j].cnt : 0u; local += cn[j]; }
+            uint32_t incl = local;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t o = __shfl_up_sync(FULL, incl, d);
+                if (lane >= d) incl += o;
+            }
+            __syncthreads();
+            if (lane == 31) s_warp[warp] = incl;
+            __syncthreads();
+            uint32_t warp_off = 0, tile_total = 0;
+#pragma unroll
+            for (int w = 0; w < FRONT_THREADS / 32; ++w) {
+                const uint32_t v = (uint32_t)s_warp[w];
+                if (w < warp) warp_off += v;
+                tile_total += v;
+            }
+            uint32_t run = carry + warp_off + (incl - local);
+#pragma unroll
+            for (int j = 0; j < SCAN_ITEMS; ++j) {
+                if (c0 + j < n_cells) p.table[c0 + j].start = run;
+                run += cn[j];
+            }
+            carry += tile_total;
+        }
     }
     grid.sync();
     stamp(4);
@@ -470,7 +524,8 @@ __global__ void __launch_bounds__(PFN_THREADS, 4) k_pfn(const PathParams p) {
         const int m = ch * 32 + lane;
         int4 pr = make_int4(0, 0, 0, 0);
         if (m < m_raw) pr = __ldg(p.prec + m);
-        const int start = pr.x, cnt = pr.y, pb = pr.z >> 16, pz = pr.z & 0xFFFF, py = pr.w >> 16, px = pr.w & 0xFFFF;
+        const int cnt = pr.y, pb = pr.z >> 16, pz = pr.z & 0xFFFF, py = pr.w >> 16, px = pr.w & 0xFFFF;
+        const int start = (m < m_raw) ? (int)__ldg(&p.table[pr.x].start) : 0;   // CSR start of the pillar's cell
         const int local = m - s_R[pb];
         const bool kept = (m < m_raw) && (local < maxv);      // pillars beyond max_voxels were never created
         const int f = s_K[pb] + local;                          // final pillar id (first-seen order, frames concatenated)
@@ -641,65 +696,192 @@ __global__ void __launch_bounds__(PFN_THREADS, 4) k_pfn(const PathParams p) {
     }
 }
 
-// ---- k_canvas -----------------------------------------------------------------------------------
-// Tile major.  Every warp is an autonomous worker walking its own sequence of canvas tiles (a tile = 32 cells of
-// one BEV row x all C channels = C rows of 128 B) with its own 8 KB tile buffer: cell table entries (prefetched one
-// tile ahead) -> final pillar ids -> pillar_features rows (256 B each, straight from L2) -> tile columns -> ONE TMA
-// tensor store per tile (128-byte swizzle, so the column writes spread over banks).  Empty tiles are four stores
-// of a shared 2 KB zero tile and cost the SM nothing.  The canvas is written exactly once, zeros included.
-constexpr int CANVAS_WARPS = 4;
-constexpr int CANVAS_THREADS = CANVAS_WARPS * 32;
+// ---- k_emit -------------------------------------------------------------------------------------
+// The fused kernel (used whenever the canvas is requested): order + decorate + PFN + max AND the canvas tile, one pass.
+// Every WARP is an autonomous worker walking its own sequence of canvas tiles (a tile = 32 cells of one BEV row x 64
+// channels = 64 rows of 128 B); no CTA barrier in the loop.  Because k_front laid the CSR out in cell order, the point
+// rows of a tile are ONE contiguous span of sorted_rows: they are staged with a single cooperative cp.async copy issued
+// a tile ahead, from table entries loaded two tiles ahead -- no dependent gathers anywhere.
+//   lane l OWNS cell l of the tile for the bookkeeping (ordering by point index, first P kept, mean in torch's
+//   summation order, voxel_coords / voxel_num_points);
+//   the arithmetic is cut into UNITS of (pillar, 4 output channels): lane l always computes channels 4*(l&15)..+3, so
+//   its Linear weight float4s and BatchNorm constants stay in REGISTERS for the whole kernel (CUDA-core FMA: a 13x64
+//   contraction is far below a tensor-core tile).  Single-point pillars are paired across the half-warps; a
+//   multi-point pillar is taken by both halves, which split its points and max-combine.
+//   A finished tile leaves in ONE TMA tensor store (128-byte swizzle so the column writes spread over banks); an
+//   empty tile is four stores of a shared 2 KB zero tile.  The canvas is written exactly once, zeros included.
+constexpr int EMIT_WARPS = 4;
+constexpr int EMIT_THREADS = EMIT_WARPS * 32;
+constexpr int STAGE_W = 64;           // staged point rows per tile (a typical tile holds ~10; the rest is read from L2)
 
-// STORE selects how a finished tile leaves the SM: 0 = one TMA tensor store, 1 = coalesced 16-byte global stores
-// (4 channel rows x 128 B per warp instruction), 2 = 4-byte stores (row pitch not a multiple of 16 bytes)
-template <int C, int STORE>
-__global__ void __launch_bounds__(CANVAS_THREADS)
-k_canvas(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap zmap, const PathParams p) {
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int F, bool ABS, bool DIST, bool BN, int STORE>
+__global__ void __launch_bounds__(EMIT_THREADS, 3)
+k_emit(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap zmap, const PathParams p) {
+    constexpr int C = 64;
+    constexpr int CIN = (ABS ? F : F - 3) + 6 + (DIST ? 1 : 0);
+    constexpr int RWc = (F + 1 + 3) / 4 * 4;   // F features + the point index, padded to float4
+    constexpr int NV = RWc / 4;
     constexpr int TILE = C * 32;
     constexpr int ZC = C / 4;
-    static_assert(C == 64, "a unit is 4 of 64 channels");
     constexpr bool TMA = (STORE == 0);
+    constexpr int NT = EMIT_THREADS;
+
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    float *tiles = reinterpret_cast<float *>(smem_raw);                    // [CANVAS_WARPS][2][TILE] double buffered
-    float *zerobuf = tiles + CANVAS_WARPS * 2 * TILE;                          // [ZC*32]
-    int *s_R = reinterpret_cast<int *>(zerobuf + ZC * 32);                 // [B+1]
-    int *s_K = s_R + (p.B + 1);                                            // [B+1]
-    __shared__ int2 s_list_all[CANVAS_WARPS][64];                          // (cell, final pillar id) of this / the next tile's pillars
+    // the TMA swizzle works on absolute shared-memory address bits: the tiles must start on a 1024-byte boundary
+    // (static shared memory in front of the dynamic part can shift it; the launcher reserves the slack)
+    uint8_t *smem_al = smem_raw + ((1024u - ((uint32_t)__cvta_generic_to_shared(smem_raw) & 1023u)) & 1023u);
+    float *tiles = reinterpret_cast<float *>(smem_al);                     // [EMIT_WARPS][TILE]
+    float *zerobuf = tiles + EMIT_WARPS * TILE;                            // [ZC*32]
+    float *stage_all = zerobuf + ZC * 32;                                  // [EMIT_WARPS][2][STAGE_W * RWc]
+    int *s_R = reinterpret_cast<int *>(stage_all + EMIT_WARPS * 2 * STAGE_W * RWc);   // [B+1] raw pillar base per frame
+    int *s_K = s_R + (p.B + 1);                                            // [B+1] kept (final) pillar base per frame
+    __shared__ float4 s_rec_all[EMIT_WARPS][32][2];                        // work lists: singles from the front, multis from the back
+    __shared__ unsigned char s_perm_all[EMIT_WARPS][32][32];               // per cell: arrival position of its rank-th point
+    __shared__ int s_bperm_all[EMIT_WARPS][32];                            // same for a pillar with > 32 arrivals
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    float *tile_base = tiles + warp * 2 * TILE;
-    for (int b = tid; b <= p.B; b += CANVAS_THREADS) s_R[b] = p.frame_raw_base[b];
-    for (int t = tid; t < ZC * 32; t += CANVAS_THREADS) zerobuf[t] = 0.f;
-    for (int t = tid; t < CANVAS_WARPS * 2 * TILE; t += CANVAS_THREADS) tiles[t] = 0.f;
+    float *tile = tiles + warp * TILE;
+    float *stage = stage_all + (size_t)warp * 2 * STAGE_W * RWc;
+    float4(*rec)[2] = s_rec_all[warp];
+    unsigned char(*perm)[32] = s_perm_all[warp];
+    int *bperm = s_bperm_all[warp];
+
+    // ---- one-time setup (the only CTA barriers) ----
+    for (int b = tid; b <= p.B; b += NT) s_R[b] = p.frame_raw_base[b];
+    for (int t = tid; t < ZC * 32; t += NT) zerobuf[t] = 0.f;
+    for (int t = tid; t < EMIT_WARPS * TILE; t += NT) tiles[t] = 0.f;
     __syncthreads();
     if (tid == 0) {
         int acc = 0;
-        for (int b = 0; b < p.B; ++b) { s_K[b] = acc; acc += min(s_R[b + 1] - s_R[b], p.max_voxels); }
+        for (int b = 0; b < p.B; ++b) {
+            s_K[b] = acc;
+            const int m = min(s_R[b + 1] - s_R[b], p.max_voxels);
+            if (blockIdx.x == 0) p.num_pillars[1 + b] = m;
+            acc += m;
+        }
         s_K[p.B] = acc;
+        if (blockIdx.x == 0) p.num_pillars[0] = acc;
     }
     if (TMA) fence_proxy_async_smem();
     __syncthreads();
 
+    // this lane's 4 channels: Linear rows and BatchNorm constants, in registers for the whole kernel
+    const int c0 = 4 * (lane & 15);
+    const int half = lane >> 4;
+    float4 w4[CIN];
+    float4 mu = make_float4(0.f, 0.f, 0.f, 0.f), iv = mu, ga = mu, be = mu, pv = mu;
+    {
+#pragma unroll
+        for (int k = 0; k < CIN; ++k)
+            w4[k] = make_float4(__ldg(p.W + (c0 + 0) * CIN + k), __ldg(p.W + (c0 + 1) * CIN + k),
+                                __ldg(p.W + (c0 + 2) * CIN + k), __ldg(p.W + (c0 + 3) * CIN + k));
+        float bnv[5][4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int c = c0 + j;
+            float y;
+            if (BN) {
+                bnv[0][j] = __ldg(p.bn_m + c);
+                bnv[1][j] = __frcp_rn(__fsqrt_rn(__fadd_rn(__ldg(p.bn_v + c), p.eps)));
+                bnv[2][j] = __ldg(p.bn_w + c);
+                bnv[3][j] = __ldg(p.bn_b + c);
+                // a zero (padded) row still goes through BN + ReLU and joins the max (pillar_vfe.py:37-42)
+                y = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(0.f, bnv[0][j]), bnv[1][j]), bnv[2][j]), bnv[3][j]);
+            } else {
+                bnv[0][j] = bnv[1][j] = bnv[2][j] = 0.f;
+                bnv[3][j] = __ldg(p.bias + c);
+                y = __fadd_rn(0.f, bnv[3][j]);
+            }
+            bnv[4][j] = (y > 0.f || y != y) ? y : 0.f;
+        }
+        mu = make_float4(bnv[0][0], bnv[0][1], bnv[0][2], bnv[0][3]); iv = make_float4(bnv[1][0], bnv[1][1], bnv[1][2], bnv[1][3]);
+        ga = make_float4(bnv[2][0], bnv[2][1], bnv[2][2], bnv[2][3]); be = make_float4(bnv[3][0], bnv[3][1], bnv[3][2], bnv[3][3]);
+        pv = make_float4(bnv[4][0], bnv[4][1], bnv[4][2], bnv[4][3]);
+    }
+
     const int tiles_per_row = (p.nx + 31) >> 5;
     const int rows_per_frame = p.ny;                       // nz == 1 (PointPillarScatter asserts it)
     const int n_rows = p.B * rows_per_frame;
-    const int maxv = p.max_voxels;
+    const int P4 = (p.P >> 2) << 2;
+    const int maxv = p.max_voxels, Pmax = p.P;
+    const float vsx = p.vsize[0], vsy = p.vsize[1], vox = p.voff[0], voy = p.voff[1];
+    const float cz = __fadd_rn(__fmul_rn(0.f, p.vsize[2]), p.voff[2]);     // z index 0: fl(fl(0*vz)+z_off)
     const CellEntry *__restrict__ table = p.table;
+    const float *__restrict__ grows = p.sorted_rows;
     const unsigned lt = (1u << lane) - 1u;
-    // lane-constant part of the swizzled tile address of channel c0+j, cell x:
-    //   (c0+j)*32 + ((( x>>2 ) ^ ((c0+j)&7)) << 2 | (x&3))
-    const int c0 = 4 * (lane & 15);
-    const int half = lane >> 4;
+    const uint64_t stream_policy = l2_policy_evict_first();   // canvas: written once, never re-read here
 
+    // one point through decorate + Linear + BN, folded into the running max (integer max on the float bits: exact for
+    // the non-negative post-ReLU values, drops negatives and -0 = the ReLU, lets a NaN 0x7fffffff win as torch.max does)
+    auto eval_row = [&](const float (&row)[RWc], float mx, float my, float mz, float cx, float cy,
+                        int &v0, int &v1, int &v2, int &v3) {
+        float feat[CIN];
+        {
+            int kf = 0;
+#pragma unroll
+            for (int q = ABS ? 0 : 3; q < F; ++q) feat[kf++] = row[q];
+            feat[kf++] = __fsub_rn(row[0], mx); feat[kf++] = __fsub_rn(row[1], my); feat[kf++] = __fsub_rn(row[2], mz);
+            feat[kf++] = __fsub_rn(row[0], cx); feat[kf++] = __fsub_rn(row[1], cy); feat[kf++] = __fsub_rn(row[2], cz);
+            // torch.norm(xyz, 2, 2) on the CPU: sqrt(fma(z,z, fma(y,y, x*x)))  (pillar_vfe.py:110-112)
+            if (DIST) feat[kf++] = __fsqrt_rn(fmaf(row[2], row[2], fmaf(row[1], row[1], __fmul_rn(row[0], row[0]))));
+        }
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+        for (int kk = 0; kk < CIN; ++kk) {     // Linear: sequential FMA in k order (pillar_vfe.py:37)
+            a0 = fmaf(feat[kk], w4[kk].x, a0); a1 = fmaf(feat[kk], w4[kk].y, a1);
+            a2 = fmaf(feat[kk], w4[kk].z, a2); a3 = fmaf(feat[kk], w4[kk].w, a3);
+        }
+        float y0, y1, y2, y3;
+        if (BN) {                              // BN eval: (((x-mean)*invstd)*gamma)+beta, 4 roundings (:39)
+            y0 = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(a0, mu.x), iv.x), ga.x), be.x);
+            y1 = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(a1, mu.y), iv.y), ga.y), be.y);
+            y2 = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(a2, mu.z), iv.z), ga.z), be.z);
+            y3 = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(a3, mu.w), iv.w), ga.w), be.w);
+        } else {
+            y0 = __fadd_rn(a0, be.x); y1 = __fadd_rn(a1, be.y); y2 = __fadd_rn(a2, be.z); y3 = __fadd_rn(a3, be.w);
+        }
+        v0 = max(v0, __float_as_int(y0)); v1 = max(v1, __float_as_int(y1));
+        v2 = max(v2, __float_as_int(y2)); v3 = max(v3, __float_as_int(y3));
+    };
+    // a point row: from the staging buffer (rel >= 0: row index in it) or from global memory (rel < 0: -1 - CSR row)
+    auto load_row = [&](const float *stg, int rel, int pos, float (&row)[RWc]) {
+        if (rel >= 0) {
+            const float4 *r4 = reinterpret_cast<const float4 *>(stg + (size_t)(rel + pos) * RWc);
+#pragma unroll
+            for (int v = 0; v < NV; ++v) { const float4 t4 = r4[v]; row[4 * v] = t4.x; row[4 * v + 1] = t4.y; row[4 * v + 2] = t4.z; row[4 * v + 3] = t4.w; }
+        } else {
+            const float4 *r4 = reinterpret_cast<const float4 *>(grows + (size_t)(-1 - rel + pos) * RWc);
+#pragma unroll
+            for (int v = 0; v < NV; ++v) { const float4 t4 = __ldg(r4 + v); row[4 * v] = t4.x; row[4 * v + 1] = t4.y; row[4 * v + 2] = t4.z; row[4 * v + 3] = t4.w; }
+        }
+    };
+    auto put_tile = [&](int cell, int v0, int v1, int v2, int v3) {
+        const int xq = cell >> 2, xr = cell & 3;
+        float *t0 = tile + c0 * 32 + xr;
+        t0[0 * 32 + ((xq ^ ((c0 + 0) & 7)) << 2)] = __int_as_float(v0);
+        t0[1 * 32 + ((xq ^ ((c0 + 1) & 7)) << 2)] = __int_as_float(v1);
+        t0[2 * 32 + ((xq ^ ((c0 + 2) & 7)) << 2)] = __int_as_float(v2);
+        t0[3 * 32 + ((xq ^ ((c0 + 3) & 7)) << 2)] = __int_as_float(v3);
+    };
+
+    // this warp's tile sequence: first tile blockIdx*W + warp, stride gridDim*W; stepping is division free
     TileStep step;
     step.tiles_per_row = tiles_per_row; step.rows_per_frame = rows_per_frame;
     {
-        const int stride_tiles = (int)gridDim.x * CANVAS_WARPS;
+        const int stride_tiles = (int)gridDim.x * EMIT_WARPS;
         step.dr = stride_tiles / tiles_per_row; step.dxt = stride_tiles - step.dr * tiles_per_row;
     }
     TilePos cur;
     {
-        const int t0 = (int)blockIdx.x * CANVAS_WARPS + warp;     // the only divisions: where this warp starts
+        const int t0 = (int)blockIdx.x * EMIT_WARPS + warp;      // the only divisions: where this warp starts
         cur.r = t0 / tiles_per_row; cur.xt = t0 - cur.r * tiles_per_row;
         cur.b = cur.r / rows_per_frame; cur.zy = cur.r - cur.b * rows_per_frame;
     }
@@ -707,57 +889,51 @@ k_canvas(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUten
     step.advance(nxt);
     TilePos nxt2 = nxt;
     step.advance(nxt2);
-    auto load_entry = [&](const TilePos &t) -> uint2 {
+    auto load_entry = [&](const TilePos &t) -> uint4 {
         const int x = t.xt * 32 + lane;
-        return (t.r < n_rows && x < p.nx) ? __ldg(reinterpret_cast<const uint2 *>(table + (size_t)t.r * p.nx + x)) : make_uint2(0, 0);
+        // row r = b*ny + y and the table is [b][y][x]: the cell index is r*nx + x
+        return (t.r < n_rows && x < p.nx) ? __ldg(reinterpret_cast<const uint4 *>(table + (size_t)t.r * p.nx + x))
+                                          : make_uint4(0, 0, 0, 0);
     };
-    const uint64_t stream_policy = l2_policy_evict_first();   // canvas: written once, never re-read here
-    // a tile's pillar list (cell, final id) from its table entries; returns the occupancy mask
-    auto make_list = [&](const uint2 ent, const TilePos &t, int2 *lst) -> unsigned {
-        const int bb = (t.r < n_rows) ? t.b : 0;
-        const int local = (int)(ent.x - 1u) - s_R[bb];
-        const bool occ = (ent.x != 0u) && (local < maxv);
-        const unsigned bal = __ballot_sync(FULL, occ);
-        if (occ) lst[__popc(bal & lt)] = make_int2(lane, s_K[bb] + local);
-        __syncwarp();
-        return bal;
-    };
-    constexpr int PRE = 4;              // pillar rows prefetched per half-warp for the next tile (covers 8 pillars)
-    auto prefetch_rows = [&](const int2 *lst, int n_p, float4 (&pre)[PRE]) {
+    // the tile's rows are sorted_rows[row0, row0 + total): one cooperative async copy of (at most STAGE_W of) them
+    auto issue_stage = [&](const uint4 e, float *stg) {
+        const int row0 = __shfl_sync(FULL, (int)e.z, 0);
+        int total = (int)e.y;
 #pragma unroll
-        for (int j = 0; j < PRE; ++j) {
-            const int k = half + 2 * j;
-            if (k < n_p) pre[j] = ld_f4_hint(p.feats + (size_t)lst[k].y * C + c0, stream_policy);
-        }
+        for (int d = 16; d > 0; d >>= 1) total += __shfl_xor_sync(FULL, total, d);
+        const int chunks = min(total, STAGE_W) * NV;
+        const float *src = grows + (size_t)row0 * RWc;
+        for (int c = lane; c < chunks; c += 32) cp_async16(stg + 4 * c, src + 4 * c);
+        cp_async_commit();
     };
 
-    int2 *list0 = s_list_all[warp], *list1 = s_list_all[warp] + 32;
-    unsigned bal = make_list(load_entry(cur), cur, list0);
-    float4 pre[PRE];
-    prefetch_rows(list0, __popc(bal), pre);
-    uint2 e_next = load_entry(nxt);
-    unsigned dirty0 = 0u, dirty1 = 0u;   // cells of each tile buffer that hold non-zero columns
-    int nb = 0;                          // non-empty tiles so far: selects the tile buffer
+    uint4 e_cur = load_entry(cur);
+    issue_stage(e_cur, stage);
+    uint4 e_nxt = load_entry(nxt);
+    unsigned dirty = 0;                  // cells of the tile buffer that hold non-zero columns
+    bool store_pending = false;          // a TMA store from the tile buffer may still be reading it
 
-    for (int it = 0; cur.r < n_rows; ++it, cur = nxt, nxt = nxt2, step.advance(nxt2)) {
-        int2 *list = (it & 1) ? list1 : list0, *list_n = (it & 1) ? list0 : list1;
-        // ---- next tile: pillar list, its first rows on their way; entries of the tile after it ----
-        const unsigned bal_n = make_list(e_next, nxt, list_n);
-        float4 pre_n[PRE];
-        if (!(p.dbg & 4)) prefetch_rows(list_n, __popc(bal_n), pre_n);
-        e_next = load_entry(nxt2);
+    for (int it = 0; cur.r < n_rows; ++it) {
+        const float *stg = stage + (size_t)(it & 1) * STAGE_W * RWc;
+        // ---- pipeline: entries of the tile after next, rows of the next tile ----
+        const uint4 e_nn = load_entry(nxt2);
+        issue_stage(e_nxt, stage + (size_t)((it + 1) & 1) * STAGE_W * RWc);
 
         const int b = cur.b, y = cur.zy, x0 = cur.xt * 32;
-        if (bal == 0u) {
-            if (TMA && !(p.dbg & 1)) {
+        const int m = (int)(e_cur.x - 1u), cnt = (int)e_cur.y, start = (int)e_cur.z;
+        const int local = m - s_R[b];
+        const bool occ = (e_cur.x != 0u) && (local < maxv);     // pillars beyond max_voxels were never created
+        const unsigned bal_occ = __ballot_sync(FULL, occ);
+        if (bal_occ == 0u) {
+            // empty tile: four stores of the shared zero tile
+            if (TMA) {
                 if (lane == 0) {
 #pragma unroll
                     for (int q4 = 0; q4 < 4; ++q4) tma_store_3d_hint(&zmap, zerobuf, x0, y, b * C + q4 * ZC, stream_policy);
                     tma_commit();
                 }
-            } else if (STORE == 1 || (TMA && (p.dbg & 1))) {
-                // lane l: 16-byte chunk (l & 7) of channel rows (l >> 3) + 4*i
-                const int xc = x0 + 4 * (lane & 7);
+            } else if (STORE == 1) {
+                const int xc = x0 + 4 * (lane & 7);      // lane l: 16-byte chunk (l & 7) of channel rows (l >> 3) + 4*i
                 if (xc < p.nx) {
                     float *dst = p.canvas + (((size_t)b * C + (lane >> 3)) * p.ny + y) * p.nx + xc;
                     const size_t plane4 = (size_t)4 * p.ny * p.nx;
@@ -768,16 +944,82 @@ k_canvas(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUten
                 for (int ch = 0; ch < C; ++ch) p.canvas[(((size_t)b * C + ch) * p.ny + y) * p.nx + x0 + lane] = 0.f;
             }
         } else {
-            // this tile's buffer: wait until the store issued from it two tiles ago has read it (the most recent
-            // store, from the other buffer, may still be in flight), then clear what that tile dirtied
-            float *tile = tile_base + (nb & 1) * TILE;
-            unsigned dirty = (nb & 1) ? dirty1 : dirty0;
-            if (TMA && !(p.dbg & 16)) {
-                if (lane == 0) tma_wait_read<1>();
-                __syncwarp();
+            const int row0 = __shfl_sync(FULL, start, 0);
+            const int rel0 = start - row0;
+            const bool staged = occ && cnt <= 32 && rel0 + cnt <= STAGE_W;
+            const int rel = staged ? rel0 : (-1 - start);         // where the pillar's rows are (see load_row)
+            const int n_keep = min(cnt, Pmax);
+            const int f = s_K[b] + local;                          // final pillar id (first-seen order, frames concatenated)
+            if (occ) {
+                p.num[f] = n_keep;
+                *reinterpret_cast<int4 *>(p.coords + 4 * (size_t)f) = make_int4(b, 0, y, x0 + lane);
             }
-            if (p.dbg & 16) {
-            } else if (__popc(dirty) > 2) {
+            cp_async_wait<1>();          // this tile's rows have landed (this lane's copies) ...
+            __syncwarp();                // ... and every other lane's
+            // ---- order the pillar's points by input index ----
+            if (occ && cnt > 1 && cnt <= SMALL_CNT) {
+                uint32_t idx[SMALL_CNT];
+#pragma unroll
+                for (int j = 0; j < SMALL_CNT; ++j) {
+                    idx[j] = 0xFFFFFFFFu;
+                    if (j < cnt) idx[j] = staged ? __float_as_uint(stg[(size_t)(rel + j) * RWc + F])
+                                                 : __float_as_uint(__ldg(grows + (size_t)(start + j) * RWc + F));
+                }
+#pragma unroll
+                for (int j = 0; j < SMALL_CNT; ++j) {
+                    int rank = 0;
+#pragma unroll
+                    for (int q = 0; q < SMALL_CNT; ++q) rank += (idx[q] < idx[j]) ? 1 : 0;
+                    if (j < cnt) perm[lane][rank] = (unsigned char)j;
+                }
+            }
+            unsigned coop = __ballot_sync(FULL, occ && cnt > SMALL_CNT && cnt <= 32);   // the warp ranks these one at a time
+            while (coop) {
+                const int o = __ffs(coop) - 1;
+                coop &= coop - 1;
+                const int cnt_o = __shfl_sync(FULL, cnt, o), rel_o = __shfl_sync(FULL, rel, o);
+                uint32_t mine = 0xFFFFFFFFu;
+                if (lane < cnt_o) mine = (rel_o >= 0) ? __float_as_uint(stg[(size_t)(rel_o + lane) * RWc + F])
+                                                      : __float_as_uint(__ldg(grows + (size_t)(-1 - rel_o + lane) * RWc + F));
+                int rank = 0;
+                for (int q = 0; q < cnt_o; ++q) rank += (__shfl_sync(FULL, mine, q) < mine) ? 1 : 0;
+                if (lane < cnt_o) perm[o][rank] = (unsigned char)lane;
+            }
+            __syncwarp();
+            // ---- mean of the kept points (torch CPU sum order) by the owning lane; the two work lists ----
+            const bool live = occ && cnt <= 32;
+            float mx = 0.f, my = 0.f, mz = 0.f;
+            if (live) {
+                float row[RWc];
+                if (cnt == 1) {
+                    load_row(stg, rel, 0, row);
+                    mx = row[0]; my = row[1]; mz = row[2];       // mean of one point is the point (x/1 is exact)
+                } else {
+                    SlotSum sum;
+                    for (int s2 = 0; s2 < n_keep; ++s2) {
+                        load_row(stg, rel, perm[lane][s2], row);
+                        sum.add(s2, P4, row[0], row[1], row[2]);
+                    }
+                    const float fn = (float)n_keep;
+                    mx = __fdiv_rn(sum.sx(), fn); my = __fdiv_rn(sum.sy(), fn); mz = __fdiv_rn(sum.sz(), fn);
+                }
+            }
+            const unsigned sbal = __ballot_sync(FULL, live && n_keep == 1);
+            const unsigned mbal = __ballot_sync(FULL, live && n_keep > 1);
+            const int n_s = __popc(sbal), n_m = __popc(mbal);
+            if (live) {
+                const int slot = (n_keep == 1) ? __popc(sbal & lt) : 31 - __popc(mbal & lt);   // singles from the front, multis from the back
+                const int pos0 = (cnt == 1) ? 0 : (int)perm[lane][0];   // the one evaluated point (rank 0 when P == 1 truncated)
+                rec[slot][0] = make_float4(mx, my, mz, __int_as_float(n_keep | (lane << 8) | (pos0 << 16)));
+                rec[slot][1] = make_float4(__int_as_float(rel), __int_as_float(f), 0.f, 0.f);
+            }
+            // the tile buffer: wait until the previous store has read it, then clear what that tile dirtied
+            if (TMA && store_pending) {
+                if (lane == 0) tma_wait_read<0>();
+                store_pending = false;
+            }
+            __syncwarp();
+            if (__popc(dirty) > 2) {
 #pragma unroll
                 for (int t = 0; t < TILE / 128; ++t) *reinterpret_cast<float4 *>(tile + t * 128 + lane * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
             } else {
@@ -787,48 +1029,125 @@ k_canvas(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUten
                     tile[swz128(lane, dc)] = 0.f; tile[swz128(lane + 32, dc)] = 0.f;
                 }
             }
-            if (nb & 1) dirty1 = bal; else dirty0 = bal;
-            ++nb;
+            dirty = bal_occ;
             __syncwarp();
-            // units: (pillar, 4 channels): lane l moves channels c0..c0+3 of the tile's pillar (l>>4) + 2*j
-            const int n_p = __popc(bal);
-            auto put = [&](int cell, const float4 v) {
-                const int xq = cell >> 2, xr = cell & 3;
-                float *t0 = tile + c0 * 32 + xr;
-                t0[0 * 32 + ((xq ^ ((c0 + 0) & 7)) << 2)] = v.x;
-                t0[1 * 32 + ((xq ^ ((c0 + 1) & 7)) << 2)] = v.y;
-                t0[2 * 32 + ((xq ^ ((c0 + 2) & 7)) << 2)] = v.z;
-                t0[3 * 32 + ((xq ^ ((c0 + 3) & 7)) << 2)] = v.w;
-            };
-            if (!(p.dbg & 2)) {
-#pragma unroll
-            for (int j = 0; j < PRE; ++j) {
-                const int k = half + 2 * j;
-                if (k < n_p) put(list[k].x, pre[j]);
+            // ---- unit phase.  lane l always computes channels c0..c0+3 ----
+            const float cy = __fadd_rn(__fmul_rn((float)y, vsy), voy);   // pillar centre: fl(fl(c*v)+off), two roundings,
+                                                                         // no FMA (pillar_vfe.py:101-103)
+            // (a) single-point pillars: half-warp h takes list entries 2*j + h
+#pragma unroll 1
+            for (int j = 0; 2 * j < n_s; ++j) {
+                const int e = 2 * j + half;
+                if (e < n_s) {
+                    const float4 r0 = rec[e][0], r1 = rec[e][1];
+                    const int meta = __float_as_int(r0.w);
+                    const int cell = (meta >> 8) & 0xFF;
+                    const float cx = __fadd_rn(__fmul_rn((float)(x0 + cell), vsx), vox);
+                    int v0 = 0, v1 = 0, v2 = 0, v3 = 0;
+                    if (1 < Pmax) { v0 = __float_as_int(pv.x); v1 = __float_as_int(pv.y); v2 = __float_as_int(pv.z); v3 = __float_as_int(pv.w); }
+                    float row[RWc];
+                    load_row(stg, __float_as_int(r1.x), meta >> 16, row);
+                    eval_row(row, r0.x, r0.y, r0.z, cx, cy, v0, v1, v2, v3);
+                    if (p.feats)
+                        st_f4_hint(p.feats + (size_t)__float_as_int(r1.y) * C + c0,
+                                   make_float4(__int_as_float(v0), __int_as_float(v1), __int_as_float(v2), __int_as_float(v3)), stream_policy);
+                    put_tile(cell, v0, v1, v2, v3);
+                }
             }
+            // (b) multi-point pillars: both half-warps on the same pillar, half h takes slots h, h+2, ...; max-combined
+#pragma unroll 1
+            for (int j = 0; j < n_m; ++j) {
+                const float4 r0 = rec[31 - j][0], r1 = rec[31 - j][1];
+                const int meta = __float_as_int(r0.w);
+                const int nk = meta & 0xFF, cell = (meta >> 8) & 0xFF;
+                const int relp = __float_as_int(r1.x);
+                const float cx = __fadd_rn(__fmul_rn((float)(x0 + cell), vsx), vox);
+                int v0 = 0, v1 = 0, v2 = 0, v3 = 0;
+                if (nk < Pmax) { v0 = __float_as_int(pv.x); v1 = __float_as_int(pv.y); v2 = __float_as_int(pv.z); v3 = __float_as_int(pv.w); }
+#pragma unroll 1
+                for (int s2 = half; s2 < nk; s2 += 2) {
+                    float row[RWc];
+                    load_row(stg, relp, perm[cell][s2], row);
+                    eval_row(row, r0.x, r0.y, r0.z, cx, cy, v0, v1, v2, v3);
+                }
+                v0 = max(v0, __shfl_xor_sync(FULL, v0, 16)); v1 = max(v1, __shfl_xor_sync(FULL, v1, 16));
+                v2 = max(v2, __shfl_xor_sync(FULL, v2, 16)); v3 = max(v3, __shfl_xor_sync(FULL, v3, 16));
+                if (half == 0) {
+                    if (p.feats)
+                        st_f4_hint(p.feats + (size_t)__float_as_int(r1.y) * C + c0,
+                                   make_float4(__int_as_float(v0), __int_as_float(v1), __int_as_float(v2), __int_as_float(v3)), stream_policy);
+                    put_tile(cell, v0, v1, v2, v3);
+                }
             }
-            // more than 2*PRE pillars in the tile: the rest in batches of PRE loads, then PRE column writes
-            for (int k0 = half + 2 * PRE; k0 < n_p && !(p.dbg & 2); k0 += 2 * PRE) {
-                float4 more[PRE];
-#pragma unroll
-                for (int j = 0; j < PRE; ++j)
-                    if (k0 + 2 * j < n_p) more[j] = ld_f4_hint(p.feats + (size_t)list[k0 + 2 * j].y * C + c0, stream_policy);
-#pragma unroll
-                for (int j = 0; j < PRE; ++j)
-                    if (k0 + 2 * j < n_p) put(list[k0 + 2 * j].x, more[j]);
+            // ---- pillars with more than 32 arrivals: the warp selects the 32 smallest point indices, then as (b) ----
+            unsigned hm = __ballot_sync(FULL, occ && cnt > 32);
+            while (hm) {
+                const int o = __ffs(hm) - 1;
+                hm &= hm - 1;
+                const int cnt_o = __shfl_sync(FULL, cnt, o), start_o = __shfl_sync(FULL, start, o), f_o = __shfl_sync(FULL, f, o);
+                const int nk = min(cnt_o, Pmax);
+                const float *grow_o = grows + (size_t)start_o * RWc;
+                bperm[lane] = select_first32(grow_o + F, RWc, cnt_o, lane);
+                __syncwarp();
+                if (p.voxels) {
+                    float *vo = p.voxels + (size_t)f_o * Pmax * F;
+                    for (int t = lane; t < Pmax * F; t += 32) {
+                        const int s2 = t / F, kk = t - s2 * F;
+                        vo[t] = (s2 < nk) ? __ldg(grow_o + (size_t)bperm[s2] * RWc + kk) : 0.f;
+                    }
+                }
+                SlotSum sum;
+                for (int s2 = 0; s2 < nk; ++s2) {
+                    const float4 v = __ldg(reinterpret_cast<const float4 *>(grow_o + (size_t)bperm[s2] * RWc));
+                    sum.add(s2, P4, v.x, v.y, v.z);
+                }
+                const float fn = (float)nk;
+                const float hx = __fdiv_rn(sum.sx(), fn), hy = __fdiv_rn(sum.sy(), fn), hz = __fdiv_rn(sum.sz(), fn);
+                const float cx = __fadd_rn(__fmul_rn((float)(x0 + o), vsx), vox);
+                int v0 = 0, v1 = 0, v2 = 0, v3 = 0;
+                if (nk < Pmax) { v0 = __float_as_int(pv.x); v1 = __float_as_int(pv.y); v2 = __float_as_int(pv.z); v3 = __float_as_int(pv.w); }
+#pragma unroll 1
+                for (int s2 = half; s2 < nk; s2 += 2) {
+                    float row[RWc];
+                    load_row(stg, -1 - start_o, bperm[s2], row);
+                    eval_row(row, hx, hy, hz, cx, cy, v0, v1, v2, v3);
+                }
+                v0 = max(v0, __shfl_xor_sync(FULL, v0, 16)); v1 = max(v1, __shfl_xor_sync(FULL, v1, 16));
+                v2 = max(v2, __shfl_xor_sync(FULL, v2, 16)); v3 = max(v3, __shfl_xor_sync(FULL, v3, 16));
+                if (half == 0) {
+                    if (p.feats)
+                        st_f4_hint(p.feats + (size_t)f_o * C + c0,
+                                   make_float4(__int_as_float(v0), __int_as_float(v1), __int_as_float(v2), __int_as_float(v3)), stream_policy);
+                    put_tile(o, v0, v1, v2, v3);
+                }
+                __syncwarp();
             }
+            // ---- optional contract output: the padded voxels tensor [M, P, F], coalesced, one pillar at a time ----
+            if (p.voxels) {
+                unsigned todo = __ballot_sync(FULL, live);
+                while (todo) {
+                    const int o = __ffs(todo) - 1;
+                    todo &= todo - 1;
+                    const int cnt_o = __shfl_sync(FULL, cnt, o), rel_o = __shfl_sync(FULL, rel, o), f_o = __shfl_sync(FULL, f, o);
+                    const int nk = min(cnt_o, Pmax);
+                    float *vo = p.voxels + (size_t)f_o * Pmax * F;
+                    for (int t = lane; t < Pmax * F; t += 32) {
+                        const int s2 = t / F, kk = t - s2 * F;
+                        float v = 0.f;
+                        if (s2 < nk) {
+                            const int pos = (cnt_o == 1) ? 0 : (int)perm[o][s2];
+                            v = (rel_o >= 0) ? stg[(size_t)(rel_o + pos) * RWc + kk] : __ldg(grows + (size_t)(-1 - rel_o + pos) * RWc + kk);
+                        }
+                        vo[t] = v;
+                    }
+                }
+            }
+            // ---- the tile goes out in one piece ----
             if (TMA) {
                 fence_proxy_async_smem();
                 __syncwarp();
-                if (lane == 0) {
-                    if (p.dbg & 8) {
-#pragma unroll
-                        for (int q4 = 0; q4 < 4; ++q4) tma_store_3d_hint(&zmap, tile + q4 * ZC * 32, x0, y, b * C + q4 * ZC, stream_policy);
-                    } else {
-                        tma_store_3d_hint(&tmap, tile, x0, y, b * C, stream_policy);
-                    }
-                    tma_commit();
-                }
+                if (lane == 0) { tma_store_3d_hint(&tmap, tile, x0, y, b * C, stream_policy); tma_commit(); }
+                store_pending = true;
             } else if (STORE == 1) {
                 __syncwarp();
                 const int xc = x0 + 4 * (lane & 7);
@@ -849,10 +1168,10 @@ k_canvas(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUten
             }
             __syncwarp();
         }
-        bal = bal_n;
-#pragma unroll
-        for (int j = 0; j < PRE; ++j) pre[j] = pre_n[j];
+        e_cur = e_nxt; e_nxt = e_nn;
+        cur = nxt; nxt = nxt2; step.advance(nxt2);
     }
+    cp_async_wait<0>();
     if (TMA && lane == 0) tma_wait_read<0>();
 }
 
@@ -937,12 +1256,12 @@ static int launch_pfn(const PathParams &p, bool with_pfn, bool abs_xyz, bool dis
     return HGSF_ERR_UNSUPPORTED;
 }
 
-static int launch_canvas(const PathParams &p, cudaStream_t stream) {
+template <int F, bool ABS, bool DIST>
+static int launch_emit_t(const PathParams &p, cudaStream_t stream) {
     constexpr int C = 64;
-    const_cast<PathParams &>(p).dbg = getenv("HGSF_DBG") ? atoi(getenv("HGSF_DBG")) : 0;
+    constexpr int RWc = (F + 1 + 3) / 4 * 4;
     const bool vec_ok = (p.nx % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.canvas) & 15) == 0);
-    // HGSF_CANVAS_STORE=tma|vec picks the tile store for experiments; default below
-    const char *env = getenv("HGSF_CANVAS_STORE");
+    const char *env = getenv("HGSF_CANVAS_STORE");      // tma | vec : which tile store to use (experiments); default tma
     const bool tma = vec_ok && !(env && env[0] == 'v');
     CUtensorMap map, zmap;
     memset(&map, 0, sizeof(map));
@@ -952,21 +1271,34 @@ static int launch_canvas(const PathParams &p, cudaStream_t stream) {
         if (st == HGSF_OK) st = make_canvas_map(&zmap, p.canvas, p.B, C, p.ny, p.nx, C / 4);
         if (st != HGSF_OK) return st;
     }
-    const size_t smem = sizeof(float) * (CANVAS_WARPS * 2 * C * 32 + (C / 4) * 32) + sizeof(int) * 2 * (size_t)(p.B + 1);
+    const size_t smem = 1024 + sizeof(float) * (EMIT_WARPS * C * 32 + (C / 4) * 32 + EMIT_WARPS * 2 * STAGE_W * RWc) +
+                        sizeof(int) * 2 * (size_t)(p.B + 1);
     const long long n_tiles = (long long)p.B * p.ny * ((p.nx + 31) / 32);
     if (n_tiles == 0) return HGSF_OK;
+    const bool bn = p.bn_w != nullptr;
     auto go = [&](auto kern) -> int {
         int grid = 1;
-        const int st = launch_persistent(kern, CANVAS_THREADS, smem, (n_tiles + CANVAS_WARPS - 1) / CANVAS_WARPS, stream, &grid);
+        const int st = launch_persistent(kern, EMIT_THREADS, smem, (n_tiles + EMIT_WARPS - 1) / EMIT_WARPS, stream, &grid);
         if (st != HGSF_OK) return st;
-        kern<<<(unsigned)grid, CANVAS_THREADS, smem, stream>>>(map, zmap, p);
+        kern<<<(unsigned)grid, EMIT_THREADS, smem, stream>>>(map, zmap, p);
         return (int)cudaGetLastError();
     };
-    if (tma) return go(k_canvas<C, 0>);
-    return vec_ok ? go(k_canvas<C, 1>) : go(k_canvas<C, 2>);
+    if (tma) return bn ? go(k_emit<F, ABS, DIST, true, 0>) : go(k_emit<F, ABS, DIST, false, 0>);
+    if (vec_ok) return bn ? go(k_emit<F, ABS, DIST, true, 1>) : go(k_emit<F, ABS, DIST, false, 1>);
+    return bn ? go(k_emit<F, ABS, DIST, true, 2>) : go(k_emit<F, ABS, DIST, false, 2>);
 }
 
-// ---- optional per-launch timing of the dominant kernel, k_canvas (bench.py's roofline leg) ---------------------------------
+static int launch_emit(const PathParams &p, bool abs_xyz, bool dist, cudaStream_t s) {
+    if (p.C != 64) return HGSF_ERR_UNSUPPORTED;
+#define HGSF_CASE(FV, A, D) if (p.F == FV && abs_xyz == A && dist == D) return launch_emit_t<FV, A, D>(p, s);
+    HGSF_CASE(4, true, false) HGSF_CASE(5, true, false) HGSF_CASE(6, true, false) HGSF_CASE(7, true, false)
+    HGSF_CASE(8, true, false) HGSF_CASE(7, false, false) HGSF_CASE(8, false, false)
+    HGSF_CASE(7, true, true) HGSF_CASE(8, true, true)
+#undef HGSF_CASE
+    return HGSF_ERR_UNSUPPORTED;
+}
+
+// ---- optional per-launch timing of the dominant kernel (k_emit, or k_pfn without a canvas): bench.py's roofline leg ---------------------------------
 // A ring of CUDA event pairs recorded on the launching stream around that launch.  Off by default.
 struct EmitTiming {
     std::vector<cudaEvent_t> ev;   // 2 * capacity
@@ -1023,17 +1355,13 @@ int launch_pillar_path(const PathParams &p, bool with_pfn, bool abs_xyz, bool di
         if (e != cudaSuccess) return (int)e;
         ++nl;
     }
-    int st = launch_pfn(p, with_pfn, abs_xyz, dist, stream);
+    // with a canvas: the fused k_emit (pillar rows + canvas in one pass); without: the pillar-major k_pfn
+    const bool timed = g_timing.capacity > 0 && g_timing.count < g_timing.capacity;
+    if (timed) cudaEventRecord(g_timing.ev[2 * g_timing.count], stream);
+    const int st = (with_pfn && p.canvas) ? launch_emit(p, abs_xyz, dist, stream) : launch_pfn(p, with_pfn, abs_xyz, dist, stream);
     if (st != HGSF_OK) return st;
+    if (timed) cudaEventRecord(g_timing.ev[2 * g_timing.count++ + 1], stream);
     ++nl;
-    if (with_pfn && p.canvas) {
-        const bool timed = g_timing.capacity > 0 && g_timing.count < g_timing.capacity;
-        if (timed) cudaEventRecord(g_timing.ev[2 * g_timing.count], stream);
-        st = launch_canvas(p, stream);
-        if (st != HGSF_OK) return st;
-        if (timed) cudaEventRecord(g_timing.ev[2 * g_timing.count++ + 1], stream);
-        ++nl;
-    }
     if (launches) *launches = nl;
     return HGSF_OK;
 }
