@@ -162,7 +162,7 @@ __global__ void __launch_bounds__(FRONT_THREADS) k_front(const PathParams p) {
     const long long gtid = (long long)blockIdx.x * FRONT_THREADS + tid, nthr = (long long)gridDim.x * FRONT_THREADS;
 
     // ---- phase 0: zero the cell table (and k_pfn's chunk ticket) ----
-    if (gtid == 0) *p.ticket = 0u;
+    if (gtid == 0) { p.ticket[0] = 0u; p.ticket[1] = 0u; }     // k_pfn's chunk ticket, k_emit's tile-chunk ticket
     {
         uint4 *t4 = reinterpret_cast<uint4 *>(p.table);
         const long long n4 = (long long)p.B * p.cells;      // one uint4 per entry
@@ -872,23 +872,39 @@ k_emit(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtenso
         t0[3 * 32 + ((xq ^ ((c0 + 3) & 7)) << 2)] = __int_as_float(v3);
     };
 
-    // this warp's tile sequence: first tile blockIdx*W + warp, stride gridDim*W; stepping is division free
-    TileStep step;
-    step.tiles_per_row = tiles_per_row; step.rows_per_frame = rows_per_frame;
-    {
-        const int stride_tiles = (int)gridDim.x * EMIT_WARPS;
-        step.dr = stride_tiles / tiles_per_row; step.dxt = stride_tiles - step.dr * tiles_per_row;
-    }
-    TilePos cur;
-    {
-        const int t0 = (int)blockIdx.x * EMIT_WARPS + warp;      // the only divisions: where this warp starts
-        cur.r = t0 / tiles_per_row; cur.xt = t0 - cur.r * tiles_per_row;
-        cur.b = cur.r / rows_per_frame; cur.zy = cur.r - cur.b * rows_per_frame;
-    }
-    TilePos nxt = cur;
-    step.advance(nxt);
-    TilePos nxt2 = nxt;
-    step.advance(nxt2);
+    // Tiles are handed out DYNAMICALLY in chunks of 4 consecutive tiles (one atomic per chunk, fetched a chunk ahead):
+    // a dense tile costs ten times a sparse one, and a static assignment leaves the unlucky warps running alone at the end.
+    constexpr int CHUNK = 4;
+    const int n_tiles = n_rows * tiles_per_row;
+    auto fetch_chunk = [&]() -> int {
+        int v = 0;
+        if (lane == 0) v = (int)atomicAdd(p.ticket + 1, 1u);
+        return __shfl_sync(FULL, v, 0) * CHUNK;
+    };
+    auto decode = [&](int t) -> TilePos {
+        TilePos q;
+        if (t >= n_tiles) { q.r = n_rows; q.xt = 0; q.b = p.B; q.zy = 0; return q; }
+        q.r = t / tiles_per_row; q.xt = t - q.r * tiles_per_row;
+        q.b = q.r / rows_per_frame; q.zy = q.r - q.b * rows_per_frame;
+        return q;
+    };
+    int seq_left = CHUNK, seq_next = 0;                   // tiles left in the current chunk; base of the prefetched next chunk
+    TilePos seq = decode(fetch_chunk());                   // the furthest tile handed to the pipeline so far
+    seq_next = fetch_chunk();
+    auto next_tile = [&]() -> TilePos {
+        if (seq_left > 1 && seq.r < n_rows) {
+            --seq_left;
+            if (++seq.xt == tiles_per_row) { seq.xt = 0; ++seq.r; if (++seq.zy == rows_per_frame) { seq.zy = 0; ++seq.b; } }
+        } else {
+            seq = decode(seq_next);
+            seq_left = CHUNK;
+            if (seq.r < n_rows) seq_next = fetch_chunk();
+        }
+        return seq;
+    };
+    TilePos cur = seq;
+    TilePos nxt = next_tile();
+    TilePos nxt2 = next_tile();
     auto load_entry = [&](const TilePos &t) -> uint4 {
         const int x = t.xt * 32 + lane;
         // row r = b*ny + y and the table is [b][y][x]: the cell index is r*nx + x
@@ -1169,7 +1185,7 @@ k_emit(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtenso
             __syncwarp();
         }
         e_cur = e_nxt; e_nxt = e_nn;
-        cur = nxt; nxt = nxt2; step.advance(nxt2);
+        cur = nxt; nxt = nxt2; nxt2 = next_tile();
     }
     cp_async_wait<0>();
     if (TMA && lane == 0) tma_wait_read<0>();
