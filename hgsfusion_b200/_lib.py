@@ -15,7 +15,9 @@ OK, ERR_INVALID_ARG, ERR_UNSUPPORTED, ERR_WORKSPACE, ERR_DRIVER = 0, -1, -2, -3,
 
 EXPORTS = ["hgsf_abi_version", "hgsf_status_string", "hgsf_pillar_capacity", "hgsf_workspace_size",
            "hgsf_pillarize", "hgsf_points_to_bev", "hgsf_pillar_vfe", "hgsf_scatter_workspace_size",
-           "hgsf_pointpillar_scatter", "hgsf_last_launch_count", "hgsf_emit_timing_begin", "hgsf_emit_timing_collect"]
+           "hgsf_pointpillar_scatter", "hgsf_last_launch_count", "hgsf_emit_timing_begin", "hgsf_emit_timing_collect",
+           "hgsf_pillarnet_workspace_size", "hgsf_pillarnet_indices", "hgsf_gather_feature", "hgsf_gather_feature_grad",
+           "hgsf_scatter_max", "hgsf_scatter_max_grad"]
 
 
 class Geometry(C.Structure):
@@ -75,6 +77,14 @@ def load():
     lib.hgsf_scatter_workspace_size.argtypes = [C.POINTER(Geometry), C.c_int32, C.POINTER(C.c_size_t)]
     lib.hgsf_pointpillar_scatter.argtypes = [C.POINTER(Geometry), C.c_void_p, C.c_void_p, C.c_int32, C.c_int64,
                                              C.c_int32, C.c_int32, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
+    lib.hgsf_pillarnet_workspace_size.argtypes = [C.c_int64, C.POINTER(C.c_size_t)]
+    lib.hgsf_pillarnet_indices.argtypes = [C.c_float, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
+                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                           C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.hgsf_gather_feature.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]
+    lib.hgsf_gather_feature_grad.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]
+    lib.hgsf_scatter_max.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.hgsf_scatter_max_grad.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p]
     lib.hgsf_emit_timing_begin.argtypes = [C.c_int]
     lib.hgsf_emit_timing_collect.argtypes = [C.POINTER(C.c_float), C.c_int]
     for name in EXPORTS:

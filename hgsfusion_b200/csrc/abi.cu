@@ -2,6 +2,7 @@
 // Validation, parameter packing, workspace carving; no allocation, no host synchronisation.
 #include "contract_ops.cuh"
 #include "pillar_path.cuh"
+#include "pillarnet_ops.cuh"
 
 #include <climits>
 
@@ -168,6 +169,72 @@ int hgsf_pointpillar_scatter(const hgsf_geometry *g, const float *feats, const v
     q.ny = g->grid[1]; q.nx = g->grid[0]; q.plane = (long long)g->grid[0] * g->grid[1];
     q.map = static_cast<unsigned *>(ws); q.canvas = canvas;
     return launch_scatter(q, static_cast<cudaStream_t>(stream), &g_last_launches);
+}
+
+// ---- Path B (PillarNet reader): replaces the pybind module pillar_cuda (pillar_api.cpp:10-22) ----------------------
+int hgsf_pillarnet_workspace_size(int64_t n_points, size_t *bytes) {
+    if (!bytes || n_points < 0) return HGSF_ERR_INVALID_ARG;
+    *bytes = align_up(sizeof(int) * (size_t)n_points, 256) + sizeof(uint32_t) * 8192;
+    return HGSF_OK;
+}
+
+int hgsf_pillarnet_indices(float bev_size, const float *xyz, const int32_t *xyz_batch_cnt, int64_t N, int32_t B, int32_t H,
+                           int32_t W, int32_t *pillar_bev_indices, int32_t *pillars, int32_t *indice_pairs,
+                           int32_t *point_idx, int32_t *pillar_idx, int32_t *counts, void *ws, size_t ws_bytes,
+                           hgsf_stream_t stream) {
+    g_last_launches = 0;
+    if (!(bev_size > 0.f) || N < 0 || B <= 0 || H <= 0 || W <= 0 || !xyz_batch_cnt || !pillar_bev_indices || !pillars ||
+        !point_idx || !pillar_idx || !counts || !ws || (N > 0 && !xyz))
+        return HGSF_ERR_INVALID_ARG;
+    if ((int64_t)B * H * W > INT_MAX || N > INT_MAX || B > 1024) return HGSF_ERR_UNSUPPORTED;
+    size_t need = 0;
+    hgsf_pillarnet_workspace_size(N, &need);
+    if (ws_bytes < need || (reinterpret_cast<uintptr_t>(ws) & 255)) return HGSF_ERR_WORKSPACE;
+    PillarNetParams q{};
+    q.xyz = xyz; q.cnt = xyz_batch_cnt; q.N = N; q.B = B; q.H = H; q.W = W; q.bev_size = bev_size;
+    q.bev = pillar_bev_indices; q.pillars = pillars; q.pairs = indice_pairs; q.point_idx = point_idx; q.pillar_idx = pillar_idx;
+    q.counts = counts;
+    q.key = static_cast<int *>(ws);
+    q.partial = reinterpret_cast<uint32_t *>(static_cast<uint8_t *>(ws) + align_up(sizeof(int) * (size_t)N, 256));
+    const int st = launch_pillarnet_indices(q, static_cast<cudaStream_t>(stream));
+    if (st == HGSF_OK) g_last_launches = 1;
+    return st;
+}
+
+int hgsf_gather_feature(const int32_t *set_indices, const float *features, int64_t L, int32_t C, float *out,
+                        hgsf_stream_t stream) {
+    g_last_launches = 0;
+    if (L < 0 || C <= 0 || (L > 0 && (!set_indices || !features || !out))) return HGSF_ERR_INVALID_ARG;
+    const int st = launch_gather(L, C, set_indices, features, out, static_cast<cudaStream_t>(stream));
+    if (st == HGSF_OK) g_last_launches = L > 0;
+    return st;
+}
+
+int hgsf_gather_feature_grad(const int32_t *set_indices, const float *grad_out, int64_t L, int32_t C, float *grad_features,
+                             hgsf_stream_t stream) {
+    g_last_launches = 0;
+    if (L < 0 || C <= 0 || (L > 0 && (!set_indices || !grad_out || !grad_features))) return HGSF_ERR_INVALID_ARG;
+    const int st = launch_gather_grad(L, C, set_indices, grad_out, grad_features, static_cast<cudaStream_t>(stream));
+    if (st == HGSF_OK) g_last_launches = L > 0;
+    return st;
+}
+
+int hgsf_scatter_max(const int32_t *index, const float *src, int32_t C, int64_t L, int64_t M, int32_t *arg, float *out,
+                     hgsf_stream_t stream) {
+    g_last_launches = 0;
+    if (C <= 0 || L < 0 || M < 0 || (M > 0 && !out) || (L > 0 && (!index || !src))) return HGSF_ERR_INVALID_ARG;
+    if ((int64_t)C * L > INT_MAX || (int64_t)C * M > INT_MAX) return HGSF_ERR_UNSUPPORTED;   // arg holds flat ids as int32
+    if (M == 0) return HGSF_OK;
+    return launch_scatter_max(C, L, M, index, src, arg, out, static_cast<cudaStream_t>(stream), &g_last_launches);
+}
+
+int hgsf_scatter_max_grad(const int32_t *arg, const float *grad_out, int32_t C, int64_t M, float *grad_src,
+                          hgsf_stream_t stream) {
+    g_last_launches = 0;
+    if (C <= 0 || M < 0 || (M > 0 && (!arg || !grad_out || !grad_src))) return HGSF_ERR_INVALID_ARG;
+    const int st = launch_scatter_max_grad(C, M, arg, grad_out, grad_src, static_cast<cudaStream_t>(stream));
+    if (st == HGSF_OK) g_last_launches = M > 0;
+    return st;
 }
 
 }  // extern "C"

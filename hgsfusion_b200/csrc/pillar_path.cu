@@ -208,6 +208,7 @@ __global__ void __launch_bounds__(FRONT_THREADS) k_front(const PathParams p) {
         const uint64_t total = block_sum(mine, s_warp, lane, warp);
         if (tid == 0) p.scan_desc[blockIdx.x] = total;
     }
+    stamp(7);
     // (b) cells: CTA c owns cells [clo, chi), a whole number of 1024-cell tiles
     const long long n_cells = (long long)p.B * p.cells;
     const long long ctiles_total = (n_cells + SCAN_TILE - 1) / SCAN_TILE;
@@ -285,6 +286,7 @@ __global__ void __launch_bounds__(FRONT_THREADS) k_front(const PathParams p) {
         if (p.n == 0 && blockIdx.x == 0)
             for (int b = tid; b <= p.B; b += FRONT_THREADS) p.frame_raw_base[b] = 0;
     }
+    stamp(6);
     {
         // (b) cells: CSR start of every cell (empty ones too: a tile's row span is start[first cell] .. start[last]+cnt)
         uint64_t before = 0;

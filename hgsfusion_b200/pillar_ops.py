@@ -1,0 +1,188 @@
+"""Path B -- the PillarNet reader ops, mirroring the reference's `pcdet/ops/pillar_ops` Python surface on top of the
+native library (no `pillar_cuda`, no per-call host syncs inside the index generation).
+
+  reference                                              here
+  pillar_utils.bev_spatial_shape              :16-19     bev_spatial_shape
+  pillar_utils.gen_indice_pairs (GenIndicePairs) :84-132 + group_utils.flatten_indices :12-31   gen_indice_pairs_flat
+  group_utils.gather_feature  (GatherFeature)  :34-58    gather_feature      (autograd, native backward)
+  scatter_utils.scatter_max   (ScatterMaxFunction) :7-45 scatter_max         (autograd, native backward)
+  pillar_utils.PillarQueryAndGroup              :22-54   PillarQueryAndGroup
+  pillar_modules.PillarMaxPooling               :10-82   PillarMaxPooling    (same parameter names: shared_mlps.0.weight, shared_mlps.1.*)
+
+`PillarMaxPooling.forward` returns `(pillar_features [M,C], pillars [M,3] (b,y,x), spatial_shape (Ny,Nx), batch_size)`
+and wraps them in `spconv.SparseConvTensor` only when spconv is importable (pillar_modules.py:82).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List
+
+import torch
+import torch.nn as nn
+from torch.autograd import Function
+
+from . import _lib
+
+
+def _s():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _need_cuda(t, name, dtype):
+    if not t.is_cuda:
+        raise ValueError(f"{name} must be a CUDA tensor (hgsfusion_b200 has no CPU path)")
+    if t.dtype != dtype:
+        raise TypeError(f"{name} must be {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name} must be contiguous")     # the reference's CHECK_INPUT, cuda_utils.h:19-21
+
+
+def bev_spatial_shape(point_cloud_range, pillar_size):
+    H = round((point_cloud_range[3] - point_cloud_range[0]) / pillar_size)
+    W = round((point_cloud_range[4] - point_cloud_range[1]) / pillar_size)
+    return int(W), int(H)          # the reference's quirk: (W, H) is then unpacked as `H, W = spatial_shape` (:102)
+
+
+@torch.no_grad()
+def gen_indice_pairs_flat(xyz, xyz_batch_cnt, pillar_size, spatial_shape, sync=True):
+    """xyz [N,3] relative coords, xyz_batch_cnt [B] int32 -> dict(pillars [M,3], pillar_bev_indices [B,H,W],
+    indice_pairs [N,1], point_set_indices [L], pillar_set_indices [L]).  One native launch; `sync=True` reads
+    (M, L) once to slice the outputs as the reference does, `sync=False` leaves them capacity-sized with `counts`."""
+    _need_cuda(xyz, "xyz", torch.float32)
+    _need_cuda(xyz_batch_cnt, "xyz_batch_cnt", torch.int32)
+    assert xyz.shape[1] == 3
+    lib = _lib.load()
+    N, B = int(xyz.shape[0]), int(xyz_batch_cnt.numel())
+    H, W = spatial_shape
+    dev = xyz.device
+    cap = max(1, min(N, B * H * W))
+    bev = torch.empty((B, H, W), dtype=torch.int32, device=dev)
+    pillars = torch.empty((cap, 3), dtype=torch.int32, device=dev)
+    pairs = torch.empty((N, 1), dtype=torch.int32, device=dev)
+    first = torch.empty((max(N, 1),), dtype=torch.int32, device=dev)
+    second = torch.empty((max(N, 1),), dtype=torch.int32, device=dev)
+    counts = torch.empty((2,), dtype=torch.int32, device=dev)
+    need = C.c_size_t(0)
+    _lib.check(lib.hgsf_pillarnet_workspace_size(N, C.byref(need)), "hgsf_pillarnet_workspace_size")
+    ws = torch.empty(need.value + 256, dtype=torch.uint8, device=dev)
+    ws_ptr = (ws.data_ptr() + 255) // 256 * 256
+    st = lib.hgsf_pillarnet_indices(float(pillar_size), _p(xyz), _p(xyz_batch_cnt), N, B, H, W, _p(bev), _p(pillars), _p(pairs),
+                                    _p(first), _p(second), _p(counts), C.c_void_p(ws_ptr), need.value, _s())
+    _lib.check(st, "hgsf_pillarnet_indices")
+    out = dict(pillar_bev_indices=bev, indice_pairs=pairs, counts=counts)
+    if sync:
+        M, L = (int(v) for v in counts.tolist())
+        out.update(pillars=pillars[:M], point_set_indices=first[:L], pillar_set_indices=second[:L])
+    else:
+        out.update(pillars=pillars, point_set_indices=first, pillar_set_indices=second)
+    return out
+
+
+class GatherFeature(Function):
+    @staticmethod
+    def forward(ctx, features: torch.Tensor, set_indices: torch.Tensor):
+        _need_cuda(features, "features", torch.float32)
+        _need_cuda(set_indices, "set_indices", torch.int32)
+        out = features.new_empty((set_indices.shape[0], features.shape[1]))
+        _lib.check(_lib.load().hgsf_gather_feature(_p(set_indices), _p(features), int(set_indices.shape[0]),
+                                                  int(features.shape[1]), _p(out), _s()), "hgsf_gather_feature")
+        ctx.for_backwards = (features.shape[0], features.shape[1], set_indices)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        N, Cc, set_indices = ctx.for_backwards
+        grad_features = grad_out.new_zeros((N, Cc))
+        g = grad_out.contiguous()
+        _lib.check(_lib.load().hgsf_gather_feature_grad(_p(set_indices), _p(g), int(set_indices.shape[0]), int(Cc),
+                                                       _p(grad_features), _s()), "hgsf_gather_feature_grad")
+        return grad_features, None
+
+
+gather_feature = GatherFeature.apply
+
+
+class ScatterMaxFunction(Function):
+    @staticmethod
+    def forward(ctx, src: torch.Tensor, index: torch.Tensor, M: int):
+        """src (C, L), index (L,) -> out (C, M)"""
+        _need_cuda(src, "src", torch.float32)
+        _need_cuda(index, "index", torch.int32)
+        Cc, L = src.size()
+        arg = torch.empty((Cc, M), dtype=torch.int32, device=src.device)
+        out = src.new_empty((Cc, M))
+        _lib.check(_lib.load().hgsf_scatter_max(_p(index), _p(src), int(Cc), int(L), int(M), _p(arg), _p(out), _s()),
+                   "hgsf_scatter_max")
+        ctx.for_backwards = (Cc, L, arg)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        Cc, L, arg = ctx.for_backwards
+        grad_src = grad_out.new_zeros((Cc, L))
+        g = grad_out.contiguous()
+        _lib.check(_lib.load().hgsf_scatter_max_grad(_p(arg), _p(g), int(Cc), int(arg.shape[1]), _p(grad_src), _s()),
+                   "hgsf_scatter_max_grad")
+        return grad_src, None, None
+
+
+scatter_max = ScatterMaxFunction.apply
+
+
+class PillarQueryAndGroup(nn.Module):
+    def __init__(self, pillar_size, point_cloud_range):
+        super().__init__()
+        self.pillar_size = pillar_size
+        self.spatial_shape = bev_spatial_shape(point_cloud_range, pillar_size)
+        self.z_center = (point_cloud_range[5] + point_cloud_range[2]) / 2
+        self.point_cloud_range = point_cloud_range
+
+    def forward(self, xyz, xyz_batch_cnt, point_features):
+        """xyz (N,3) relative, xyz_batch_cnt (B,), point_features (N,C) ->
+        pillars (M,3) [b y x], pillar_set_indices (L,), group_features (L, C+6)   (pillar_utils.py:31-54)"""
+        r = gen_indice_pairs_flat(xyz, xyz_batch_cnt, self.pillar_size, self.spatial_shape)
+        pillars, point_set_indices, pillar_set_indices = r["pillars"], r["point_set_indices"], r["pillar_set_indices"]
+        # pillar centres as the reference builds them (pillar_utils.py:117-121): z centre in absolute coordinates
+        pillar_centers = torch.zeros([pillars.shape[0], 3], dtype=torch.float32, device=xyz.device)
+        pillar_centers[:, 0] = (pillars[:, 2] + 0.5) * self.pillar_size
+        pillar_centers[:, 1] = (pillars[:, 1] + 0.5) * self.pillar_size
+        pillar_centers[:, 2] = self.z_center
+        group_point_features = gather_feature(point_features, point_set_indices)
+        group_point_xyz = gather_feature(xyz, point_set_indices)
+        group_pillar_centers = gather_feature(pillar_centers, pillar_set_indices)
+        group_pillar_centers = group_point_xyz - group_pillar_centers
+        group_features = torch.cat([group_point_features.detach(), group_point_xyz.detach(),
+                                    group_pillar_centers.detach()], dim=1)
+        return pillars, pillar_set_indices, group_features
+
+
+class PillarMaxPooling(nn.Module):
+    def __init__(self, mlps: List[int], pillar_size: float, point_cloud_range: List[float]):
+        super().__init__()
+        self.bev_width, self.bev_height = bev_spatial_shape(point_cloud_range, pillar_size)
+        self.groups = PillarQueryAndGroup(pillar_size, point_cloud_range)
+        shared_mlp = []
+        for k in range(len(mlps) - 1):
+            shared_mlp.extend([nn.Linear(mlps[k], mlps[k + 1], bias=False),
+                               nn.BatchNorm1d(mlps[k + 1], eps=1e-3, momentum=0.01), nn.ReLU()])
+        self.shared_mlps = nn.Sequential(*shared_mlp)       # the reference's own cuBLAS MLP (pillar_modules.py:19-26)
+
+    def forward(self, xyz, xyz_batch_cnt, pt_feature):
+        B = xyz_batch_cnt.shape[0]
+        pillar_indices, pillar_set_indices, group_features = self.groups(xyz, xyz_batch_cnt, pt_feature)
+        group_features = self.shared_mlps(group_features)
+        group_features = group_features.transpose(1, 0).contiguous()
+        pillar_features = scatter_max(group_features, pillar_set_indices, pillar_indices.shape[0])
+        pillar_features = pillar_features.transpose(1, 0)
+        try:
+            try:
+                import spconv.pytorch as spconv
+            except ImportError:
+                import spconv
+            return spconv.SparseConvTensor(pillar_features, pillar_indices, (self.bev_height, self.bev_width), B)
+        except ImportError:
+            return pillar_features, pillar_indices, (self.bev_height, self.bev_width), B

@@ -159,6 +159,44 @@ HGSF_API int hgsf_last_launch_count(void);
 HGSF_API int hgsf_emit_timing_begin(int capacity);
 HGSF_API int hgsf_emit_timing_collect(float *ms, int n);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * Path B -- the PillarNet reader the shipped HGSFusion YAMLs run.  These replace the reference's pybind module
+ * `pillar_cuda` (pcdet/ops/pillar_ops/src/pillar_api.cpp:10-22) and the Python glue around it.
+ * --------------------------------------------------------------------------------------------------------------- */
+
+/* Bytes of workspace hgsf_pillarnet_indices needs. */
+HGSF_API int hgsf_pillarnet_workspace_size(int64_t n_points, size_t *bytes);
+
+/* gen_indice_pairs + flatten_indices (pcdet/ops/pillar_ops/pillar_utils.py:84-132, group_utils.py:12-31; kernels
+ * create_pillar_indices_stack / create_pillar_indices / create_pillar_indice_pairs_stack / flatten_indice_pairs,
+ * pillar_ops_gpu.cu:13-117, group_ops_gpu.cu:9-24) in ONE launch, without the reference's two cumsum + .item() syncs.
+ *   xyz [N,3] fp32 relative coordinates, xyz_batch_cnt [B] int32; H = Ny, W = Nx
+ *   pillar_bev_indices [B,H,W] int32 (pillar id per cell, -1 none); pillars [>= min(N, B*H*W), 3] int32 (b, y, x),
+ *   raster order; indice_pairs [N] int32 (pillar id per point or -1; may be NULL); point_idx / pillar_idx [N] int32
+ *   (the points that have a pillar, in input order, and their pillar ids); counts [2] int32 = {M, L} on the device. */
+HGSF_API int hgsf_pillarnet_indices(float bev_size, const float *xyz, const int32_t *xyz_batch_cnt, int64_t n_points,
+                                    int32_t batch_size, int32_t H, int32_t W, int32_t *pillar_bev_indices,
+                                    int32_t *pillars, int32_t *indice_pairs, int32_t *point_idx, int32_t *pillar_idx,
+                                    int32_t *counts, void *workspace, size_t workspace_bytes, hgsf_stream_t stream);
+
+/* out[l, :] = features[set_indices[l], :]   (gather_feature_wrapper, group_ops_gpu.cu:42-55) */
+HGSF_API int hgsf_gather_feature(const int32_t *set_indices, const float *features, int64_t L, int32_t C, float *out,
+                                 hgsf_stream_t stream);
+/* grad_features[set_indices[l], :] += grad_out[l, :]; grad_features pre-zeroed by the caller
+ * (gather_feature_grad_wrapper, group_ops_gpu.cu:57-70) */
+HGSF_API int hgsf_gather_feature_grad(const int32_t *set_indices, const float *grad_out, int64_t L, int32_t C,
+                                      float *grad_features, hgsf_stream_t stream);
+
+/* out[c, index[p]] = max(0, max_p src[c, p]); arg[c, m] = a flat id c*L+p whose src is within 1e-5 of out[c, m], -1 if
+ * none (scatter_max_wrapper, scatter_ops_gpu.cu:13-46).  src [C,L], out/arg [C,M]; both are initialised here.
+ * arg may be NULL (forward only). */
+HGSF_API int hgsf_scatter_max(const int32_t *index, const float *src, int32_t C, int64_t L, int64_t M, int32_t *arg,
+                              float *out, hgsf_stream_t stream);
+/* grad_src.flat[arg[c, m]] = grad_out[c, m] where arg >= 0; grad_src [C,L] pre-zeroed by the caller
+ * (scatter_max_grad_wrapper, scatter_ops_gpu.cu:48-58) */
+HGSF_API int hgsf_scatter_max_grad(const int32_t *arg, const float *grad_out, int32_t C, int64_t M, float *grad_src,
+                                   hgsf_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

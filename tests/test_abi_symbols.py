@@ -58,7 +58,7 @@ def test_capacity_and_workspace_queries():
     need = C.c_size_t(0)
     assert lib.hgsf_workspace_size(C.byref(g), 480000, 16, 7, C.byref(need)) == 0
     table = 16 * 320 * 320 * 16
-    assert table < need.value < table + 480000 * (4 + 4 + 32) + (1 << 20)
+    assert table < need.value < table + 480000 * (4 + 4 + 32 + 16) + (1 << 20)   # key, arrival, rows, pillar records
     assert lib.hgsf_workspace_size(C.byref(g), 480000, 0, 7, C.byref(need)) == _lib.ERR_INVALID_ARG
     assert lib.hgsf_workspace_size(C.byref(g), 480000, 16, 7, None) == _lib.ERR_INVALID_ARG
     # B * cells must fit int32 keys

@@ -1,0 +1,163 @@
+"""GPU parity of the Path B (PillarNet reader) ops: against the numpy restatement, and -- when
+oracle/_ref/libref_pillar_ops.so is present -- against the REFERENCE's own CUDA kernels compiled unmodified from
+pcdet/ops/pillar_ops/src (oracle/build_ref_pillar_ops.sh) and run on the same GPU."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from hgsfusion_b200 import pillar_ops as po
+from oracle import pathb_oracle as pb
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_SO = os.path.join(ROOT, "oracle", "_ref", "libref_pillar_ops.so")
+
+
+def make_points(B, n, seed, H=320, W=320, s=0.16, spread=1.15):
+    rng = np.random.default_rng(seed)
+    cnt = rng.integers(n // 2, n, size=B).astype(np.int32)
+    N = int(cnt.sum())
+    xyz = np.stack([rng.uniform(-0.1 * W * s, spread * W * s, N), rng.uniform(-0.1 * H * s, spread * H * s, N),
+                    rng.uniform(-3, 2, N)], axis=1).astype(np.float32)
+    # clusters, so that pillars hold several points
+    k = N // 3
+    xyz[:k, :2] = (rng.uniform(0, W * s, size=(1, 2)) + rng.normal(0, 0.5, size=(k, 2))).astype(np.float32)
+    rng.shuffle(xyz)
+    return xyz, cnt
+
+
+@pytest.mark.parametrize("B,n,H,W,s", [(2, 3000, 320, 320, 0.16), (3, 5000, 496, 432, 0.16), (1, 1, 8, 8, 1.0), (4, 200, 16, 40, 0.5)])
+def test_indices_match_numpy_oracle(cuda, B, n, H, W, s):
+    xyz, cnt = make_points(B, n, seed=B * 7 + n, H=H, W=W, s=s)
+    ref = pb.gen_indice_pairs_flat(xyz, cnt, s, H, W)
+    got = po.gen_indice_pairs_flat(torch.from_numpy(xyz).to(cuda), torch.from_numpy(cnt).to(cuda), s, (H, W))
+    assert got["counts"].tolist() == [ref["M"], ref["L"]]
+    for k in ("pillars", "pillar_bev_indices", "indice_pairs", "point_set_indices", "pillar_set_indices"):
+        assert np.array_equal(got[k].cpu().numpy(), ref[k]), k
+
+
+def test_surplus_points_and_empty(cuda):
+    xyz = np.array([[0.1, 0.1, 0]] * 5, dtype=np.float32)
+    got = po.gen_indice_pairs_flat(torch.from_numpy(xyz).to(cuda), torch.tensor([2, 1], dtype=torch.int32, device=cuda), 1.0, (2, 2))
+    assert got["pillars"].tolist() == [[0, 0, 0], [1, 0, 0]] and got["indice_pairs"].view(-1).tolist() == [0, 0, 1, 1, 1]
+    got = po.gen_indice_pairs_flat(torch.zeros((0, 3), device=cuda), torch.tensor([0], dtype=torch.int32, device=cuda), 1.0, (4, 4))
+    assert got["counts"].tolist() == [0, 0] and (got["pillar_bev_indices"] == -1).all()
+
+
+def test_gather_scatter_forward_backward(cuda):
+    rng = np.random.default_rng(3)
+    N, Cf, L, M, Cc = 4000, 29, 3500, 900, 32
+    feats = torch.from_numpy(rng.normal(size=(N, Cf)).astype(np.float32)).to(cuda).requires_grad_(True)
+    idx_np = rng.integers(0, N, size=L).astype(np.int32)
+    idx = torch.from_numpy(idx_np).to(cuda)
+    g = po.gather_feature(feats, idx)
+    assert np.array_equal(g.detach().cpu().numpy(), pb.gather_feature(feats.detach().cpu().numpy(), idx_np))
+    go = torch.from_numpy(rng.normal(size=(L, Cf)).astype(np.float32)).to(cuda)
+    g.backward(go)
+    assert np.allclose(feats.grad.cpu().numpy(), pb.gather_feature_grad(idx_np, go.cpu().numpy(), N), atol=1e-5)
+
+    src_np = rng.normal(size=(Cc, L)).astype(np.float32)
+    pidx_np = rng.integers(0, M - 5, size=L).astype(np.int32)
+    src = torch.from_numpy(src_np).to(cuda).requires_grad_(True)
+    pidx = torch.from_numpy(pidx_np).to(cuda)
+    out = po.scatter_max(src, pidx, M)
+    ref = pb.scatter_max(src_np, pidx_np, M)
+    assert np.array_equal(out.detach().cpu().numpy(), ref)          # max is order independent: exact
+    gout = torch.from_numpy(rng.normal(size=(Cc, M)).astype(np.float32)).to(cuda)
+    out.backward(gout)
+    gs = src.grad.cpu().numpy()
+    # every positive maximum routes its gradient to exactly one arg-max element; nothing else receives any
+    nz = np.argwhere(gs != 0)
+    assert len(nz) == int((ref > 0).sum())
+    for c, p in nz[:: max(1, len(nz) // 300)]:
+        assert abs(src_np[c, p] - ref[c, pidx_np[p]]) < 1e-5 and gs[c, p] == gout[c, pidx_np[p]].item()
+
+
+def test_pillar_max_pooling_module(cuda):
+    """PillarMaxPooling (Path B reader, VoD 'split' width 29+6 -> 32) against a plain torch composition."""
+    rng = np.random.default_rng(5)
+    rng_pc = [0, -25.6, -3, 51.2, 25.6, 2]
+    xyz_np, cnt_np = make_points(2, 4000, 11, spread=1.0)
+    N = xyz_np.shape[0]
+    pf_np = rng.normal(size=(N, 29)).astype(np.float32)
+    m = po.PillarMaxPooling([35, 32], 0.16, rng_pc).to(cuda).eval()
+    with torch.no_grad():
+        m.shared_mlps[1].running_mean.normal_(); m.shared_mlps[1].running_var.uniform_(0.5, 2.0)
+        xyz, cnt, pf = torch.from_numpy(xyz_np).to(cuda), torch.from_numpy(cnt_np).to(cuda), torch.from_numpy(pf_np).to(cuda)
+        res = m(xyz, cnt, pf)
+        feats, pillars, shape, B = res if isinstance(res, tuple) else (res.features, res.indices, res.spatial_shape, res.batch_size)
+        ref = pb.gen_indice_pairs_flat(xyz_np, cnt_np, 0.16, 320, 320)
+        assert np.array_equal(pillars.cpu().numpy(), ref["pillars"]) and tuple(shape) == (320, 320) and B == 2
+        pi = torch.from_numpy(ref["point_set_indices"]).long().to(cuda)
+        qi = torch.from_numpy(ref["pillar_set_indices"]).long().to(cuda)
+        centers = torch.zeros((ref["M"], 3), device=cuda)
+        P = torch.from_numpy(ref["pillars"]).to(cuda)
+        centers[:, 0] = (P[:, 2] + 0.5) * 0.16; centers[:, 1] = (P[:, 1] + 0.5) * 0.16; centers[:, 2] = (2 + -3) / 2
+        gfeat = torch.cat([pf[pi], xyz[pi], xyz[pi] - centers[qi]], dim=1)
+        h = m.shared_mlps(gfeat)
+        exp = torch.zeros((ref["M"], 32), device=cuda)
+        exp.index_reduce_(0, qi, h, "amax", include_self=True)
+        assert torch.equal(feats, exp)
+
+
+@pytest.mark.skipif(not os.path.exists(REF_SO), reason="oracle/_ref/libref_pillar_ops.so not built (needs /root/reference)")
+def test_against_the_reference_kernels(cuda):
+    """Bit-for-bit against the reference's own kernels (compiled from its unmodified sources) on this GPU."""
+    ref = C.CDLL(REF_SO)
+    B, H, W, s = 3, 320, 320, 0.16
+    xyz_np, cnt_np = make_points(B, 6000, 21)
+    N = xyz_np.shape[0]
+    xyz, cnt = torch.from_numpy(xyz_np).to(cuda), torch.from_numpy(cnt_np).to(cuda)
+    p = lambda t: C.c_void_p(t.data_ptr())
+    # the reference's Python glue (pillar_utils.py:99-124, group_utils.py:20-29) around its kernels
+    mask = torch.zeros((B, H, W), dtype=torch.bool, device=cuda)
+    torch.cuda.synchronize()
+    ref.ref_create_pillar_indices_stack(N, B, H, W, C.c_float(s), p(xyz), p(cnt), p(mask))
+    location = torch.cumsum(mask.view(-1), 0).int()
+    M = location[-1].item()
+    bev = (location.view(B, H, W) * mask - 1).int().contiguous()
+    pillars = torch.zeros((M, 3), dtype=torch.int32, device=cuda)
+    ref.ref_create_pillar_indices(B, H, W, p(bev), p(pillars))
+    pairs = torch.full((N, 1), -1, dtype=torch.int32, device=cuda)
+    ref.ref_create_pillar_indice_pairs_stack(N, B, H, W, C.c_float(s), p(xyz), p(cnt), p(bev), p(pairs))
+    valid = pairs.view(-1) > -1
+    position = torch.cumsum(valid, 0).int()
+    L = position[-1].item()
+    position = (position * valid - 1).int().contiguous()
+    first = torch.zeros(L, dtype=torch.int32, device=cuda)
+    second = torch.zeros(L, dtype=torch.int32, device=cuda)
+    ref.ref_flatten_indice_pairs(N, 1, p(pairs), p(position), p(first), p(second))
+    torch.cuda.synchronize()
+    got = po.gen_indice_pairs_flat(xyz, cnt, s, (H, W))
+    assert got["counts"].tolist() == [M, L]
+    assert torch.equal(got["pillars"], pillars) and torch.equal(got["pillar_bev_indices"], bev)
+    assert torch.equal(got["indice_pairs"], pairs)
+    assert torch.equal(got["point_set_indices"], first) and torch.equal(got["pillar_set_indices"], second)
+    # gather / scatter_max
+    feats = torch.randn((N, 31), device=cuda)
+    out_ref = torch.zeros((L, 31), device=cuda)
+    ref.ref_gather_feature(L, 31, p(first), p(feats), p(out_ref))
+    torch.cuda.synchronize()
+    assert torch.equal(po.gather_feature(feats, first), out_ref)
+    src = torch.randn((32, L), device=cuda)
+    arg_ref = torch.full((32, M), -1, dtype=torch.int32, device=cuda)
+    o_ref = torch.zeros((32, M), device=cuda)
+    ref.ref_scatter_max(32, L, M, p(second), p(src), p(arg_ref), p(o_ref))
+    torch.cuda.synchronize()
+    o = po.scatter_max(src, second, M)
+    assert torch.equal(o, o_ref)
+    assert pb.check_arg(arg_ref.cpu().numpy(), src.cpu().numpy(), second.cpu().numpy(), o_ref.cpu().numpy())
+    # our arg through the backward pass: same rule
+    gout = torch.randn((32, M), device=cuda)
+    gs_ref = torch.zeros((32, L), device=cuda)
+    ref.ref_scatter_max_grad(32, M, p(arg_ref), p(gout), p(gs_ref))
+    torch.cuda.synchronize()
+    src2 = src.clone().requires_grad_(True)
+    po.scatter_max(src2, second, M).backward(gout)
+    # identical wherever the maximum is attained by a single element (ties may route differently, as in the reference)
+    same = (src2.grad == gs_ref).float().mean().item()
+    assert same > 0.999
+    assert torch.equal((src2.grad != 0).sum(), (gs_ref != 0).sum())
