@@ -322,6 +322,11 @@ def main_ours(args):
 
 
 if __name__ == "__main__":
+    # Only the JSON line may reach stdout: libraries (NCCL's version banner, torchrun notices) write there too, so
+    # file descriptor 1 is pointed at stderr for the whole run and the JSON goes to the saved descriptor.
+    _real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = _real_stdout
     a = parse()
     if a.impl == "reference":
         main_reference(a)
