@@ -82,7 +82,10 @@ static int run_path(const hgsf_geometry *g, const hgsf_points *pt, const hgsf_pf
     p.ticket = reinterpret_cast<uint32_t *>(base + w.off_ticket);
     p.scan_desc = reinterpret_cast<uint64_t *>(base + w.off_desc);
     p.frame_raw_base = reinterpret_cast<int32_t *>(base + w.off_raw_base);
-    p.table = reinterpret_cast<CellEntry *>(base + w.off_table);
+    p.cell_tag = reinterpret_cast<uint32_t *>(base + w.off_table);
+    p.cell_cnt = reinterpret_cast<uint32_t *>(base + w.off_table + w.cell_array_bytes);
+    p.cell_start = reinterpret_cast<uint32_t *>(base + w.off_table + 2 * w.cell_array_bytes);
+    p.table_bytes = 3 * w.cell_array_bytes;
     p.frame_offsets = pt->frame_offsets ? const_cast<int32_t *>(pt->frame_offsets)
                                         : reinterpret_cast<int32_t *>(base + w.off_frame_offsets);
     p.key = reinterpret_cast<int32_t *>(base + w.off_key);

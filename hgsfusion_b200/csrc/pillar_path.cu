@@ -97,9 +97,8 @@ __device__ __forceinline__ void count_point(const PathParams &p, int i, int lane
     const int rank = __popc(peers & ((1u << lane) - 1u));
     unsigned base = 0;
     if (lane == leader && key >= 0) {
-        CellEntry *e = p.table + key;
-        base = atomicAdd(&e->cnt, (unsigned)__popc(peers));
-        atomicMax(&e->tag, 0xFFFFFFFFu - (unsigned)i);
+        base = atomicAdd(p.cell_cnt + key, (unsigned)__popc(peers));
+        atomicMax(p.cell_tag + key, 0xFFFFFFFFu - (unsigned)i);
     }
     base = __shfl_sync(FULL, base, leader);
     if (i < p.n) {
@@ -112,11 +111,10 @@ __device__ __forceinline__ void count_point(const PathParams &p, int i, int lane
 __device__ __forceinline__ void fill_point(const PathParams &p, int i) {
     const int key = p.key[i];
     if (key < 0) return;
-    const uint4 e = *reinterpret_cast<const uint4 *>(p.table + key);
     const int b = key / p.cells;
-    const int local = (int)(e.x - 1u) - p.frame_raw_base[b];
+    const int local = (int)(p.cell_tag[key] - 1u) - p.frame_raw_base[b];
     if (local >= p.max_voxels) return;            // pillar beyond max_voxels: never created
-    const size_t pos = (size_t)e.z + p.arrival[i];
+    const size_t pos = (size_t)p.cell_start[key] + p.arrival[i];
     const float *src = p.pts + (size_t)i * p.stride + p.xyz_col;
     float4 *dst = reinterpret_cast<float4 *>(p.sorted_rows + pos * p.RW);
     for (int k = 0; k < p.RW; k += 4) {
@@ -164,8 +162,8 @@ __global__ void __launch_bounds__(FRONT_THREADS) k_front(const PathParams p) {
     // ---- phase 0: zero the cell table (and k_pfn's chunk ticket) ----
     if (gtid == 0) { p.ticket[0] = 0u; p.ticket[1] = 0u; }     // k_pfn's chunk ticket, k_emit's tile-chunk ticket
     {
-        uint4 *t4 = reinterpret_cast<uint4 *>(p.table);
-        const long long n4 = (long long)p.B * p.cells;      // one uint4 per entry
+        uint4 *t4 = reinterpret_cast<uint4 *>(p.cell_tag);  // tag, cnt, start: three arrays back to back
+        const long long n4 = (long long)(p.table_bytes >> 4);
         for (long long i = gtid; i < n4; i += nthr) t4[i] = make_uint4(0u, 0u, 0u, 0u);
     }
     grid.sync();
@@ -190,9 +188,8 @@ __global__ void __launch_bounds__(FRONT_THREADS) k_front(const PathParams p) {
         for (int j = 0; j < SCAN_ITEMS; ++j) {
             flag[j] = 0; cnt[j] = 0;
             if (keys[j] >= 0) {
-                const uint2 e = *reinterpret_cast<const uint2 *>(p.table + keys[j]);   // tag, cnt
-                flag[j] = (e.x == 0xFFFFFFFFu - (uint32_t)(base + j)) ? 1u : 0u;
-                cnt[j] = flag[j] ? e.y : 0u;
+                flag[j] = (p.cell_tag[keys[j]] == 0xFFFFFFFFu - (uint32_t)(base + j)) ? 1u : 0u;
+                cnt[j] = flag[j] ? p.cell_cnt[keys[j]] : 0u;
             }
             local += pack2(flag[j], cnt[j]);
         }
@@ -217,12 +214,13 @@ __global__ void __launch_bounds__(FRONT_THREADS) k_front(const PathParams p) {
     const long long chi = min(((long long)blockIdx.x + 1) * ctiles_per_cta, ctiles_total) * SCAN_TILE;
     {
         uint64_t mine = 0;
-        for (long long t0 = clo; t0 < chi; t0 += SCAN_TILE)
-#pragma unroll
-            for (int j = 0; j < SCAN_ITEMS; ++j) {
-                const long long c = t0 + tid * SCAN_ITEMS + j;
-                if (c < n_cells) mine += p.table[c].cnt;
+        for (long long t0 = clo; t0 < chi; t0 += SCAN_TILE) {
+            const long long c = t0 + tid * SCAN_ITEMS;          // 4 consecutive counts = one 16-byte load (arrays are padded)
+            if (c < n_cells) {
+                const uint4 v = *reinterpret_cast<const uint4 *>(p.cell_cnt + c);
+                mine += v.x + v.y + v.z + v.w;
             }
+        }
         const uint64_t total = block_sum(mine, s_warp, lane, warp);
         if (tid == 0) p.scan_desc[2048 + blockIdx.x] = total;
     }
@@ -260,8 +258,7 @@ __global__ void __launch_bounds__(FRONT_THREADS) k_front(const PathParams p) {
                 const uint32_t pillars = (uint32_t)(run >> 32);
                 s_excl[tid * SCAN_ITEMS + j] = pillars;
                 if (flag[j]) {
-                    CellEntry *e = p.table + keys[j];
-                    e->tag = pillars + 1u;     // raw pillar id + 1 (disjoint from the 0xFFFFFFFF-i values phase 1 left)
+                    p.cell_tag[keys[j]] = pillars + 1u;   // raw pillar id + 1 (disjoint from the 0xFFFFFFFF-i values phase 1 left)
                     // the pillar's record, in first-seen order (one thread per pillar pays the divisions)
                     const int key = keys[j];
                     const int b = key / p.cells, rem = key - b * p.cells;
@@ -296,7 +293,13 @@ __global__ void __launch_bounds__(FRONT_THREADS) k_front(const PathParams p) {
             const long long c0 = t0 + tid * SCAN_ITEMS;
             uint32_t cn[SCAN_ITEMS], local = 0;
 #pragma unroll
-            for (int j = 0; j < SCAN_ITEMS; ++j) { cn[j] = (c0 + j < n_cells) ? p.table[c0 + j].cnt : 0u; local += cn[j]; }
+            for (int j = 0; j < SCAN_ITEMS; ++j) cn[j] = 0u;
+            if (c0 < n_cells) {
+                const uint4 v = *reinterpret_cast<const uint4 *>(p.cell_cnt + c0);
+                cn[0] = v.x; cn[1] = v.y; cn[2] = v.z; cn[3] = v.w;
+            }
+#pragma unroll
+            for (int j = 0; j < SCAN_ITEMS; ++j) local += cn[j];
             uint32_t incl = local;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
@@ -313,12 +316,9 @@ __global__ void __launch_bounds__(FRONT_THREADS) k_front(const PathParams p) {
                 if (w < warp) warp_off += v;
                 tile_total += v;
             }
-            uint32_t run = carry + warp_off + (incl - local);
-#pragma unroll
-            for (int j = 0; j < SCAN_ITEMS; ++j) {
-                if (c0 + j < n_cells) p.table[c0 + j].start = run;
-                run += cn[j];
-            }
+            const uint32_t run = carry + warp_off + (incl - local);
+            if (c0 < n_cells)
+                *reinterpret_cast<uint4 *>(p.cell_start + c0) = make_uint4(run, run + cn[0], run + cn[0] + cn[1], run + cn[0] + cn[1] + cn[2]);
             carry += tile_total;
         }
     }
@@ -527,7 +527,7 @@ __global__ void __launch_bounds__(PFN_THREADS, 4) k_pfn(const PathParams p) {
         int4 pr = make_int4(0, 0, 0, 0);
         if (m < m_raw) pr = __ldg(p.prec + m);
         const int cnt = pr.y, pb = pr.z >> 16, pz = pr.z & 0xFFFF, py = pr.w >> 16, px = pr.w & 0xFFFF;
-        const int start = (m < m_raw) ? (int)__ldg(&p.table[pr.x].start) : 0;   // CSR start of the pillar's cell
+        const int start = (m < m_raw) ? (int)__ldg(p.cell_start + pr.x) : 0;   // CSR start of the pillar's cell
         const int local = m - s_R[pb];
         const bool kept = (m < m_raw) && (local < maxv);      // pillars beyond max_voxels were never created
         const int f = s_K[pb] + local;                          // final pillar id (first-seen order, frames concatenated)
@@ -816,7 +816,6 @@ k_emit(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtenso
     const int maxv = p.max_voxels, Pmax = p.P;
     const float vsx = p.vsize[0], vsy = p.vsize[1], vox = p.voff[0], voy = p.voff[1];
     const float cz = __fadd_rn(__fmul_rn(0.f, p.vsize[2]), p.voff[2]);     // z index 0: fl(fl(0*vz)+z_off)
-    const CellEntry *__restrict__ table = p.table;
     const float *__restrict__ grows = p.sorted_rows;
     const unsigned lt = (1u << lane) - 1u;
     const uint64_t stream_policy = l2_policy_evict_first();   // canvas: written once, never re-read here
@@ -910,8 +909,12 @@ k_emit(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtenso
     auto load_entry = [&](const TilePos &t) -> uint4 {
         const int x = t.xt * 32 + lane;
         // row r = b*ny + y and the table is [b][y][x]: the cell index is r*nx + x
-        return (t.r < n_rows && x < p.nx) ? __ldg(reinterpret_cast<const uint4 *>(table + (size_t)t.r * p.nx + x))
-                                          : make_uint4(0, 0, 0, 0);
+        uint4 e = make_uint4(0, 0, 0, 0);
+        if (t.r < n_rows && x < p.nx) {
+            const size_t c = (size_t)t.r * p.nx + x;
+            e.x = __ldg(p.cell_tag + c); e.y = __ldg(p.cell_cnt + c); e.z = __ldg(p.cell_start + c);
+        }
+        return e;
     };
     // the tile's rows are sorted_rows[row0, row0 + total): one cooperative async copy of (at most STAGE_W of) them
     auto issue_stage = [&](const uint4 e, float *stg) {

@@ -19,7 +19,8 @@ struct PathParams {
     uint32_t *ticket;                  // [1]      zeroed
     uint64_t *scan_desc;               // [tiles]  zeroed
     int32_t *frame_raw_base;           // [B+1]    zeroed; raw (pre max_voxels) pillar id at each frame start
-    CellEntry *table;                  // [B*cells] zeroed
+    uint32_t *cell_tag, *cell_cnt, *cell_start;   // [B*cells] each (padded to 16 entries), back to back; zeroed by k_front
+    size_t table_bytes;                // bytes of the three arrays together
     int32_t *frame_offsets;            // [B+1] (aliases frame_offsets_in when given)
     int32_t *key;                      // [n] cell key of each point, -1 = outside the grid
     uint32_t *arrival;                 // [n] unordered arrival rank of the point inside its cell
@@ -40,7 +41,7 @@ struct WorkspaceLayout {
     size_t zero_bytes;     // leading region that must be zero at the start of every call
     size_t off_ticket, off_desc, off_raw_base, off_table;
     size_t off_frame_offsets, off_key, off_arrival, off_sorted_rows, off_prec;
-    size_t total;
+    size_t total, cell_array_bytes;
     int scan_tiles, RW;
 };
 
@@ -54,7 +55,8 @@ inline WorkspaceLayout workspace_layout(int64_t n, int B, int64_t cells, int F) 
     w.off_ticket = o;      o = align_up(o + 16, 256);
     w.off_desc = o;        o = align_up(o + sizeof(uint64_t) * 4096, 256);          // per-CTA slice totals of k_front's scan
     w.off_raw_base = o;    o = align_up(o + sizeof(int32_t) * (size_t)(B + 1), 256);
-    w.off_table = o;       o = align_up(o + sizeof(CellEntry) * (size_t)B * (size_t)cells, 256);
+    w.cell_array_bytes = align_up(sizeof(uint32_t) * ((size_t)B * (size_t)cells + 16), 256);
+    w.off_table = o;       o = o + 3 * w.cell_array_bytes;
     w.zero_bytes = o;
     w.off_frame_offsets = o; o = align_up(o + sizeof(int32_t) * (size_t)(B + 1), 256);
     w.off_key = o;         o = align_up(o + sizeof(int32_t) * (size_t)n, 256);
