@@ -59,8 +59,13 @@ __device__ __forceinline__ int find_frame(const int32_t *__restrict__ off, int B
     return lo;
 }
 
-// phase 1 body for point i (every lane of the warp calls it, i >= n for the padding lanes)
-__device__ __forceinline__ void count_point(const PathParams &p, int i, int lane) {
+// phase 1, split in three so that two points per thread can be in flight at once:
+//   point_key     loads the point, derives frame_offsets on the fly, returns the cell key (-1 = outside the grid)
+//   count_issue   warp-aggregated atomics: lanes of the same cell elect the lowest lane (= lowest point index), which
+//                 adds the group size to the cell count and maxes the inverted index into the tag
+//   count_finish  broadcasts the leader's base and stores key + arrival rank
+// every lane of the warp calls them (i >= n for the padding lanes)
+__device__ __forceinline__ int point_key(const PathParams &p, int i) {
     int key = -1;
     if (i < p.n) {
         const float *row = p.pts + (size_t)i * p.stride;
@@ -91,15 +96,20 @@ __device__ __forceinline__ void count_point(const PathParams &p, int i, int lane
                         (qz >= 0.f) && (qz < (float)p.nz);
         if (ok) key = b * p.cells + (__float2int_rz(qz) * p.ny + __float2int_rz(qy)) * p.nx + __float2int_rz(qx);
     }
-    // warp-aggregated atomics: lanes of the same cell elect the lowest lane (= lowest point index)
+    return key;
+}
+__device__ __forceinline__ unsigned count_issue(const PathParams &p, int i, int key, int lane, int &leader, int &rank) {
     const unsigned peers = __match_any_sync(FULL, key);
-    const int leader = __ffs(peers) - 1;
-    const int rank = __popc(peers & ((1u << lane) - 1u));
+    leader = __ffs(peers) - 1;
+    rank = __popc(peers & ((1u << lane) - 1u));
     unsigned base = 0;
     if (lane == leader && key >= 0) {
         base = atomicAdd(p.cell_cnt + key, (unsigned)__popc(peers));
         atomicMax(p.cell_tag + key, 0xFFFFFFFFu - (unsigned)i);
     }
+    return base;
+}
+__device__ __forceinline__ void count_finish(const PathParams &p, int i, int key, unsigned base, int leader, int rank) {
     base = __shfl_sync(FULL, base, leader);
     if (i < p.n) {
         p.key[i] = key;
@@ -171,7 +181,18 @@ __global__ void __launch_bounds__(FRONT_THREADS) k_front(const PathParams p) {
     // ---- phase 1: count ----
     {
         const long long n_pad = ((long long)p.n + 31) & ~31ll;
-        for (long long i = gtid; i < n_pad; i += nthr) count_point(p, (int)i, lane);
+        for (long long i = gtid; i < n_pad; i += 2 * nthr) {
+            const long long i2 = i + nthr;                     // a second, independent point: its loads and atomics overlap the first's
+            const bool two = i2 < n_pad;                       // warp-uniform (n_pad and nthr are multiples of 32)
+            const int k1 = point_key(p, (int)i);
+            const int k2 = two ? point_key(p, (int)i2) : -1;
+            int l1, r1, l2 = 0, r2 = 0;
+            const unsigned b1 = count_issue(p, (int)i, k1, lane, l1, r1);
+            unsigned b2 = 0;
+            if (two) b2 = count_issue(p, (int)i2, k2, lane, l2, r2);
+            count_finish(p, (int)i, k1, b1, l1, r1);
+            if (two) count_finish(p, (int)i2, k2, b2, l2, r2);
+        }
     }
     grid.sync();
     stamp(2);
@@ -325,7 +346,10 @@ __global__ void __launch_bounds__(FRONT_THREADS) k_front(const PathParams p) {
     grid.sync();
     stamp(4);
     // ---- phase 3: fill ----
-    for (long long i = gtid; i < p.n; i += nthr) fill_point(p, (int)i);
+    for (long long i = gtid; i < p.n; i += 2 * nthr) {
+        fill_point(p, (int)i);
+        if (i + nthr < p.n) fill_point(p, (int)(i + nthr));
+    }
     stamp(5);
 }
 
