@@ -901,10 +901,12 @@ k_emit(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtenso
     // a dense tile costs ten times a sparse one, and a static assignment leaves the unlucky warps running alone at the end.
     constexpr int CHUNK = 4;
     const int n_tiles = n_rows * tiles_per_row;
-    auto fetch_chunk = [&]() -> int {
+    // the ticket stays in lane 0's register until the chunk is actually started: broadcasting it right away would
+    // stall the whole warp on the atomic's round trip
+    auto fetch_chunk_raw = [&]() -> int {
         int v = 0;
         if (lane == 0) v = (int)atomicAdd(p.ticket + 1, 1u);
-        return __shfl_sync(FULL, v, 0) * CHUNK;
+        return v;
     };
     auto decode = [&](int t) -> TilePos {
         TilePos q;
@@ -913,17 +915,17 @@ k_emit(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtenso
         q.b = q.r / rows_per_frame; q.zy = q.r - q.b * rows_per_frame;
         return q;
     };
-    int seq_left = CHUNK, seq_next = 0;                   // tiles left in the current chunk; base of the prefetched next chunk
-    TilePos seq = decode(fetch_chunk());                   // the furthest tile handed to the pipeline so far
-    seq_next = fetch_chunk();
+    int seq_left = CHUNK, seq_next_raw = 0;               // tiles left in the current chunk; ticket of the prefetched next chunk (lane 0)
+    TilePos seq = decode(__shfl_sync(FULL, fetch_chunk_raw(), 0) * CHUNK);   // the furthest tile handed to the pipeline so far
+    seq_next_raw = fetch_chunk_raw();
     auto next_tile = [&]() -> TilePos {
         if (seq_left > 1 && seq.r < n_rows) {
             --seq_left;
             if (++seq.xt == tiles_per_row) { seq.xt = 0; ++seq.r; if (++seq.zy == rows_per_frame) { seq.zy = 0; ++seq.b; } }
         } else {
-            seq = decode(seq_next);
+            seq = decode(__shfl_sync(FULL, seq_next_raw, 0) * CHUNK);
             seq_left = CHUNK;
-            if (seq.r < n_rows) seq_next = fetch_chunk();
+            if (seq.r < n_rows) seq_next_raw = fetch_chunk_raw();
         }
         return seq;
     };

@@ -4,6 +4,7 @@ They keep the reference's plugin API (constructor keywords, `forward(batch_dict)
 `get_output_feature_dim`, `num_bev_features`) and parameter names, so reference checkpoints load:
 
   PillarVFE            <-> pcdet/models/backbones_3d/vfe/pillar_vfe.py:52-123   (VFE.NAME: PillarVFE)
+  Radar7PillarVFE      <-> pcdet/models/backbones_3d/vfe/pillar_vfe.py:125-271  (VFE.NAME: Radar7PillarVFE)
   PointPillarScatter   <-> pcdet/models/backbones_2d/map_to_bev/pointpillar_scatter.py:5-41
   FusedPillarVFE       points -> pillars -> PillarVFE -> canvas in one native call; used with
                        DATA_PROCESSOR `transform_points_to_voxels_placeholder`
@@ -104,6 +105,74 @@ class PillarVFE(_VFEBase):
         return batch_dict
 
 
+class Radar7PillarVFE(nn.Module):
+    """The VoD radar variant (pillar_vfe.py:125-271): the raw features entering the PFN are chosen by the flags
+    USE_XYZ / USE_RCS / USE_VR / USE_VR_COMP / USE_TIME (ascending column order x y z rcs v_r v_r_comp time), and with
+    USE_ELEVATION False z is zeroed IN PLACE in batch_dict['voxels'] before anything else, exactly as the reference does.
+
+    It runs on the same native kernel as PillarVFE: the Linear weight [C, Cin_selected] is expanded to the full
+    [C, 7 + 6] layout with zero columns for the unselected features.  The kernel's dot product is a sequential fmaf in
+    column order, and fmaf(x, 0, acc) == acc exactly for finite x, so the result is bit-identical to evaluating the
+    selected columns only (checked against the reference's own outputs, tests/golden/radar7_*.npz).
+    USE_DISTANCE must be False: the reference itself fails with it (it appends the range without widening the Linear)."""
+
+    AVAILABLE = ['x', 'y', 'z', 'rcs', 'v_r', 'v_r_comp', 'time']
+
+    def __init__(self, model_cfg, num_point_features, voxel_size, point_cloud_range, grid_size=None, **kwargs):
+        super().__init__()
+        _lib.load()
+        self.model_cfg = model_cfg
+        self.use_norm = self.model_cfg.USE_NORM
+        self.use_xyz = self.model_cfg.USE_XYZ
+        self.with_distance = self.model_cfg.USE_DISTANCE
+        params = ["USE_RCS", "USE_VR", "USE_VR_COMP", "USE_TIME", "USE_ELEVATION"]
+        if not all(hasattr(self.model_cfg, a) for a in params):
+            raise Exception("config does not have the right parameters, please use a radar config")
+        if self.with_distance:
+            raise NotImplementedError("Radar7PillarVFE with USE_DISTANCE: the reference's own forward fails "
+                                      "(Linear width does not count the range feature)")
+        self.use_elevation = self.model_cfg.USE_ELEVATION
+        sel = []
+        if self.use_xyz:
+            sel += [0, 1, 2]
+        for flag, name in (("USE_RCS", 'rcs'), ("USE_VR", 'v_r'), ("USE_VR_COMP", 'v_r_comp'), ("USE_TIME", 'time')):
+            if getattr(self.model_cfg, flag):
+                sel.append(self.AVAILABLE.index(name))
+        self.selected_indexes = torch.LongTensor(sel)
+        self.z_ind = 2
+        self.num_filters = list(self.model_cfg.NUM_FILTERS)
+        if len(self.num_filters) != 1:
+            raise NotImplementedError("single-layer PFN only (NUM_FILTERS: [64])")
+        self.pfn_layers = nn.ModuleList([_PFNLayerParams(len(sel) + 6, self.num_filters[0], self.use_norm, True)])
+        self.voxel_size = [float(v) for v in voxel_size]
+        self.path = PillarPath(point_cloud_range, self.voxel_size, max_points_per_voxel=1, max_voxels=1,
+                               num_point_features=7, grid_size=grid_size)
+
+    def get_output_feature_dim(self):
+        return self.num_filters[-1]
+
+    def _expanded(self) -> PfnWeights:
+        layer = self.pfn_layers[0]
+        w = layer.linear.weight.detach()
+        full = torch.zeros((w.shape[0], 13), dtype=w.dtype, device=w.device)
+        k = len(self.selected_indexes)
+        full[:, self.selected_indexes.to(w.device)] = w[:, :k]        # raw features, in place
+        full[:, 7:13] = w[:, k:k + 6]                                 # f_cluster, f_center
+        pf = layer.weights(True, False)
+        pf.weight = full
+        return pf
+
+    def forward(self, batch_dict, **kwargs):
+        if self.training and torch.is_grad_enabled():
+            raise NotImplementedError("hgsfusion_b200 modules are forward-only this round: call .eval() / no_grad()")
+        voxels, num, coords = batch_dict['voxels'], batch_dict['voxel_num_points'], batch_dict['voxel_coords']
+        if not self.use_elevation:
+            voxels[:, :, self.z_ind] = 0          # in place on the caller's tensor, like pillar_vfe.py:232-233
+        features = self.path.pillar_vfe(voxels, coords, num, self._expanded())
+        batch_dict['pillar_features'] = features.view(-1, 1, features.shape[-1]).squeeze()
+        return batch_dict
+
+
 class PointPillarScatter(nn.Module):
     """pillar_features + voxel_coords -> spatial_features [B, C, ny, nx]."""
 
@@ -200,8 +269,10 @@ def register(vfe_all: dict | None = None, map_to_bev_all: dict | None = None, ov
     if vfe_all is not None:
         vfe_all['FusedPillarVFE'] = FusedPillarVFE
         vfe_all['PillarVFEB200'] = PillarVFE
+        vfe_all['Radar7PillarVFEB200'] = Radar7PillarVFE
         if override:
             vfe_all['PillarVFE'] = PillarVFE
+            vfe_all['Radar7PillarVFE'] = Radar7PillarVFE
     if map_to_bev_all is not None:
         map_to_bev_all['PillarScatterPassthrough'] = PillarScatterPassthrough
         map_to_bev_all['PointPillarScatterB200'] = PointPillarScatter

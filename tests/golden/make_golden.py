@@ -44,7 +44,7 @@ def load_reference():
     load("refvfe.vfe_template", f"{REF}/pcdet/models/backbones_3d/vfe/vfe_template.py")
     vfe = load("refvfe.pillar_vfe", f"{REF}/pcdet/models/backbones_3d/vfe/pillar_vfe.py")
     sc = load("refscatter", f"{REF}/pcdet/models/backbones_2d/map_to_bev/pointpillar_scatter.py")
-    return vfe.PillarVFE, sc.PointPillarScatter
+    return vfe.PillarVFE, sc.PointPillarScatter, vfe.Radar7PillarVFE
 
 
 CASES = [
@@ -111,9 +111,59 @@ def run_case(PillarVFE, PointPillarScatter, name, config, B, n, P, max_voxels, m
                                  torch.__version__, np.__version__])), canvas
 
 
+RADAR7_CASES = [
+    # name, flags (USE_XYZ, USE_RCS, USE_VR, USE_VR_COMP, USE_TIME, USE_ELEVATION, USE_DISTANCE), P
+    ("radar7_all",        dict(USE_XYZ=True, USE_RCS=True, USE_VR=True, USE_VR_COMP=True, USE_TIME=True, USE_ELEVATION=True, USE_DISTANCE=False), 10),
+    ("radar7_subset_noz", dict(USE_XYZ=True, USE_RCS=True, USE_VR=False, USE_VR_COMP=True, USE_TIME=False, USE_ELEVATION=False, USE_DISTANCE=False), 10),
+    ("radar7_p32_sparse", dict(USE_XYZ=True, USE_RCS=False, USE_VR=False, USE_VR_COMP=True, USE_TIME=True, USE_ELEVATION=True, USE_DISTANCE=False), 32),
+    # USE_DISTANCE=True cannot be pinned: the reference itself crashes (it appends the range feature without
+    # counting it in the Linear's input width, pillar_vfe.py:133,250-252)
+]
+
+
+def run_radar7(Radar7PillarVFE, name, flags, P):
+    """Radar7PillarVFE (pillar_vfe.py:125-271): feature selection by flags, optional in-place zeroing of z."""
+    import contextlib, io
+    cfg = synthetic.CONFIGS["vod"]
+    geom = oracle.Geometry(cfg["pc_range"], cfg["voxel_size"])
+    pts, offs = synthetic.make_batch("vod", 1, 2500, "clustered", seed0=31, oob_fraction=0.02)
+    vox, c3, num = oracle.voxelize(pts, geom, P, 40000, F=7, xcol=1)
+    coords = np.concatenate([np.zeros((c3.shape[0], 1), np.int32), c3], axis=1)
+    model_cfg = SimpleNamespace(USE_NORM=True, NUM_FILTERS=[64], **flags)
+    with contextlib.redirect_stdout(io.StringIO()):          # the reference prints its feature list
+        vfe = Radar7PillarVFE(model_cfg=model_cfg, num_point_features=7, voxel_size=list(cfg["voxel_size"]),
+                              point_cloud_range=np.array(cfg["pc_range"], dtype=np.float32))
+    Cin = vfe.pfn_layers[0].linear.weight.shape[1]
+    w = synthetic.make_pfn(Cin, 64, seed=len(name))
+    sd = vfe.state_dict()
+    sd["pfn_layers.0.linear.weight"] = torch.from_numpy(w.weight)
+    sd["pfn_layers.0.norm.weight"] = torch.from_numpy(w.gamma)
+    sd["pfn_layers.0.norm.bias"] = torch.from_numpy(w.beta)
+    sd["pfn_layers.0.norm.running_mean"] = torch.from_numpy(w.running_mean)
+    sd["pfn_layers.0.norm.running_var"] = torch.from_numpy(w.running_var)
+    vfe.load_state_dict(sd)
+    vfe.eval()
+    bd = dict(voxels=torch.from_numpy(vox.copy()).float(), voxel_coords=torch.from_numpy(coords).float(),
+              voxel_num_points=torch.from_numpy(num).float())
+    with torch.no_grad():
+        bd = vfe(bd)
+    return dict(voxels=vox, voxel_coords=coords, voxel_num_points=num, weight=w.weight, gamma=w.gamma, beta=w.beta,
+                running_mean=w.running_mean, running_var=w.running_var,
+                ref_invstd=(1 / torch.sqrt(torch.from_numpy(w.running_var) + 1e-3)).numpy(),
+                selected_indexes=vfe.selected_indexes.numpy().astype(np.int32),
+                pillar_features=bd["pillar_features"].numpy(),
+                voxels_after=bd["voxels"].numpy(),            # the reference zeroes z in place when USE_ELEVATION is False
+                flags=np.asarray([f"{k}={int(v)}" for k, v in flags.items()]), P=np.asarray(P))
+
+
 def main():
     check = "--check" in sys.argv
-    PillarVFE, PointPillarScatter = load_reference()
+    PillarVFE, PointPillarScatter, Radar7PillarVFE = load_reference()
+    for name, flags, P in RADAR7_CASES:
+        data = run_radar7(Radar7PillarVFE, name, flags, P)
+        path = os.path.join(HERE, f"{name}.npz")
+        np.savez_compressed(path, **data)
+        print(f"{name:18s} M={data['voxels'].shape[0]:6d} Cin={data['weight'].shape[1]} -> {os.path.basename(path)} ({os.path.getsize(path) / 1e3:.0f} kB)")
     torch.manual_seed(0)
     for case in CASES:
         data, canvas = run_case(PillarVFE, PointPillarScatter, *case)

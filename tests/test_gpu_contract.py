@@ -169,3 +169,25 @@ def test_use_norm_false_and_relative_xyz_and_distance(cuda):
         assert np.array_equal(got["voxel_coords"].cpu().numpy(), ref["voxel_coords"])
         assert bits_equal(got["pillar_features"].cpu().numpy(), ref["pillar_features"]), (use_abs, with_dist, use_norm)
         assert bits_equal(got["spatial_features"].cpu().numpy(), ref["spatial_features"])
+
+
+RADAR7 = sorted(glob.glob(os.path.join(HERE, "golden", "radar7_*.npz")))
+
+
+@pytest.mark.parametrize("path", RADAR7, ids=[os.path.basename(p)[:-4] for p in RADAR7])
+def test_radar7_module_against_reference_fixture(cuda, path):
+    d = np.load(path)
+    cfg = synthetic.CONFIGS["vod"]
+    flags = {str(f).split("=")[0]: bool(int(str(f).split("=")[1])) for f in d["flags"]}
+    m = modules.Radar7PillarVFE(model_cfg=SimpleNamespace(USE_NORM=True, NUM_FILTERS=[64], **flags), num_point_features=7,
+                                voxel_size=cfg["voxel_size"], point_cloud_range=np.asarray(cfg["pc_range"], dtype=np.float32))
+    assert m.selected_indexes.tolist() == d["selected_indexes"].tolist()
+    _load_weights(m, SimpleNamespace(weight=d["weight"], gamma=d["gamma"], beta=d["beta"], running_mean=d["running_mean"],
+                                     running_var=d["running_var"]))
+    m = m.to(cuda).eval()
+    bd = dict(voxels=torch.from_numpy(d["voxels"].copy()).to(cuda), voxel_coords=torch.from_numpy(d["voxel_coords"]).to(cuda).float(),
+              voxel_num_points=torch.from_numpy(d["voxel_num_points"]).to(cuda).float())
+    with torch.no_grad():
+        bd = m(bd)
+    assert features_close(bd["pillar_features"].cpu().numpy(), d["pillar_features"], RTOL)
+    assert np.array_equal(bd["voxels"].cpu().numpy(), d["voxels_after"])        # same in-place side effect on z

@@ -71,3 +71,30 @@ def test_fixture_voxels_come_from_the_oracle_voxelizer(path):
     assert np.array_equal(res["voxel_coords"], d["voxel_coords"])
     assert np.array_equal(res["voxel_num_points"], d["voxel_num_points"])
     assert np.array_equal(res["voxels"], d["voxels"])
+
+
+RADAR7 = sorted(glob.glob(os.path.join(HERE, "golden", "radar7_*.npz")))
+
+
+def expand_radar7_weight(w, selected):
+    """[C, len(sel)+6] -> [C, 13]: zero columns for the unselected raw features (modules.Radar7PillarVFE._expanded)."""
+    full = np.zeros((w.shape[0], 13), dtype=np.float32)
+    k = len(selected)
+    full[:, selected] = w[:, :k]
+    full[:, 7:13] = w[:, k:k + 6]
+    return full
+
+
+@pytest.mark.parametrize("path", RADAR7, ids=[os.path.basename(p)[:-4] for p in RADAR7])
+def test_radar7_equals_zero_column_pillar_vfe(path):
+    """Radar7PillarVFE (pillar_vfe.py:125-271) == PillarVFE arithmetic with zero weight columns, bit for bit."""
+    d = np.load(path)
+    cfg = synthetic.CONFIGS["vod"]
+    geom = oracle.Geometry(cfg["pc_range"], cfg["voxel_size"])
+    pfn = oracle.PfnParams(expand_radar7_weight(d["weight"], d["selected_indexes"]), d["gamma"], d["beta"],
+                           d["running_mean"], d["running_var"])
+    got = oracle.pillar_vfe(d["voxels_after"], d["voxel_coords"], d["voxel_num_points"], geom, pfn,
+                            invstd_override=d["ref_invstd"])
+    assert np.array_equal(got.view(np.uint32), d["pillar_features"].view(np.uint32))
+    noz = any(str(f) == "USE_ELEVATION=0" for f in d["flags"])
+    assert (d["voxels_after"][:, :, 2] == 0).all() == noz          # z zeroed in place only without elevation
