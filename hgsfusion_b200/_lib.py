@@ -17,7 +17,7 @@ EXPORTS = ["hgsf_abi_version", "hgsf_status_string", "hgsf_pillar_capacity", "hg
            "hgsf_pillarize", "hgsf_points_to_bev", "hgsf_pillar_vfe", "hgsf_scatter_workspace_size",
            "hgsf_pointpillar_scatter", "hgsf_last_launch_count", "hgsf_emit_timing_begin", "hgsf_emit_timing_collect",
            "hgsf_pillarnet_workspace_size", "hgsf_pillarnet_indices", "hgsf_gather_feature", "hgsf_gather_feature_grad",
-           "hgsf_scatter_max", "hgsf_scatter_max_grad"]
+           "hgsf_scatter_max", "hgsf_scatter_max_grad", "hgsf_split_encode"]
 
 
 class Geometry(C.Structure):
@@ -85,6 +85,8 @@ def load():
     lib.hgsf_gather_feature_grad.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]
     lib.hgsf_scatter_max.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.hgsf_scatter_max_grad.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p]
+    lib.hgsf_split_encode.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                      C.POINTER(C.c_float), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.hgsf_emit_timing_begin.argtypes = [C.c_int]
     lib.hgsf_emit_timing_collect.argtypes = [C.POINTER(C.c_float), C.c_int]
     for name in EXPORTS:

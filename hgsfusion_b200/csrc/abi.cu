@@ -240,4 +240,29 @@ int hgsf_scatter_max_grad(const int32_t *arg, const float *grad_out, int32_t C, 
     return st;
 }
 
+int hgsf_split_encode(const float *points, int64_t n_rows, int32_t Fin, int32_t Fout, int32_t n_split, int32_t batch_size,
+                      int32_t encoding, const float *pc_min, const int32_t *order, float *xyz, float *pt_features,
+                      int32_t *xyz_batch_cnt, int32_t *info, hgsf_stream_t stream) {
+    g_last_launches = 0;
+    if (n_rows < 0 || Fin < 3 || batch_size <= 0 || !pc_min || !xyz_batch_cnt || !info) return HGSF_ERR_INVALID_ARG;
+    if (n_rows > 0 && (!points || !xyz || !pt_features)) return HGSF_ERR_INVALID_ARG;
+    if (Fin + 1 > 40 || batch_size > 32767) return HGSF_ERR_UNSUPPORTED;
+    switch (encoding) {
+        case HGSF_ENCODE_SPLIT:
+            if (Fin < 5 || n_split < 0 || 3 + n_split > Fin - 2 || Fout < 3 + 2 * n_split + 2) return HGSF_ERR_INVALID_ARG;
+            break;
+        case HGSF_ENCODE_COPY: if (Fout != Fin) return HGSF_ERR_INVALID_ARG; break;
+        case HGSF_ENCODE_DIRECT: if (Fin < 5 || Fout != Fin - 2) return HGSF_ERR_INVALID_ARG; break;
+        default: return HGSF_ERR_INVALID_ARG;
+    }
+    SplitEncodeParams q{};
+    q.points = points; q.order = order; q.L = n_rows; q.Fin = Fin; q.Fout = Fout; q.n_split = n_split;
+    q.B = batch_size; q.mode = encoding;
+    for (int j = 0; j < 3; ++j) q.pc_min[j] = pc_min[j];
+    q.xyz = xyz; q.feat = pt_features; q.cnt = xyz_batch_cnt; q.info = info;
+    const int st = launch_split_encode(q, static_cast<cudaStream_t>(stream));
+    if (st == HGSF_OK) g_last_launches = n_rows > 0;
+    return st;
+}
+
 }  // extern "C"

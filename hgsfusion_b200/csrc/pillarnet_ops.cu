@@ -319,4 +319,90 @@ int launch_scatter_max_grad(int C, long long M, const int *arg, const float *gou
     return (int)cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------------
+// Reader input prep (vfe/pillarnet.py:51-58 + dynamic_pillar_encoder.py:55-118): split the collated points by frame, build
+// the "split" real/virtual feature rows and the range-relative xyz.  A warp stages 32 input rows in shared memory (one
+// coalesced span when the rows are taken in input order) and writes 32 output rows as one coalesced span.
+//   info[0] bit 0: the emitted order is not the reference's (rows not grouped by ascending frame, or a dropped row before
+//                  a kept one) -> the caller must pass `order`;  info[1] = rows kept.
+constexpr int ENC_THREADS = 256;
+constexpr int ENC_MAX_W = 40;     // 1 + Fin
+
+__global__ void __launch_bounds__(ENC_THREADS) k_split_encode(const SplitEncodeParams q) {
+    __shared__ float s_rows[ENC_THREADS / 32][32 * ENC_MAX_W];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    float *rows = s_rows[wib];
+    const int W = q.Fin + 1, Fo = q.Fout, n = q.n_split;
+    const long long nw = ((long long)gridDim.x * ENC_THREADS) >> 5;
+    for (long long r0 = ((((long long)blockIdx.x * ENC_THREADS) >> 5) + wib) * 32; r0 < q.L; r0 += nw * 32) {
+        const int nr = (int)min((long long)32, q.L - r0);
+        if (q.order == nullptr) {
+            const float *src = q.points + (size_t)r0 * W;
+            for (int e = lane; e < nr * W; e += 32) rows[e] = __ldg(src + e);
+        } else {
+            for (int e = lane; e < nr * W; e += 32) {
+                const int r = e / W, c = e - r * W;
+                rows[e] = __ldg(q.points + (size_t)__ldg(q.order + r0 + r) * W + c);
+            }
+        }
+        __syncwarp();
+        // frame key of my row: the frame index when the reference keeps the row (`points[:,0] == i` for an i in [0, B)), else B
+        int key = q.B;
+        if (lane < nr) {
+            const float b = rows[lane * W];
+            if (b >= 0.f && b < (float)q.B && b == truncf(b)) key = (int)b;
+        }
+        int prev = __shfl_up_sync(FULL, key, 1);
+        if (lane == 0) {
+            prev = 0;
+            if (r0 > 0) {
+                const long long pr = q.order ? (long long)__ldg(q.order + r0 - 1) : r0 - 1;
+                const float b = __ldg(q.points + (size_t)pr * W);
+                prev = (b >= 0.f && b < (float)q.B && b == truncf(b)) ? (int)b : q.B;
+            }
+        }
+        const bool keep = key < q.B;
+        const unsigned bad = __ballot_sync(FULL, lane < nr && key < prev);
+        const unsigned peers = __match_any_sync(FULL, key);
+        if (keep && lane == __ffs(peers) - 1) atomicAdd(q.cnt + key, __popc(peers));
+        const unsigned kept = __ballot_sync(FULL, keep);
+        if (lane == 0) {
+            if (bad) atomicOr(q.info, 1);
+            if (kept) atomicAdd(q.info + 1, __popc(kept));
+        }
+        // xyz relative to the range minimum: one rounded fp32 subtract per coordinate (absl_to_relative, :46-53)
+        for (int e = lane; e < nr * 3; e += 32) {
+            const int r = e / 3, c = e - r * 3;
+            if ((kept >> r) & 1) q.xyz[(size_t)r0 * 3 + e] = __fsub_rn(rows[r * W + 1 + c], c == 0 ? q.pc_min[0] : (c == 1 ? q.pc_min[1] : q.pc_min[2]));
+        }
+        for (int e = lane; e < nr * Fo; e += 32) {
+            const int r = e / Fo, c = e - r * Fo;
+            if (!((kept >> r) & 1)) continue;
+            const float *row = rows + r * W + 1;
+            float v;
+            if (q.mode == HGSF_ENCODE_SPLIT) {
+                const bool virt = row[q.Fin - 2] < 0.5f;                               // :68
+                if (c < 3) v = row[c];                                                  // :69
+                else if (c >= Fo - 2) v = row[q.Fin - 2 + (c - (Fo - 2))];              // :80-81
+                else if (c < 3 + n) v = virt ? 0.f : row[c];                            // :72 / :75
+                else if (c < 3 + 2 * n) v = virt ? row[c - n] : 0.f;                    // :73 / :76
+                else v = 0.f;
+            } else {
+                v = row[c];                                                             // mixed / plain: all columns; direct: Fout = Fin - 2
+            }
+            q.feat[(size_t)r0 * Fo + e] = v;
+        }
+        __syncwarp();
+    }
+}
+
+int launch_split_encode(const SplitEncodeParams &q, cudaStream_t s) {
+    cudaError_t e = cudaMemsetAsync(q.cnt, 0, sizeof(int) * (size_t)q.B, s);
+    if (e == cudaSuccess) e = cudaMemsetAsync(q.info, 0, sizeof(int) * 2, s);
+    if (e != cudaSuccess) return (int)e;
+    if (q.L == 0) return HGSF_OK;
+    k_split_encode<<<grid_for(q.L), ENC_THREADS, 0, s>>>(q);
+    return (int)cudaGetLastError();
+}
+
 }  // namespace hgsf

@@ -20,6 +20,20 @@ struct PillarNetParams {
     uint32_t *partial;       // workspace [8192] per-CTA slice totals (cells, points)
 };
 
+struct SplitEncodeParams {
+    const float *points;     // [L, 1 + Fin] collated points, column 0 = frame index (dataset.py:237-244)
+    const int *order;        // optional [L] row order (stable by frame); null = input order
+    long long L;
+    int Fin, Fout, n_split;  // split: Fout >= 3 + 2 n_split + 2 (VoD 17 -> 29, n = 12; TJ4D 18 -> 31, n = 13)
+    int B, mode;
+    float pc_min[3];
+    float *xyz;              // [L, 3] relative
+    float *feat;             // [L, Fout]
+    int *cnt;                // [B] xyz_batch_cnt
+    int *info;               // [2] {flags, rows kept}
+};
+
+int launch_split_encode(const SplitEncodeParams &q, cudaStream_t stream);
 int launch_pillarnet_indices(const PillarNetParams &q, cudaStream_t stream);
 int launch_gather(long long L, int C, const int *idx, const float *f, float *out, cudaStream_t s);
 int launch_gather_grad(long long L, int C, const int *idx, const float *gout, float *gin, cudaStream_t s);

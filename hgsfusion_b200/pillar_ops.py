@@ -8,6 +8,8 @@ native library (no `pillar_cuda`, no per-call host syncs inside the index genera
   scatter_utils.scatter_max   (ScatterMaxFunction) :7-45 scatter_max         (autograd, native backward)
   pillar_utils.PillarQueryAndGroup              :22-54   PillarQueryAndGroup
   pillar_modules.PillarMaxPooling               :10-82   PillarMaxPooling    (same parameter names: shared_mlps.0.weight, shared_mlps.1.*)
+  vfe/pillarnet.py:51-58 (per-frame split) + pillarnet_modules/dynamic_pillar_encoder.py:55-118   split_encode
+  dynamic_pillar_encoder.DynamicPillarFeatureNet :9-121  DynamicPillarFeatureNet (forward takes the collated points or the reference's list)
 
 `PillarMaxPooling.forward` returns `(pillar_features [M,C], pillars [M,3] (b,y,x), spatial_shape (Ny,Nx), batch_size)`
 and wraps them in `spconv.SparseConvTensor` only when spconv is importable (pillar_modules.py:82).
@@ -186,3 +188,83 @@ class PillarMaxPooling(nn.Module):
             return spconv.SparseConvTensor(pillar_features, pillar_indices, (self.bev_height, self.bev_width), B)
         except ImportError:
             return pillar_features, pillar_indices, (self.bev_height, self.bev_width), B
+
+
+_ENCODINGS = {"split": 0, "mixed": 1, "direct": 2}
+_SPLIT_N = {"vod": 12, "tj4d": 13}          # dynamic_pillar_encoder.py:72-76
+
+
+@torch.no_grad()
+def split_encode(points, pc_range, num_input, virtual=True, encoding_type="split", dataset="vod", batch_size=None):
+    """Collated `points [L, 1+Fin]` (frame index in column 0) -> `(xyz [L',3], xyz_batch_cnt [B] int32, pt_features
+    [L', Fout])`, what `PillarNet.forward` (vfe/pillarnet.py:51-58) and `DynamicPillarFeatureNet.forward`
+    (dynamic_pillar_encoder.py:55-118) hand to the reader.  One native launch and one 8-byte read (rows kept, order
+    flag) instead of `.max().item()` plus a boolean-mask pass per frame; `batch_size=None` reads it from column 0 like the
+    reference, `batch_dict['batch_size']` avoids that sync."""
+    _need_cuda(points, "points", torch.float32)
+    lib = _lib.load()
+    L, Fin = int(points.shape[0]), int(points.shape[1]) - 1
+    if batch_size is None:
+        batch_size = int(points[:, 0].max().item()) + 1                  # pillarnet.py:52
+    if not virtual:
+        mode, Fout, n = 1, Fin, 0
+    elif encoding_type == "split":
+        if dataset not in _SPLIT_N:
+            raise NotImplementedError(dataset)                            # :77-78
+        mode, Fout, n = 0, int(num_input), _SPLIT_N[dataset]
+    elif encoding_type == "mixed":
+        mode, Fout, n = 1, Fin, 0
+    elif encoding_type == "direct":
+        mode, Fout, n = 2, Fin - 2, 0
+    else:
+        raise NotImplementedError(encoding_type)                          # :97-98
+    dev = points.device
+    xyz = torch.empty((L, 3), dtype=torch.float32, device=dev)
+    feat = torch.empty((L, Fout), dtype=torch.float32, device=dev)
+    cnt = torch.empty((batch_size,), dtype=torch.int32, device=dev)
+    info = torch.empty((2,), dtype=torch.int32, device=dev)
+    pc_min = (C.c_float * 3)(*[float(v) for v in pc_range[:3]])
+
+    def run(order):
+        _lib.check(lib.hgsf_split_encode(_p(points), L, Fin, Fout, n, batch_size, mode, pc_min, _p(order), _p(xyz), _p(feat),
+                                         _p(cnt), _p(info), _s()), "hgsf_split_encode")
+        return [int(v) for v in info.tolist()]
+
+    flags, kept = run(None)
+    if flags & 1:
+        # rows not grouped by frame (never the case for a collated batch): a stable order by frame, dropped rows last
+        b = points[:, 0]
+        key = torch.where((b >= 0) & (b < batch_size) & (b == b.trunc()), b, torch.full_like(b, float(batch_size)))
+        order = torch.sort(key, stable=True).indices.to(torch.int32)
+        flags, kept = run(order)
+        assert not (flags & 1)
+    return xyz[:kept], cnt, feat[:kept]
+
+
+class DynamicPillarFeatureNet(nn.Module):
+    """Drop-in for pillarnet_modules/dynamic_pillar_encoder.py:9-121 (same constructor, same `pfn_layers.*` parameter
+    names).  `forward(example)` accepts the reference's `dict(points=[per-frame tensors])` or, without the Python split,
+    `dict(points=collated [L,1+Fin], batch_size=B)`."""
+
+    def __init__(self, num_input_features=2, num_filters=(32,), pillar_size=0.1, virtual=False,
+                 pc_range=(0, -40, -3, 70.4, 40, 1), encoding_type="split", dataset="vod", **kwargs):
+        super().__init__()
+        self.pc_range = pc_range
+        assert len(num_filters) > 0
+        self.num_input = num_input_features
+        self.pfn_layers = PillarMaxPooling(mlps=[6 + num_input_features] + list(num_filters), pillar_size=pillar_size,
+                                           point_cloud_range=pc_range)
+        self.virtual = virtual
+        self.encoding_type = encoding_type
+        self.dataset = dataset
+
+    def forward(self, example, **kwargs):
+        points = example.pop("points")
+        batch_size = example.get("batch_size")
+        if isinstance(points, (list, tuple)):
+            batch_size = len(points)
+            points = torch.cat([torch.cat([torch.full((p.shape[0], 1), float(i), dtype=p.dtype, device=p.device), p], dim=1)
+                                for i, p in enumerate(points)], dim=0).contiguous()
+        xyz, cnt, feat = split_encode(points, self.pc_range, self.num_input, self.virtual, self.encoding_type, self.dataset,
+                                      batch_size)
+        return self.pfn_layers(xyz, cnt, feat)

@@ -197,6 +197,32 @@ HGSF_API int hgsf_scatter_max(const int32_t *index, const float *src, int32_t C,
 HGSF_API int hgsf_scatter_max_grad(const int32_t *arg, const float *grad_out, int32_t C, int64_t M, float *grad_src,
                                    hgsf_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Path B input prep: PillarNet.forward's per-frame split (pcdet/models/backbones_3d/vfe/pillarnet.py:51-58) and
+ * DynamicPillarFeatureNet.forward's feature encoding (pillarnet_modules/dynamic_pillar_encoder.py:55-118) in ONE launch
+ * instead of the reference's Python loop of boolean-mask assigns per frame.
+ *   points [L, 1+Fin] fp32 collated points, column 0 = frame index (pcdet/datasets/dataset.py:237-244)
+ *   encoding  HGSF_ENCODE_SPLIT : USE_VIRTUAL_POINT + ENCODING_TYPE 'split' (:65-86): pt_features[:, :3] = xyz;
+ *                                 rows whose column Fin-2 is >= 0.5 (real) copy columns 3..3+n into 3..3+n, the others
+ *                                 (virtual) into 3+n..3+2n; the last two columns are the two flag columns; everything
+ *                                 else 0.  VoD: Fin 17, n 12, Fout 29 (:72-73); TJ4D: Fin 18, n 13, Fout 31 (:75-76)
+ *             HGSF_ENCODE_COPY  : 'mixed' or no virtual points (:87-91, :100-104): pt_features = the Fin columns
+ *             HGSF_ENCODE_DIRECT: 'direct' (:92-96): pt_features = the first Fin-2 columns
+ *   pc_min[3] range minimum; xyz [L,3] = points[:, 1:4] - pc_min (one fp32 subtract each, :46-53)
+ *   pt_features [L, Fout]; xyz_batch_cnt [B] int32 = rows per frame; info [2] int32 on the device:
+ *   info[1] = rows kept (rows whose frame index is not an integer in [0, B) match no `points[:,0] == i` mask and are
+ *   dropped, as in the reference); info[0] bit 0 set = rows were not grouped by ascending frame (or a dropped row
+ *   precedes a kept one), so the emitted order is not the reference's: call again with `order` [L] int32 = a stable
+ *   ordering of the rows by frame with the dropped rows last (NULL = input order; the collated batch is always grouped).
+ *   Rows [info[1], L) of the outputs are not written. */
+#define HGSF_ENCODE_SPLIT  0
+#define HGSF_ENCODE_COPY   1
+#define HGSF_ENCODE_DIRECT 2
+HGSF_API int hgsf_split_encode(const float *points, int64_t n_rows, int32_t Fin, int32_t Fout, int32_t n_split,
+                               int32_t batch_size, int32_t encoding, const float *pc_min, const int32_t *order,
+                               float *xyz, float *pt_features, int32_t *xyz_batch_cnt, int32_t *info,
+                               hgsf_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -156,8 +156,85 @@ def run_radar7(Radar7PillarVFE, name, flags, P):
                 flags=np.asarray([f"{k}={int(v)}" for k, v in flags.items()]), P=np.asarray(P))
 
 
+SPLIT_CASES = [
+    # name, dataset, Fin, num_input (READER.NUM_INPUT_FEATURES, hgsfusion_vod.yaml:107 / hgsfusion_tj4d.yaml:103), virtual, encoding, frame order
+    ("split_vod",          "vod",  17, 29, True,  "split",  "grouped"),
+    ("split_tj4d",         "tj4d", 18, 31, True,  "split",  "grouped"),
+    ("split_vod_unsorted", "vod",  17, 29, True,  "split",  "shuffled"),
+    ("split_vod_mixed",    "vod",  17, 17, True,  "mixed",  "grouped"),
+    ("split_vod_direct",   "vod",  17, 15, True,  "direct", "grouped"),
+    ("split_plain7",       "vod",   7,  7, False, "split",  "grouped"),
+]
+
+
+def make_hybrid_points(dataset, Fin, B, n, seed, order):
+    """Hybrid radar rows as vod_dataset.py:498-530 lays them out: xyz, features, two flag columns
+    (1,1 raw radar point; 0,0 radar point inside a mask; 0,1 virtual point), frame index in column 0."""
+    rng = np.random.default_rng(seed)
+    cfg = synthetic.CONFIGS[dataset]
+    lo, hi = np.asarray(cfg["pc_range"][:3]), np.asarray(cfg["pc_range"][3:])
+    rows = []
+    for b in range(B):
+        nb = n + 37 * b
+        p = rng.standard_normal((nb, 1 + Fin)).astype(np.float32)
+        p[:, 0] = b
+        p[:, 1:4] = (lo + (hi - lo) * rng.random((nb, 3)) * 1.04 - 0.02 * (hi - lo)).astype(np.float32)
+        if Fin >= 5:
+            kind = rng.integers(0, 3, nb)
+            p[:, -2] = (kind == 0)
+            p[:, -1] = (kind != 1)
+        rows.append(p)
+    pts = np.concatenate(rows)
+    if order == "shuffled":
+        pts = pts[rng.permutation(pts.shape[0])]
+    return pts
+
+
+def run_split(name, dataset, Fin, num_input, virtual, encoding, order):
+    """Runs the reference's DynamicPillarFeatureNet.forward (dynamic_pillar_encoder.py:55-121) unmodified; the PillarMaxPooling
+    it calls at :120 (needs spconv) is replaced by a recorder, so what is pinned is exactly the reader's input."""
+    seen = {}
+
+    class Recorder(torch.nn.Module):
+        def __init__(self, **kw):
+            super().__init__()
+
+        def forward(self, xyz, xyz_batch_cnt, pt_feature):
+            seen.update(xyz=xyz.numpy().copy(), cnt=xyz_batch_cnt.numpy().copy(), feat=pt_feature.numpy().copy())
+            return None
+
+    for modname in ("pcdet", "pcdet.ops", "pcdet.ops.pillar_ops"):
+        sys.modules.setdefault(modname, types.ModuleType(modname))
+    stub = types.ModuleType("pcdet.ops.pillar_ops.pillar_modules")
+    stub.PillarMaxPooling = Recorder
+    sys.modules["pcdet.ops.pillar_ops.pillar_modules"] = stub
+    spec = importlib.util.spec_from_file_location(
+        "ref_dynamic_pillar_encoder", f"{REF}/pcdet/models/backbones_3d/vfe/pillarnet_modules/dynamic_pillar_encoder.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    cfg = synthetic.CONFIGS[dataset]
+    reader = mod.DynamicPillarFeatureNet(num_input_features=num_input, num_filters=[32], pillar_size=0.16,
+                                         pc_range=list(cfg["pc_range"]), virtual=virtual, encoding_type=encoding, dataset=dataset)
+    pts = make_hybrid_points(dataset, Fin, 3, 300, seed=len(name), order=order)
+    t = torch.from_numpy(pts)
+    # PillarNet.forward's split (vfe/pillarnet.py:51-58; the file itself needs spconv to import)
+    batch_size = t[:, 0].max().item()
+    frames = [t[t[:, 0] == i][:, 1:] for i in range(int(batch_size) + 1)]
+    reader(dict(points=frames))
+    return dict(points=pts, xyz=seen["xyz"], xyz_batch_cnt=seen["cnt"], pt_features=seen["feat"],
+                pc_range=np.asarray(cfg["pc_range"], dtype=np.float64),
+                meta=np.asarray([dataset, str(Fin), str(num_input), str(int(virtual)), encoding, order]))
+
+
 def main():
     check = "--check" in sys.argv
+    for case in SPLIT_CASES:
+        data = run_split(*case)
+        path = os.path.join(HERE, f"{case[0]}.npz")
+        np.savez_compressed(path, **data)
+        print(f"{case[0]:18s} L={data['xyz'].shape[0]:6d} Fout={data['pt_features'].shape[1]} -> {os.path.basename(path)} ({os.path.getsize(path) / 1e3:.0f} kB)")
+    if "--only-split" in sys.argv:
+        return
     PillarVFE, PointPillarScatter, Radar7PillarVFE = load_reference()
     for name, flags, P in RADAR7_CASES:
         data = run_radar7(Radar7PillarVFE, name, flags, P)

@@ -161,3 +161,64 @@ def test_against_the_reference_kernels(cuda):
     same = (src2.grad == gs_ref).float().mean().item()
     assert same > 0.999
     assert torch.equal((src2.grad != 0).sum(), (gs_ref != 0).sum())
+
+
+# ---- split_encode (a13): PillarNet.forward's frame split + DynamicPillarFeatureNet.forward's encoding -----------------
+import glob
+
+SPLIT_FIXTURES = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "split_*.npz")))
+
+
+@pytest.mark.parametrize("path", SPLIT_FIXTURES, ids=lambda p: os.path.basename(p)[:-4])
+@pytest.mark.parametrize("give_batch_size", [False, True])
+def test_split_encode_matches_reference_fixture(cuda, path, give_batch_size):
+    d = np.load(path)
+    dataset, Fin, num_input, virtual, encoding, order = d["meta"]
+    B = len(d["xyz_batch_cnt"]) if give_batch_size else None
+    xyz, cnt, feat = po.split_encode(torch.from_numpy(d["points"]).to(cuda), d["pc_range"], int(num_input), bool(int(virtual)),
+                                     str(encoding), str(dataset), B)
+    assert cnt.dtype == torch.int32 and np.array_equal(cnt.cpu().numpy(), d["xyz_batch_cnt"])
+    assert np.array_equal(xyz.cpu().numpy().view(np.uint32), d["xyz"].view(np.uint32))
+    assert np.array_equal(feat.cpu().numpy().view(np.uint32), d["pt_features"].view(np.uint32))
+
+
+@pytest.mark.parametrize("dataset,Fin,Fout", [("vod", 17, 29), ("tj4d", 18, 31)])
+def test_split_encode_large_and_dropped_rows(cuda, dataset, Fin, Fout):
+    rng = np.random.default_rng(Fin)
+    B, L = 16, 480_000 + 13
+    pts = rng.standard_normal((L, 1 + Fin)).astype(np.float32)
+    pts[:, 0] = np.sort(rng.integers(0, B, L))
+    pts[:, -2] = rng.integers(0, 2, L)
+    pts[:, -1] = rng.integers(0, 2, L)
+    pts[-5:, 0] = [B, -1, 0.5, np.nan, 99]                        # match no `points[:,0] == i`: dropped (tail -> no reorder needed)
+    rng_range = [0, -25.6, -3, 51.2, 25.6, 2]
+    ref = pb.split_encode(pts[:-5], rng_range, "split", dataset, Fout)
+    xyz, cnt, feat = po.split_encode(torch.from_numpy(pts).to(cuda), rng_range, Fout, True, "split", dataset, B)
+    assert np.array_equal(cnt.cpu().numpy(), ref[1])
+    assert np.array_equal(xyz.cpu().numpy().view(np.uint32), ref[0].view(np.uint32))
+    assert np.array_equal(feat.cpu().numpy().view(np.uint32), ref[2].view(np.uint32))
+    # a dropped row in the middle and frames out of order take the ordered second pass
+    pts2 = pts[rng.permutation(L)]
+    ref2 = pb.split_encode(pts2[np.isfinite(pts2[:, 0])], rng_range, "split", dataset, Fout)   # (the oracle's max() must not see the NaN)
+    xyz, cnt, feat = po.split_encode(torch.from_numpy(pts2).to(cuda), rng_range, Fout, True, "split", dataset, B)
+    keep = ref2[1][:B]
+    assert np.array_equal(cnt.cpu().numpy(), keep)
+    n = int(keep.sum())
+    assert xyz.shape[0] == n and np.array_equal(feat.cpu().numpy().view(np.uint32), ref2[2][:n].view(np.uint32))
+
+
+def test_dynamic_pillar_feature_net_reader(cuda):
+    """The module mirror end to end: collated points in, the reader's (features, pillars, shape, B) out; both input forms agree."""
+    d = np.load(os.path.join(ROOT, "tests", "golden", "split_vod.npz"))
+    torch.manual_seed(0)
+    net = po.DynamicPillarFeatureNet(num_input_features=29, num_filters=[32], pillar_size=0.16, virtual=True,
+                                     pc_range=[0, -25.6, -3, 51.2, 25.6, 2], encoding_type="split", dataset="vod").to(cuda).eval()
+    assert "pfn_layers.shared_mlps.0.weight" in net.state_dict() and net.state_dict()["pfn_layers.shared_mlps.0.weight"].shape == (32, 35)
+    pts = torch.from_numpy(d["points"]).to(cuda)
+    with torch.no_grad():
+        a = net(dict(points=pts, batch_size=3))
+        frames = [pts[pts[:, 0] == i][:, 1:] for i in range(3)]
+        b = net(dict(points=frames))
+    fa, pa = (a.features, a.indices) if hasattr(a, "features") else (a[0], a[1])
+    fb, pb_ = (b.features, b.indices) if hasattr(b, "features") else (b[0], b[1])
+    assert torch.equal(fa, fb) and torch.equal(pa, pb_) and fa.shape[1] == 32 and pa.shape[1] == 3

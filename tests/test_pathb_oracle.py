@@ -67,3 +67,40 @@ def test_gather_and_grad():
     gi = pb.gather_feature_grad(idx, go, 30)
     for n in range(30):
         assert np.allclose(gi[n], go[idx == n].sum(axis=0), atol=1e-5)
+
+
+# ---- split_encode: pinned against the reference's DynamicPillarFeatureNet.forward (tests/golden/make_golden.py) ----
+import glob
+import os
+
+import pytest
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+SPLIT_FIXTURES = sorted(glob.glob(os.path.join(GOLDEN, "split_*.npz")))
+
+
+def test_split_fixtures_present():
+    assert len(SPLIT_FIXTURES) == 6
+
+
+@pytest.mark.parametrize("path", SPLIT_FIXTURES, ids=lambda p: os.path.basename(p)[:-4])
+def test_split_encode_matches_reference_fixture(path):
+    d = np.load(path)
+    dataset, Fin, num_input, virtual, encoding, order = d["meta"]
+    xyz, cnt, feat = pb.split_encode(d["points"], d["pc_range"], encoding, dataset, int(num_input), bool(int(virtual)))
+    assert np.array_equal(cnt, d["xyz_batch_cnt"]) and cnt.dtype == np.int32
+    assert np.array_equal(xyz.view(np.uint32), d["xyz"].view(np.uint32))
+    assert np.array_equal(feat.view(np.uint32), d["pt_features"].view(np.uint32))
+
+
+def test_split_encode_hand_case():
+    # Fin = 17: xyz, 12 features, flags.  (1,1) raw radar point -> real block; (0,1) virtual -> virtual block; (0,0) -> virtual block
+    row = lambda b, f0, f1: [b, 10, -5, 1] + list(range(100, 112)) + [f0, f1]
+    pts = np.array([row(0, 1, 1), row(0, 0, 1), row(1, 0, 0), row(0.5, 1, 1)], dtype=np.float32)
+    xyz, cnt, feat = pb.split_encode(pts, [0, -25.6, -3, 51.2, 25.6, 2], "split", "vod", 29)
+    assert cnt.tolist() == [2, 1]                                  # the row with frame index 0.5 matches no mask
+    assert np.allclose(xyz[0], [10, 20.6, 4])
+    assert feat.shape == (3, 29)
+    assert feat[0, 3:15].tolist() == list(range(100, 112)) and not feat[0, 15:27].any() and feat[0, 27:].tolist() == [1, 1]
+    assert feat[1, 15:27].tolist() == list(range(100, 112)) and not feat[1, 3:15].any() and feat[1, 27:].tolist() == [0, 1]
+    assert feat[2, 15:27].tolist() == list(range(100, 112)) and feat[2, 27:].tolist() == [0, 0]
