@@ -86,6 +86,34 @@ __device__ __forceinline__ void st_volatile_u64(uint64_t *p, uint64_t v) {
     asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
+// ---- packed fp32 pairs (sm_100 FFMA2 / FMUL2 / FADD2): two independent IEEE round-to-nearest operations per
+// instruction, bit-identical to the scalar forms.  ptxas 12.9 contracts mul.rn.f32x2 -> add.rn.f32x2 into FFMA2 even
+// under -fmad=false (scalar .rn ops are left alone), so a rounded multiply must never feed a PACKED add: the callers
+// finish such chains with scalar __fadd_rn.
+__device__ __forceinline__ uint64_t pack_f2(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack_f2(uint64_t v, float &lo, float &hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma2_rn(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ uint64_t sub2_rn(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t mul2_rn(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+
 // 128-byte TMA swizzle: 16-byte chunk index (address bits 4..6) XOR row index (bits 7..9).
 // `row` = 128-byte row of a 1024-byte aligned tile, `col` = float column 0..31.
 __device__ __forceinline__ int swz128(int row, int col) {

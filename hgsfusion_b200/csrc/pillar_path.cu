@@ -459,13 +459,14 @@ __global__ void __launch_bounds__(PFN_THREADS, 4) k_pfn(const PathParams p) {
 
     // this lane's 4 channels: Linear rows and BatchNorm constants, in registers for the whole kernel
     const int c0 = 4 * (lane & 15);
-    float4 w4[CIN];
+    uint64_t w01[CIN], w23[CIN];           // channel pairs (c0, c0+1), (c0+2, c0+3): one FFMA2 each per input feature
     float4 mu = make_float4(0.f, 0.f, 0.f, 0.f), iv = mu, ga = mu, be = mu, pv = mu;
     if (PFN) {
 #pragma unroll
-        for (int k = 0; k < CIN; ++k)
-            w4[k] = make_float4(__ldg(p.W + (c0 + 0) * CIN + k), __ldg(p.W + (c0 + 1) * CIN + k),
-                                __ldg(p.W + (c0 + 2) * CIN + k), __ldg(p.W + (c0 + 3) * CIN + k));
+        for (int k = 0; k < CIN; ++k) {
+            w01[k] = pack_f2(__ldg(p.W + (c0 + 0) * CIN + k), __ldg(p.W + (c0 + 1) * CIN + k));
+            w23[k] = pack_f2(__ldg(p.W + (c0 + 2) * CIN + k), __ldg(p.W + (c0 + 3) * CIN + k));
+        }
         float bnv[5][4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -489,6 +490,8 @@ __global__ void __launch_bounds__(PFN_THREADS, 4) k_pfn(const PathParams p) {
         ga = make_float4(bnv[2][0], bnv[2][1], bnv[2][2], bnv[2][3]); be = make_float4(bnv[3][0], bnv[3][1], bnv[3][2], bnv[3][3]);
         pv = make_float4(bnv[4][0], bnv[4][1], bnv[4][2], bnv[4][3]);
     }
+    const uint64_t mu01 = pack_f2(mu.x, mu.y), mu23 = pack_f2(mu.z, mu.w), iv01 = pack_f2(iv.x, iv.y), iv23 = pack_f2(iv.z, iv.w),
+                   ga01 = pack_f2(ga.x, ga.y), ga23 = pack_f2(ga.z, ga.w);
 
     const int P4 = (p.P >> 2) << 2;
     const int maxv = p.max_voxels, Pmax = p.P;
@@ -521,20 +524,21 @@ __global__ void __launch_bounds__(PFN_THREADS, 4) k_pfn(const PathParams p) {
             // torch.norm(xyz, 2, 2) on the CPU: sqrt(fma(z,z, fma(y,y, x*x)))  (pillar_vfe.py:110-112)
             if (DIST) feat[kf++] = __fsqrt_rn(fmaf(row[2], row[2], fmaf(row[1], row[1], __fmul_rn(row[0], row[0]))));
         }
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        uint64_t a01 = 0ull, a23 = 0ull;       // (+0, +0)
 #pragma unroll
-        for (int kk = 0; kk < CIN; ++kk) {     // Linear: sequential FMA in k order (pillar_vfe.py:37)
-            a0 = fmaf(feat[kk], w4[kk].x, a0); a1 = fmaf(feat[kk], w4[kk].y, a1);
-            a2 = fmaf(feat[kk], w4[kk].z, a2); a3 = fmaf(feat[kk], w4[kk].w, a3);
+        for (int kk = 0; kk < CIN; ++kk) {     // Linear: sequential FMA in k order (pillar_vfe.py:37), two channels per FFMA2
+            const uint64_t ff = pack_f2(feat[kk], feat[kk]);
+            a01 = fma2_rn(ff, w01[kk], a01);
+            a23 = fma2_rn(ff, w23[kk], a23);
         }
         float y0, y1, y2, y3;
-        if (BN) {                              // BN eval: (((x-mean)*invstd)*gamma)+beta, 4 roundings (:39)
-            y0 = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(a0, mu.x), iv.x), ga.x), be.x);
-            y1 = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(a1, mu.y), iv.y), ga.y), be.y);
-            y2 = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(a2, mu.z), iv.z), ga.z), be.z);
-            y3 = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(a3, mu.w), iv.w), ga.w), be.w);
+        if (BN) {                              // BN eval: (((x-mean)*invstd)*gamma)+beta, 4 roundings (:39); the last add scalar (common.cuh)
+            unpack_f2(mul2_rn(mul2_rn(sub2_rn(a01, mu01), iv01), ga01), y0, y1);
+            unpack_f2(mul2_rn(mul2_rn(sub2_rn(a23, mu23), iv23), ga23), y2, y3);
+            y0 = __fadd_rn(y0, be.x); y1 = __fadd_rn(y1, be.y); y2 = __fadd_rn(y2, be.z); y3 = __fadd_rn(y3, be.w);
         } else {
-            y0 = __fadd_rn(a0, be.x); y1 = __fadd_rn(a1, be.y); y2 = __fadd_rn(a2, be.z); y3 = __fadd_rn(a3, be.w);
+            unpack_f2(a01, y0, y1); unpack_f2(a23, y2, y3);
+            y0 = __fadd_rn(y0, be.x); y1 = __fadd_rn(y1, be.y); y2 = __fadd_rn(y2, be.z); y3 = __fadd_rn(y3, be.w);
         }
         v0 = max(v0, __float_as_int(y0)); v1 = max(v1, __float_as_int(y1));
         v2 = max(v2, __float_as_int(y2)); v3 = max(v3, __float_as_int(y3));
@@ -802,13 +806,14 @@ k_emit(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtenso
     // this lane's 4 channels: Linear rows and BatchNorm constants, in registers for the whole kernel
     const int c0 = 4 * (lane & 15);
     const int half = lane >> 4;
-    float4 w4[CIN];
+    uint64_t w01[CIN], w23[CIN];           // channel pairs (c0, c0+1), (c0+2, c0+3): one FFMA2 each per input feature
     float4 mu = make_float4(0.f, 0.f, 0.f, 0.f), iv = mu, ga = mu, be = mu, pv = mu;
     {
 #pragma unroll
-        for (int k = 0; k < CIN; ++k)
-            w4[k] = make_float4(__ldg(p.W + (c0 + 0) * CIN + k), __ldg(p.W + (c0 + 1) * CIN + k),
-                                __ldg(p.W + (c0 + 2) * CIN + k), __ldg(p.W + (c0 + 3) * CIN + k));
+        for (int k = 0; k < CIN; ++k) {
+            w01[k] = pack_f2(__ldg(p.W + (c0 + 0) * CIN + k), __ldg(p.W + (c0 + 1) * CIN + k));
+            w23[k] = pack_f2(__ldg(p.W + (c0 + 2) * CIN + k), __ldg(p.W + (c0 + 3) * CIN + k));
+        }
         float bnv[5][4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -832,6 +837,8 @@ k_emit(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtenso
         ga = make_float4(bnv[2][0], bnv[2][1], bnv[2][2], bnv[2][3]); be = make_float4(bnv[3][0], bnv[3][1], bnv[3][2], bnv[3][3]);
         pv = make_float4(bnv[4][0], bnv[4][1], bnv[4][2], bnv[4][3]);
     }
+    const uint64_t mu01 = pack_f2(mu.x, mu.y), mu23 = pack_f2(mu.z, mu.w), iv01 = pack_f2(iv.x, iv.y), iv23 = pack_f2(iv.z, iv.w),
+                   ga01 = pack_f2(ga.x, ga.y), ga23 = pack_f2(ga.z, ga.w);
 
     const int tiles_per_row = (p.nx + 31) >> 5;
     const int rows_per_frame = p.ny;                       // nz == 1 (PointPillarScatter asserts it)
@@ -858,20 +865,21 @@ k_emit(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtenso
             // torch.norm(xyz, 2, 2) on the CPU: sqrt(fma(z,z, fma(y,y, x*x)))  (pillar_vfe.py:110-112)
             if (DIST) feat[kf++] = __fsqrt_rn(fmaf(row[2], row[2], fmaf(row[1], row[1], __fmul_rn(row[0], row[0]))));
         }
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        uint64_t a01 = 0ull, a23 = 0ull;       // (+0, +0)
 #pragma unroll
-        for (int kk = 0; kk < CIN; ++kk) {     // Linear: sequential FMA in k order (pillar_vfe.py:37)
-            a0 = fmaf(feat[kk], w4[kk].x, a0); a1 = fmaf(feat[kk], w4[kk].y, a1);
-            a2 = fmaf(feat[kk], w4[kk].z, a2); a3 = fmaf(feat[kk], w4[kk].w, a3);
+        for (int kk = 0; kk < CIN; ++kk) {     // Linear: sequential FMA in k order (pillar_vfe.py:37), two channels per FFMA2
+            const uint64_t ff = pack_f2(feat[kk], feat[kk]);
+            a01 = fma2_rn(ff, w01[kk], a01);
+            a23 = fma2_rn(ff, w23[kk], a23);
         }
         float y0, y1, y2, y3;
-        if (BN) {                              // BN eval: (((x-mean)*invstd)*gamma)+beta, 4 roundings (:39)
-            y0 = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(a0, mu.x), iv.x), ga.x), be.x);
-            y1 = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(a1, mu.y), iv.y), ga.y), be.y);
-            y2 = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(a2, mu.z), iv.z), ga.z), be.z);
-            y3 = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(a3, mu.w), iv.w), ga.w), be.w);
+        if (BN) {                              // BN eval: (((x-mean)*invstd)*gamma)+beta, 4 roundings (:39); the last add scalar (common.cuh)
+            unpack_f2(mul2_rn(mul2_rn(sub2_rn(a01, mu01), iv01), ga01), y0, y1);
+            unpack_f2(mul2_rn(mul2_rn(sub2_rn(a23, mu23), iv23), ga23), y2, y3);
+            y0 = __fadd_rn(y0, be.x); y1 = __fadd_rn(y1, be.y); y2 = __fadd_rn(y2, be.z); y3 = __fadd_rn(y3, be.w);
         } else {
-            y0 = __fadd_rn(a0, be.x); y1 = __fadd_rn(a1, be.y); y2 = __fadd_rn(a2, be.z); y3 = __fadd_rn(a3, be.w);
+            unpack_f2(a01, y0, y1); unpack_f2(a23, y2, y3);
+            y0 = __fadd_rn(y0, be.x); y1 = __fadd_rn(y1, be.y); y2 = __fadd_rn(y2, be.z); y3 = __fadd_rn(y3, be.w);
         }
         v0 = max(v0, __float_as_int(y0)); v1 = max(v1, __float_as_int(y1));
         v2 = max(v2, __float_as_int(y2)); v3 = max(v3, __float_as_int(y3));
