@@ -3,6 +3,7 @@
 #include "contract_ops.cuh"
 #include "pillar_path.cuh"
 #include "pillarnet_ops.cuh"
+#include "train_ops.cuh"
 
 #include <climits>
 
@@ -262,6 +263,73 @@ int hgsf_split_encode(const float *points, int64_t n_rows, int32_t Fin, int32_t 
     q.xyz = xyz; q.feat = pt_features; q.cnt = xyz_batch_cnt; q.info = info;
     const int st = launch_split_encode(q, static_cast<cudaStream_t>(stream));
     if (st == HGSF_OK) g_last_launches = n_rows > 0;
+    return st;
+}
+
+// ---- training (train_ops.cu) ------------------------------------------------------------------------------------------
+int64_t hgsf_train_stats_doubles(int32_t C, int32_t cin) { return (C > 0 && cin > 0) ? (int64_t)train_stats_len(C, cin) : 0; }
+int64_t hgsf_train_scratch_doubles(int32_t C, int32_t cin) { return (C > 0 && cin > 0) ? (int64_t)train_acc_len(C, cin) : 0; }
+
+static int vfe_params(const hgsf_geometry *g, const hgsf_pfn *pfn, const float *voxels, const void *coords, const void *num,
+                      int32_t coords_are_float, int32_t num_are_float, int64_t M, int32_t P, int32_t F, VfeParams &q,
+                      bool &abs_xyz, bool &dist) {
+    if (!geom_ok(g) || !pfn || M < 0 || P <= 0 || F < 3 || !pfn->weight) return HGSF_ERR_INVALID_ARG;
+    if (M > 0 && (!voxels || !coords || !num)) return HGSF_ERR_INVALID_ARG;
+    abs_xyz = pfn->use_absolute_xyz != 0; dist = pfn->with_distance != 0;
+    if ((abs_xyz ? F : F - 3) + 6 + (dist ? 1 : 0) != pfn->in_channels) return HGSF_ERR_INVALID_ARG;
+    q = VfeParams{};
+    q.voxels = voxels; q.coords = coords; q.num = num; q.coords_float = coords_are_float; q.num_float = num_are_float;
+    q.M = M; q.P = P; q.F = F; q.C = pfn->out_channels;
+    for (int j = 0; j < 3; ++j) { q.vsize[j] = g->voxel_size[j]; q.voff[j] = g->centre_off[j]; }
+    q.pfn = PfnArgs{pfn->weight, pfn->bias, pfn->bn_weight, pfn->bn_bias, pfn->bn_mean, pfn->bn_var, pfn->bn_eps};
+    return HGSF_OK;
+}
+
+int hgsf_pillar_vfe_batch_stats(const hgsf_geometry *g, const hgsf_pfn *pfn, const float *voxels, const void *coords,
+                                const void *num, int32_t coords_are_float, int32_t num_are_float, int64_t M, int32_t P,
+                                int32_t F, float momentum, float *running_mean, float *running_var, float *batch_mean,
+                                float *batch_var, double *stats, hgsf_stream_t stream) {
+    g_last_launches = 0;
+    VfeParams q;
+    bool abs_xyz, dist;
+    int st = vfe_params(g, pfn, voxels, coords, num, coords_are_float, num_are_float, M, P, F, q, abs_xyz, dist);
+    if (st != HGSF_OK) return st;
+    if (!batch_mean || !batch_var || !stats || M == 0) return HGSF_ERR_INVALID_ARG;   // BatchNorm needs at least one row
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    st = launch_vfe_stats(q, abs_xyz, dist, stats, s);
+    if (st != HGSF_OK) return st;
+    st = launch_bn_finalize(stats, (double)M * P, q.C, momentum, running_mean, running_var, batch_mean, batch_var, s);
+    if (st == HGSF_OK) g_last_launches = 2;
+    return st;
+}
+
+int hgsf_pillar_vfe_backward(const hgsf_geometry *g, const hgsf_pfn *pfn, const float *voxels, const void *coords,
+                             const void *num, int32_t coords_are_float, int32_t num_are_float, int64_t M, int32_t P,
+                             int32_t F, const float *grad_out, const double *stats, double *scratch, float *grad_weight,
+                             float *grad_bn_weight, float *grad_bn_bias, hgsf_stream_t stream) {
+    g_last_launches = 0;
+    VfeParams q;
+    bool abs_xyz, dist;
+    int st = vfe_params(g, pfn, voxels, coords, num, coords_are_float, num_are_float, M, P, F, q, abs_xyz, dist);
+    if (st != HGSF_OK) return st;
+    if (!scratch || !grad_weight || (M > 0 && !grad_out)) return HGSF_ERR_INVALID_ARG;
+    const bool bn = pfn->bn_weight != nullptr;
+    if (bn && !(pfn->bn_bias && pfn->bn_mean && pfn->bn_var && grad_bn_weight && grad_bn_bias)) return HGSF_ERR_INVALID_ARG;
+    if (!bn && (!pfn->bias || stats)) return HGSF_ERR_INVALID_ARG;
+    const int mode = !bn ? 2 : (stats ? 0 : 1);
+    return launch_vfe_backward(q, abs_xyz, dist, grad_out, stats, mode, scratch, grad_weight, grad_bn_weight, grad_bn_bias,
+                               static_cast<cudaStream_t>(stream), &g_last_launches);
+}
+
+int hgsf_pointpillar_scatter_backward(const hgsf_geometry *g, const float *grad_canvas, const void *coords,
+                                      int32_t coords_are_float, int64_t M, int32_t C, int32_t B, float *grad_feats,
+                                      hgsf_stream_t stream) {
+    g_last_launches = 0;
+    if (!geom_ok(g) || M < 0 || B <= 0 || C <= 0 || g->grid[2] != 1) return HGSF_ERR_INVALID_ARG;
+    if (M > 0 && (!grad_canvas || !coords || !grad_feats)) return HGSF_ERR_INVALID_ARG;
+    const int st = launch_scatter_grad(grad_canvas, coords, coords_are_float, M, C, B, g->grid[1], g->grid[0], grad_feats,
+                                       static_cast<cudaStream_t>(stream));
+    if (st == HGSF_OK) g_last_launches = M > 0;
     return st;
 }
 

@@ -11,7 +11,10 @@ They keep the reference's plugin API (constructor keywords, `forward(batch_dict)
                        (pcdet/datasets/processor/data_processor.py:107-115) so that no CPU voxelizer runs
   PillarScatterPassthrough   MAP_TO_BEV plugin for FusedPillarVFE: spatial_features already exists
 
-Inference (eval mode) only in this round: the backward pass is SURVEY.md §8(f) rank 1.
+Training works through the same modules: in train mode the PFN's BatchNorm1d runs on batch statistics (zero-padded
+rows included, running statistics updated) and `linear.weight` / `norm.weight` / `norm.bias` receive gradients from
+native backward kernels (csrc/train_ops.cu) -- what torch autograd computes over PFNLayer.forward
+(pillar_vfe.py:29-49) and PointPillarScatter.forward (pointpillar_scatter.py:33-35) in the reference.
 There is no PyTorch fallback: without the CUDA library these modules raise at construction.
 """
 from __future__ import annotations
@@ -22,6 +25,74 @@ import torch.nn as nn
 
 from . import _lib
 from .ops import PfnWeights, PillarPath
+
+
+class _PillarVFEFunction(torch.autograd.Function):
+    """PFNLayer.forward (pillar_vfe.py:29-49) on the contract tensors, differentiable w.r.t. the layer's parameters.
+    The inputs (voxels, coords, counts) are data: the reference's voxels tensor does not require grad either."""
+
+    @staticmethod
+    def forward(ctx, path, voxels, coords, num, weight, gamma, beta, bias, running_mean, running_var, eps, momentum,
+                batch_stats, use_absolute_xyz, with_distance):
+        kw = dict(eps=eps, use_absolute_xyz=use_absolute_xyz, with_distance=with_distance)
+        w = weight.detach().contiguous()
+        stats = None
+        if gamma is not None:
+            mean, var = running_mean, running_var
+            if batch_stats:
+                probe = PfnWeights(weight=w, bn_weight=gamma.detach(), bn_bias=beta.detach(), running_mean=running_mean,
+                                   running_var=running_var, **kw)
+                mean, var, stats = path.pillar_vfe_batch_stats(voxels, coords, num, probe, momentum, running_mean, running_var)
+            pfn = PfnWeights(weight=w, bn_weight=gamma.detach(), bn_bias=beta.detach(), running_mean=mean, running_var=var, **kw)
+        else:
+            pfn = PfnWeights(weight=w, bias=bias.detach(), **kw)
+        out = path.pillar_vfe(voxels, coords, num, pfn)
+        ctx.path, ctx.pfn, ctx.stats = path, pfn, stats
+        ctx.save_for_backward(voxels, coords, num)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        voxels, coords, num = ctx.saved_tensors
+        dW, dg, db = ctx.path.pillar_vfe_backward(voxels, coords, num, ctx.pfn, grad_out.contiguous(), ctx.stats)
+        bn = ctx.pfn.bn_weight is not None
+        return (None, None, None, None, dW, dg if bn else None, db if bn else None, None if bn else db,
+                None, None, None, None, None, None, None)
+
+
+class _ScatterFunction(torch.autograd.Function):
+    """PointPillarScatter.forward (pointpillar_scatter.py:14-41); backward = gather at the pillar cells."""
+
+    @staticmethod
+    def forward(ctx, path, pillar_features, coords, batch_size):
+        ctx.path, ctx.batch_size = path, batch_size
+        ctx.save_for_backward(coords)
+        return path.pointpillar_scatter(pillar_features, coords, batch_size)
+
+    @staticmethod
+    def backward(ctx, grad_canvas):
+        (coords,) = ctx.saved_tensors
+        return None, ctx.path.pointpillar_scatter_backward(grad_canvas.contiguous(), coords, ctx.batch_size), None, None
+
+
+def _pfn_forward(path, layer, voxels, coords, num, use_absolute_xyz, with_distance, training, weight=None):
+    """Eval without gradients: the plain native forward.  Otherwise the autograd function (batch statistics in train mode)."""
+    weight = layer.linear.weight if weight is None else weight
+    params = [weight] + ([layer.norm.weight, layer.norm.bias] if layer.use_norm else [layer.linear.bias])
+    needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+    batch_stats = bool(training and layer.use_norm)
+    if not needs_grad and not batch_stats:
+        pfn = layer.weights(use_absolute_xyz, with_distance)
+        pfn.weight = weight.detach()
+        return path.pillar_vfe(voxels, coords, num, pfn)
+    if batch_stats and layer.norm.num_batches_tracked is not None:
+        layer.norm.num_batches_tracked += 1
+    if layer.use_norm:
+        n = layer.norm
+        return _PillarVFEFunction.apply(path, voxels, coords, num, weight, n.weight, n.bias, None, n.running_mean, n.running_var,
+                                        n.eps, n.momentum, batch_stats, use_absolute_xyz, with_distance)
+    return _PillarVFEFunction.apply(path, voxels, coords, num, weight, None, None, layer.linear.bias, None, None, 1e-3, 0.0,
+                                    False, use_absolute_xyz, with_distance)
 
 
 class _PFNLayerParams(nn.Module):
@@ -81,10 +152,6 @@ class _VFEBase(nn.Module):
     def get_output_feature_dim(self):
         return self.num_filters[-1]
 
-    def _check_mode(self):
-        if self.training and torch.is_grad_enabled():
-            raise NotImplementedError("hgsfusion_b200 modules are forward-only this round: call .eval() / no_grad()")
-
     def _pfn(self) -> PfnWeights:
         return self.pfn_layers[0].weights(self.use_absolute_xyz, self.with_distance)
 
@@ -98,9 +165,9 @@ class PillarVFE(_VFEBase):
                                num_point_features=self.num_raw_features, grid_size=grid_size)
 
     def forward(self, batch_dict, **kwargs):
-        self._check_mode()
         voxels, num, coords = batch_dict['voxels'], batch_dict['voxel_num_points'], batch_dict['voxel_coords']
-        features = self.path.pillar_vfe(voxels, coords, num, self._pfn())
+        features = _pfn_forward(self.path, self.pfn_layers[0], voxels, coords, num, self.use_absolute_xyz,
+                                self.with_distance, self.training)
         batch_dict['pillar_features'] = features.view(-1, 1, features.shape[-1]).squeeze()   # pillar_vfe.py:121
         return batch_dict
 
@@ -151,24 +218,20 @@ class Radar7PillarVFE(nn.Module):
     def get_output_feature_dim(self):
         return self.num_filters[-1]
 
-    def _expanded(self) -> PfnWeights:
-        layer = self.pfn_layers[0]
-        w = layer.linear.weight.detach()
-        full = torch.zeros((w.shape[0], 13), dtype=w.dtype, device=w.device)
+    def _expanded_weight(self) -> torch.Tensor:
+        """[C, len(sel)+6] -> [C, 13] with zero columns; built with differentiable torch ops so that the gradient of the
+        expanded weight flows back to the selected columns of the parameter."""
+        w = self.pfn_layers[0].linear.weight
         k = len(self.selected_indexes)
-        full[:, self.selected_indexes.to(w.device)] = w[:, :k]        # raw features, in place
-        full[:, 7:13] = w[:, k:k + 6]                                 # f_cluster, f_center
-        pf = layer.weights(True, False)
-        pf.weight = full
-        return pf
+        cols = torch.cat([self.selected_indexes.to(w.device), torch.arange(7, 13, device=w.device)])
+        return torch.zeros((w.shape[0], 13), dtype=w.dtype, device=w.device).index_copy(1, cols, w[:, :k + 6])
 
     def forward(self, batch_dict, **kwargs):
-        if self.training and torch.is_grad_enabled():
-            raise NotImplementedError("hgsfusion_b200 modules are forward-only this round: call .eval() / no_grad()")
         voxels, num, coords = batch_dict['voxels'], batch_dict['voxel_num_points'], batch_dict['voxel_coords']
         if not self.use_elevation:
             voxels[:, :, self.z_ind] = 0          # in place on the caller's tensor, like pillar_vfe.py:232-233
-        features = self.path.pillar_vfe(voxels, coords, num, self._expanded())
+        features = _pfn_forward(self.path, self.pfn_layers[0], voxels, coords, num, True, False, self.training,
+                                weight=self._expanded_weight())
         batch_dict['pillar_features'] = features.view(-1, 1, features.shape[-1]).squeeze()
         return batch_dict
 
@@ -197,7 +260,10 @@ class PointPillarScatter(nn.Module):
             batch_size = int(batch_dict['batch_size'])
         if pillar_features.dim() == 1:                 # the reference's squeeze() dropped M == 1
             pillar_features = pillar_features.view(1, -1)
-        batch_dict['spatial_features'] = self.path.pointpillar_scatter(pillar_features, coords, batch_size)
+        if torch.is_grad_enabled() and pillar_features.requires_grad:
+            batch_dict['spatial_features'] = _ScatterFunction.apply(self.path, pillar_features, coords, batch_size)
+        else:
+            batch_dict['spatial_features'] = self.path.pointpillar_scatter(pillar_features, coords, batch_size)
         return batch_dict
 
 
@@ -227,10 +293,30 @@ class FusedPillarVFE(_VFEBase):
                                            int(self._max_voxels[mode]), self.num_raw_features, grid_size=self._grid)
         return self._paths[mode]
 
+    def _forward_train(self, points, batch_size):
+        """Train mode / parameters that need gradients: pillarize natively, then the differentiable PFN and scatter
+        (the same native kernels PillarVFE and PointPillarScatter use); one host sync for the pillar count."""
+        path = self._path()
+        out = path.pillarize(points, batch_size, xyz_col=1, batch_col=0, want_voxels=True).trim()
+        out.pop('num_pillars')
+        feats = _pfn_forward(path, self.pfn_layers[0], out['voxels'], out['voxel_coords'], out['voxel_num_points'],
+                             self.use_absolute_xyz, self.with_distance, self.training)
+        out['pillar_features'] = feats
+        if torch.is_grad_enabled() and feats.requires_grad:
+            out['spatial_features'] = _ScatterFunction.apply(path, feats, out['voxel_coords'], batch_size)
+        else:
+            out['spatial_features'] = path.pointpillar_scatter(feats, out['voxel_coords'], batch_size)
+        if not self.return_voxels:
+            out.pop('voxels')
+        return out
+
     def forward(self, batch_dict, **kwargs):
-        self._check_mode()
         points = batch_dict['points']
         batch_size = int(batch_dict['batch_size'])
+        layer = self.pfn_layers[0]
+        if (self.training and layer.use_norm) or (torch.is_grad_enabled() and any(p.requires_grad for p in layer.parameters())):
+            batch_dict.update(self._forward_train(points, batch_size))
+            return batch_dict
         res = self._path().points_to_bev(points, batch_size, self._pfn(), xyz_col=1, batch_col=0,
                                          want_voxels=self.return_voxels)
         if self.trim:

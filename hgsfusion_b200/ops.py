@@ -208,6 +208,60 @@ class PillarPath:
         self.last_launches = int(self.lib.hgsf_last_launch_count())
         return out
 
+    # -- training (include/hgsfusion_b200.h "Training through the path") ---------------------------------------
+    def _contract_args(self, voxels, voxel_coords, voxel_num_points):
+        vox = _f32c(voxels, "voxels")
+        M, P, F = (int(v) for v in vox.shape)
+        co, cf = _coords(voxel_coords, "voxel_coords")
+        nu, nf = _coords(voxel_num_points, "voxel_num_points")
+        return vox, co, cf, nu, nf, M, P, F
+
+    def pillar_vfe_batch_stats(self, voxels, voxel_coords, voxel_num_points, pfn: PfnWeights, momentum: float,
+                               running_mean=None, running_var=None):
+        """BatchNorm1d train-mode statistics of PFNLayer.forward (pillar_vfe.py:38-40) over all M*P rows: returns
+        (batch_mean, batch_var (biased), stats) and updates running_mean / running_var in place like torch does."""
+        vox, co, cf, nu, nf, M, P, F = self._contract_args(voxels, voxel_coords, voxel_num_points)
+        pf = pfn.to_struct()
+        Cc, cin = int(pfn.weight.shape[0]), int(pfn.weight.shape[1])
+        stats = torch.empty(int(self.lib.hgsf_train_stats_doubles(Cc, cin)), dtype=torch.float64, device=vox.device)
+        mean = torch.empty(Cc, dtype=torch.float32, device=vox.device)
+        var = torch.empty(Cc, dtype=torch.float32, device=vox.device)
+        st = self.lib.hgsf_pillar_vfe_batch_stats(C.byref(self.geom), C.byref(pf), _ptr(vox), _ptr(co), _ptr(nu), cf, nf, M, P, F,
+                                                  float(momentum), _ptr(running_mean), _ptr(running_var), _ptr(mean), _ptr(var),
+                                                  _ptr(stats), _stream())
+        _lib.check(st, "hgsf_pillar_vfe_batch_stats")
+        self.last_launches = int(self.lib.hgsf_last_launch_count())
+        return mean, var, stats
+
+    def pillar_vfe_backward(self, voxels, voxel_coords, voxel_num_points, pfn: PfnWeights, grad_out, stats=None):
+        """grad of pillar_features [M,C] -> (grad_weight [C,Cin], grad_gamma [C] or None, grad_beta_or_bias [C]).
+        `pfn` must carry the statistics the forward normalised with; `stats` = what pillar_vfe_batch_stats returned
+        (train mode) or None (running statistics, constants)."""
+        vox, co, cf, nu, nf, M, P, F = self._contract_args(voxels, voxel_coords, voxel_num_points)
+        pf = pfn.to_struct()
+        Cc, cin = int(pfn.weight.shape[0]), int(pfn.weight.shape[1])
+        g = _f32c(grad_out, "grad_pillar_features").view(M, Cc)
+        scratch = torch.empty(int(self.lib.hgsf_train_scratch_doubles(Cc, cin)), dtype=torch.float64, device=vox.device)
+        dW = torch.empty((Cc, cin), dtype=torch.float32, device=vox.device)
+        dg = torch.empty(Cc, dtype=torch.float32, device=vox.device) if pfn.bn_weight is not None else None
+        db = torch.empty(Cc, dtype=torch.float32, device=vox.device)
+        st = self.lib.hgsf_pillar_vfe_backward(C.byref(self.geom), C.byref(pf), _ptr(vox), _ptr(co), _ptr(nu), cf, nf, M, P, F,
+                                               _ptr(g), _ptr(stats), _ptr(scratch), _ptr(dW), _ptr(dg), _ptr(db), _stream())
+        _lib.check(st, "hgsf_pillar_vfe_backward")
+        self.last_launches = int(self.lib.hgsf_last_launch_count())
+        return dW, dg, db
+
+    def pointpillar_scatter_backward(self, grad_spatial_features, voxel_coords, batch_size: int) -> torch.Tensor:
+        gc = _f32c(grad_spatial_features, "grad_spatial_features")
+        co, cf = _coords(voxel_coords, "voxel_coords")
+        M, Cc = int(co.shape[0]), int(gc.shape[1])
+        out = torch.empty((M, Cc), dtype=torch.float32, device=gc.device)
+        st = self.lib.hgsf_pointpillar_scatter_backward(C.byref(self.geom), _ptr(gc), _ptr(co), cf, M, Cc, int(batch_size),
+                                                        _ptr(out), _stream())
+        _lib.check(st, "hgsf_pointpillar_scatter_backward")
+        self.last_launches = int(self.lib.hgsf_last_launch_count())
+        return out
+
     def pointpillar_scatter(self, pillar_features, voxel_coords, batch_size: int) -> torch.Tensor:
         """pillar_features [M,C] + voxel_coords [M,4] -> spatial_features [B, C, ny, nx]."""
         pf = _f32c(pillar_features, "pillar_features")

@@ -223,6 +223,50 @@ HGSF_API int hgsf_split_encode(const float *points, int64_t n_rows, int32_t Fin,
                                float *xyz, float *pt_features, int32_t *xyz_batch_cnt, int32_t *info,
                                hgsf_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Training through the path.  The reference trains PillarVFE with torch autograd over
+ * PFNLayer.forward (pillar_vfe.py:29-49): BatchNorm1d in train mode normalises with the statistics of ALL M*P rows of a
+ * channel (zero-padded rows included) and updates the running statistics (momentum 0.01, unbiased variance); backward
+ * goes through max -> ReLU -> batch-norm -> Linear.  Three calls on the contract layout (voxels, voxel_coords,
+ * voxel_num_points as in hgsf_pillar_vfe):
+ *
+ *   forward, train mode:  hgsf_pillar_vfe_batch_stats -> batch_mean / batch_var (and the running-stat update), then
+ *                         hgsf_pillar_vfe with pfn.bn_mean = batch_mean, pfn.bn_var = batch_var
+ *   backward:             hgsf_pillar_vfe_backward with the same pfn the forward used
+ *
+ * `stats` is device scratch of hgsf_train_stats_doubles(C, Cin) doubles, written by batch_stats and read by backward
+ * (keep it between the two); `scratch` of backward is hgsf_train_scratch_doubles(C, Cin) doubles. */
+HGSF_API int64_t hgsf_train_stats_doubles(int32_t out_channels, int32_t in_channels);
+HGSF_API int64_t hgsf_train_scratch_doubles(int32_t out_channels, int32_t in_channels);
+
+/* running_mean / running_var (device [C], may be NULL) are updated in place as torch.nn.BatchNorm1d does;
+ * batch_mean / batch_var (device [C]) receive the biased batch statistics the forward normalises with. */
+HGSF_API int hgsf_pillar_vfe_batch_stats(const hgsf_geometry *geom, const hgsf_pfn *pfn, const float *voxels,
+                                         const void *voxel_coords, const void *voxel_num_points,
+                                         int32_t coords_are_float, int32_t num_are_float, int64_t num_pillars,
+                                         int32_t max_points_per_voxel, int32_t num_features, float momentum,
+                                         float *running_mean, float *running_var, float *batch_mean, float *batch_var,
+                                         double *stats, hgsf_stream_t stream);
+
+/* grad_pillar_features [M,C] -> grad_weight [C,Cin], grad_bn_weight [C], grad_bn_bias [C] (USE_NORM False: grad_bn_bias
+ * receives the Linear bias gradient, grad_bn_weight is ignored).  `stats` = the buffer hgsf_pillar_vfe_batch_stats
+ * filled when the forward ran on batch statistics, NULL when it ran on the running statistics (eval-mode BN: the
+ * statistics are constants). */
+HGSF_API int hgsf_pillar_vfe_backward(const hgsf_geometry *geom, const hgsf_pfn *pfn, const float *voxels,
+                                      const void *voxel_coords, const void *voxel_num_points,
+                                      int32_t coords_are_float, int32_t num_are_float, int64_t num_pillars,
+                                      int32_t max_points_per_voxel, int32_t num_features,
+                                      const float *grad_pillar_features, const double *stats, double *scratch,
+                                      float *grad_weight, float *grad_bn_weight, float *grad_bn_bias,
+                                      hgsf_stream_t stream);
+
+/* PointPillarScatter backward (autograd of pointpillar_scatter.py:33-35): grad_pillar_features[m, :] =
+ * grad_spatial_features[b, :, y, x]; rows whose coordinates fall outside the canvas get zeros. */
+HGSF_API int hgsf_pointpillar_scatter_backward(const hgsf_geometry *geom, const float *grad_spatial_features,
+                                               const void *voxel_coords, int32_t coords_are_float, int64_t num_pillars,
+                                               int32_t C, int32_t batch_size, float *grad_pillar_features,
+                                               hgsf_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

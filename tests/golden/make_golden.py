@@ -5,6 +5,7 @@ the GPU box); the .npz fixtures it writes are committed.
 
     python tests/golden/make_golden.py            # rewrite fixtures
     python tests/golden/make_golden.py --check    # also compare the C oracle against them
+    python tests/golden/make_golden.py --only-split | --only-train   # just the Path B input-prep / the training fixtures
 
 The voxelizer that feeds these fixtures is oracle.voxelize (spconv is not available, see
 oracle/pillar_oracle.c header); the fixtures pin PillarVFE + PointPillarScatter, whose inputs
@@ -226,8 +227,79 @@ def run_split(name, dataset, Fin, num_input, virtual, encoding, order):
                 meta=np.asarray([dataset, str(Fin), str(num_input), str(int(virtual)), encoding, order]))
 
 
+TRAIN_CASES = [
+    # name, config, n points, P, use_abs, with_dist
+    ("train_vod_p10",  "vod",  600, 10, True,  False),
+    ("train_vod_p32",  "vod",  500, 32, True,  False),
+    ("train_tj4d_p5",  "tj4d", 600,  5, True,  False),
+    ("train_vod_rel",  "vod",  400, 10, False, False),
+    ("train_vod_dist", "vod",  400, 10, True,  True),
+]
+
+
+def run_train(PillarVFE, PointPillarScatter, name, config, n, P, use_abs, with_dist):
+    """The reference's PillarVFE in TRAIN mode under torch autograd (CPU): forward on batch statistics, running-stat update,
+    gradients of sum(pillar_features * R) and of a random cotangent on the canvas."""
+    cfg = synthetic.CONFIGS[config]
+    F = cfg["F"]
+    geom = oracle.Geometry(cfg["pc_range"], cfg["voxel_size"])
+    pts, offs = synthetic.make_batch(config, 2, n, "clustered", seed0=41, oob_fraction=0.02)
+    vox, coords, num = [], [], []
+    for b in range(2):
+        v, c, k = oracle.voxelize(pts[offs[b]:offs[b + 1]], geom, P, 40000, F=F, xcol=1)
+        vox.append(v); num.append(k)
+        coords.append(np.concatenate([np.full((c.shape[0], 1), b, np.int32), c], axis=1))
+    vox, coords, num = np.concatenate(vox), np.concatenate(coords), np.concatenate(num)
+    Cin = (F if use_abs else F - 3) + 6 + (1 if with_dist else 0)
+    w = synthetic.make_pfn(Cin, 64, seed=len(name))
+    model_cfg = SimpleNamespace(USE_NORM=True, WITH_DISTANCE=with_dist, USE_ABSLOTE_XYZ=use_abs, NUM_FILTERS=[64])
+    vfe = PillarVFE(model_cfg=model_cfg, num_point_features=F, voxel_size=list(cfg["voxel_size"]),
+                    point_cloud_range=np.array(cfg["pc_range"], dtype=np.float32))
+    sd = vfe.state_dict()
+    sd["pfn_layers.0.linear.weight"] = torch.from_numpy(w.weight)
+    sd["pfn_layers.0.norm.weight"] = torch.from_numpy(w.gamma)
+    sd["pfn_layers.0.norm.bias"] = torch.from_numpy(w.beta)
+    sd["pfn_layers.0.norm.running_mean"] = torch.from_numpy(w.running_mean)
+    sd["pfn_layers.0.norm.running_var"] = torch.from_numpy(w.running_var)
+    vfe.load_state_dict(sd)
+    vfe.train()
+    bd = dict(voxels=torch.from_numpy(vox).float(), voxel_coords=torch.from_numpy(coords).float(),
+              voxel_num_points=torch.from_numpy(num).float())
+    bd = vfe(bd)
+    pf = bd["pillar_features"]
+    g = grid = geom.grid
+    sc = PointPillarScatter(model_cfg=SimpleNamespace(NUM_BEV_FEATURES=64), grid_size=np.array([g[0], g[1], g[2]]))
+    bd = sc(bd)
+    canvas = bd["spatial_features"]
+    rng = np.random.default_rng(len(name))
+    R = rng.standard_normal(pf.shape).astype(np.float32)
+    # a sparse cotangent on the canvas: values at the occupied cells of every 3rd pillar, one channel band
+    Rc = np.zeros(canvas.shape, dtype=np.float32)
+    sel = np.arange(0, coords.shape[0], 3)
+    Rc[coords[sel, 0], 8:24, coords[sel, 2], coords[sel, 3]] = rng.standard_normal((sel.size, 16)).astype(np.float32)
+    loss = (pf * torch.from_numpy(R)).sum() + (canvas * torch.from_numpy(Rc)).sum()
+    loss.backward()
+    lin, bn = vfe.pfn_layers[0].linear, vfe.pfn_layers[0].norm
+    return dict(voxels=vox, voxel_coords=coords, voxel_num_points=num, weight=w.weight, gamma=w.gamma, beta=w.beta,
+                running_mean=w.running_mean, running_var=w.running_var,
+                pillar_features=pf.detach().numpy(), grad_out=R, grad_canvas_idx=sel.astype(np.int32),
+                grad_canvas_vals=Rc[coords[sel, 0], 8:24, coords[sel, 2], coords[sel, 3]],
+                grad_weight=lin.weight.grad.numpy(), grad_gamma=bn.weight.grad.numpy(), grad_beta=bn.bias.grad.numpy(),
+                running_mean_after=bn.running_mean.numpy().copy(), running_var_after=bn.running_var.numpy().copy(),
+                meta=np.asarray([config, str(P), str(int(use_abs)), str(int(with_dist)), torch.__version__]))
+
+
 def main():
     check = "--check" in sys.argv
+    if "--only-split" not in sys.argv:
+        PillarVFE, PointPillarScatter, _ = load_reference()
+        for case in TRAIN_CASES:
+            data = run_train(PillarVFE, PointPillarScatter, *case)
+            path = os.path.join(HERE, f"{case[0]}.npz")
+            np.savez_compressed(path, **data)
+            print(f"{case[0]:20s} M={data['voxels'].shape[0]:6d} -> {os.path.basename(path)} ({os.path.getsize(path) / 1e3:.0f} kB)")
+        if "--only-train" in sys.argv:
+            return
     for case in SPLIT_CASES:
         data = run_split(*case)
         path = os.path.join(HERE, f"{case[0]}.npz")
