@@ -62,7 +62,8 @@ def test_module_guards():
                                num_point_features=7, voxel_size=[0.16, 0.16, 5],
                                point_cloud_range=np.array([0, -25.6, -3, 51.2, 25.6, 2], dtype=np.float32))
     m.train()
-    with pytest.raises(NotImplementedError):
+    assert m._path().max_voxels == 16000                         # MAX_NUMBER_OF_VOXELS['train'] (data_processor.py:146)
+    with pytest.raises(ValueError, match="CUDA tensor"):         # train mode goes native too: CPU tensors are refused
         m({'points': torch.zeros(1, 8), 'batch_size': 1})
     m.eval()
     assert m._path().max_voxels == 40000
