@@ -17,7 +17,7 @@ EXPORTS = ["hgsf_abi_version", "hgsf_status_string", "hgsf_pillar_capacity", "hg
            "hgsf_pillarize", "hgsf_points_to_bev", "hgsf_pillar_vfe", "hgsf_scatter_workspace_size",
            "hgsf_pointpillar_scatter", "hgsf_last_launch_count", "hgsf_emit_timing_begin", "hgsf_emit_timing_collect",
            "hgsf_pillarnet_workspace_size", "hgsf_pillarnet_indices", "hgsf_gather_feature", "hgsf_gather_feature_grad",
-           "hgsf_scatter_max", "hgsf_scatter_max_grad", "hgsf_split_encode",
+           "hgsf_scatter_max", "hgsf_scatter_max_grad", "hgsf_split_encode", "hgsf_pillarnet_reader",
            "hgsf_train_stats_doubles", "hgsf_train_scratch_doubles", "hgsf_pillar_vfe_batch_stats",
            "hgsf_pillar_vfe_backward", "hgsf_pointpillar_scatter_backward"]
 
@@ -89,6 +89,8 @@ def load():
     lib.hgsf_scatter_max_grad.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p]
     lib.hgsf_split_encode.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                       C.POINTER(C.c_float), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.hgsf_pillarnet_reader.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
+                                          C.c_float, C.c_float, C.POINTER(Pfn), C.c_void_p, C.c_void_p]
     lib.hgsf_train_stats_doubles.restype = C.c_int64
     lib.hgsf_train_stats_doubles.argtypes = [C.c_int32, C.c_int32]
     lib.hgsf_train_scratch_doubles.restype = C.c_int64

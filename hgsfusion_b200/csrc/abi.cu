@@ -266,6 +266,24 @@ int hgsf_split_encode(const float *points, int64_t n_rows, int32_t Fin, int32_t 
     return st;
 }
 
+int hgsf_pillarnet_reader(const float *xyz, const float *pt_features, int32_t Cf, const int32_t *point_idx,
+                          const int32_t *pillar_idx, int64_t L, const int32_t *pillars, int64_t M, float bev_size, float z_center,
+                          const hgsf_pfn *pfn, float *pillar_features, hgsf_stream_t stream) {
+    g_last_launches = 0;
+    if (L < 0 || M < 0 || Cf <= 0 || !pfn || !pfn->weight || !(bev_size > 0.f)) return HGSF_ERR_INVALID_ARG;
+    if (!(pfn->bn_weight && pfn->bn_bias && pfn->bn_mean && pfn->bn_var)) return HGSF_ERR_INVALID_ARG;
+    if (pfn->in_channels != Cf + 6) return HGSF_ERR_INVALID_ARG;
+    if (M > 0 && !pillar_features) return HGSF_ERR_INVALID_ARG;
+    if (L > 0 && (!xyz || !pt_features || !point_idx || !pillar_idx || !pillars || M == 0)) return HGSF_ERR_INVALID_ARG;
+    if (pfn->out_channels != 32 || Cf + 6 > 40) return HGSF_ERR_UNSUPPORTED;
+    ReaderParams q{};
+    q.xyz = xyz; q.feat = pt_features; q.Cf = Cf; q.point_idx = point_idx; q.pillar_idx = pillar_idx; q.L = L; q.M = M;
+    q.pillars = pillars; q.bev_size = bev_size; q.z_center = z_center;
+    q.W = pfn->weight; q.bn_w = pfn->bn_weight; q.bn_b = pfn->bn_bias; q.bn_m = pfn->bn_mean; q.bn_v = pfn->bn_var;
+    q.eps = pfn->bn_eps; q.out = pillar_features;
+    return launch_reader_fused(q, static_cast<cudaStream_t>(stream), &g_last_launches);
+}
+
 // ---- training (train_ops.cu) ------------------------------------------------------------------------------------------
 int64_t hgsf_train_stats_doubles(int32_t C, int32_t cin) { return (C > 0 && cin > 0) ? (int64_t)train_stats_len(C, cin) : 0; }
 int64_t hgsf_train_scratch_doubles(int32_t C, int32_t cin) { return (C > 0 && cin > 0) ? (int64_t)train_acc_len(C, cin) : 0; }

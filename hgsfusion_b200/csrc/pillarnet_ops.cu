@@ -405,4 +405,97 @@ int launch_split_encode(const SplitEncodeParams &q, cudaStream_t s) {
     return (int)cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------------
+// The reader's forward in ONE kernel (eval mode): PillarQueryAndGroup's gather + centre offsets (pillar_utils.py:31-54),
+// the shared MLP Linear(no bias) + BatchNorm1d(eval) + ReLU (pillar_modules.py:19-26,76) and scatter_max
+// (scatter_ops_gpu.cu:13-25) -- the reference materialises group_features [L, Cf+6], the MLP output [L, 32] and its
+// transpose on the way.  A warp takes 32 consecutive grouped points; lane = output channel (C = 32) with its Linear
+// row in registers; the staged point rows are read as shared-memory broadcasts; consecutive points of the same
+// pillar are max-combined in registers and leave as one 128-byte integer atomicMax (values are post-ReLU >= 0, the
+// output starts at 0: float order = integer order of the bits).
+constexpr int RD_WARPS = 8;
+constexpr int RD_MAXCIN = 40;
+
+template <int CIN4>   // Cin padded to a multiple of 4, in float4s
+__global__ void __launch_bounds__(RD_WARPS * 32) k_reader_fused(const ReaderParams q) {
+    constexpr int CINP = CIN4 * 4;
+    __shared__ __align__(16) float s_rows[RD_WARPS][32][CINP];
+    __shared__ int s_pid[RD_WARPS][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float(*rows)[CINP] = s_rows[warp];
+    int *pid = s_pid[warp];
+    const int Cf = q.Cf, Cin = Cf + 6;
+    float w[CINP];
+#pragma unroll
+    for (int k = 0; k < CINP; ++k) w[k] = (k < Cin) ? __ldg(q.W + (size_t)lane * Cin + k) : 0.f;
+    const float mu = __ldg(q.bn_m + lane), iv = __frcp_rn(__fsqrt_rn(__fadd_rn(__ldg(q.bn_v + lane), q.eps)));
+    const float ga = __ldg(q.bn_w + lane), be = __ldg(q.bn_b + lane);
+    const long long nchunks = (q.L + 31) >> 5;
+    const long long nw = (long long)gridDim.x * RD_WARPS;
+    for (long long ch = (long long)blockIdx.x * RD_WARPS + warp; ch < nchunks; ch += nw) {
+        const long long l0 = ch << 5;
+        const int np = (int)min((long long)32, q.L - l0);
+        // ---- stage: lane l owns grouped point l0 + l ----
+        int my_pt = 0, my_pid = -1;
+        if (lane < np) { my_pt = __ldg(q.point_idx + l0 + lane); my_pid = __ldg(q.pillar_idx + l0 + lane); }
+        pid[lane] = my_pid;
+        for (int r = 0; r < np; ++r) {                       // feature rows: one coalesced read per point
+            const int pt = __shfl_sync(FULL, my_pt, r);
+            const float *src = q.feat + (size_t)pt * Cf;
+            for (int k = lane; k < Cf; k += 32) rows[r][k] = __ldg(src + k);
+        }
+        if (lane < np) {
+            const float x = __ldg(q.xyz + (size_t)my_pt * 3), y = __ldg(q.xyz + (size_t)my_pt * 3 + 1), z = __ldg(q.xyz + (size_t)my_pt * 3 + 2);
+            const int py = __ldg(q.pillars + (size_t)my_pid * 3 + 1), px = __ldg(q.pillars + (size_t)my_pid * 3 + 2);
+            // centres (pillar_utils.py:117-121): (idx + 0.5) * pillar_size in fp32; z centre is the range's absolute mid height
+            const float cx = __fmul_rn(__fadd_rn((float)px, 0.5f), q.bev_size), cy = __fmul_rn(__fadd_rn((float)py, 0.5f), q.bev_size);
+            float *g = rows[lane];
+            g[Cf] = x; g[Cf + 1] = y; g[Cf + 2] = z;
+            g[Cf + 3] = __fsub_rn(x, cx); g[Cf + 4] = __fsub_rn(y, cy); g[Cf + 5] = __fsub_rn(z, q.z_center);
+            for (int k = Cin; k < CINP; ++k) g[k] = 0.f;
+        }
+        __syncwarp();
+        // ---- lane = channel: Linear + BN + ReLU, max over runs of equal pillar ----
+        int run_pid = pid[0];
+        float run_max = 0.f;
+        for (int r = 0; r < np; ++r) {
+            const int p_r = pid[r];
+            if (p_r != run_pid) {
+                if (run_max > 0.f) atomicMax(reinterpret_cast<int *>(q.out + (size_t)run_pid * 32 + lane), __float_as_int(run_max));
+                run_pid = p_r; run_max = 0.f;
+            }
+            const float4 *g4 = reinterpret_cast<const float4 *>(rows[r]);
+            float acc = 0.f;
+#pragma unroll
+            for (int v = 0; v < CIN4; ++v) {
+                const float4 g = g4[v];
+                acc = fmaf(g.x, w[4 * v], acc); acc = fmaf(g.y, w[4 * v + 1], acc);
+                acc = fmaf(g.z, w[4 * v + 2], acc); acc = fmaf(g.w, w[4 * v + 3], acc);
+            }
+            const float y = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(acc, mu), iv), ga), be);
+            run_max = fmaxf(run_max, y);
+        }
+        if (run_max > 0.f) atomicMax(reinterpret_cast<int *>(q.out + (size_t)run_pid * 32 + lane), __float_as_int(run_max));
+        __syncwarp();
+    }
+}
+
+int launch_reader_fused(const ReaderParams &q, cudaStream_t s, int *launches) {
+    if (launches) *launches = 0;
+    cudaError_t e = cudaMemsetAsync(q.out, 0, sizeof(float) * (size_t)q.M * 32, s);
+    if (e != cudaSuccess) return (int)e;
+    if (q.L == 0 || q.M == 0) return HGSF_OK;
+    const int cin4 = (q.Cf + 6 + 3) / 4;
+    const long long chunks = (q.L + 31) / 32;
+    const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>((chunks + RD_WARPS - 1) / RD_WARPS, 148 * 4));
+    switch (cin4) {
+#define HGSF_RD(N) case N: k_reader_fused<N><<<grid, RD_WARPS * 32, 0, s>>>(q); break;
+        HGSF_RD(2) HGSF_RD(3) HGSF_RD(4) HGSF_RD(5) HGSF_RD(6) HGSF_RD(7) HGSF_RD(8) HGSF_RD(9) HGSF_RD(10)
+#undef HGSF_RD
+        default: return HGSF_ERR_UNSUPPORTED;
+    }
+    if (launches) *launches = 1;
+    return (int)cudaGetLastError();
+}
+
 }  // namespace hgsf

@@ -33,6 +33,20 @@ struct SplitEncodeParams {
     int *info;               // [2] {flags, rows kept}
 };
 
+struct ReaderParams {
+    const float *xyz;        // [N, 3] relative coordinates
+    const float *feat;       // [N, Cf]
+    int Cf;
+    const int *point_idx, *pillar_idx;   // [L] grouped points and their pillars (hgsf_pillarnet_indices)
+    long long L, M;
+    const int *pillars;      // [M, 3] (b, y, x)
+    float bev_size, z_center;
+    const float *W, *bn_w, *bn_b, *bn_m, *bn_v;   // Linear [32, Cf+6] (no bias), BatchNorm1d eval
+    float eps;
+    float *out;              // [M, 32]
+};
+
+int launch_reader_fused(const ReaderParams &q, cudaStream_t stream, int *launches);
 int launch_split_encode(const SplitEncodeParams &q, cudaStream_t stream);
 int launch_pillarnet_indices(const PillarNetParams &q, cudaStream_t stream);
 int launch_gather(long long L, int C, const int *idx, const float *f, float *out, cudaStream_t s);

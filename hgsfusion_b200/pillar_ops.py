@@ -173,13 +173,44 @@ class PillarMaxPooling(nn.Module):
                                nn.BatchNorm1d(mlps[k + 1], eps=1e-3, momentum=0.01), nn.ReLU()])
         self.shared_mlps = nn.Sequential(*shared_mlp)       # the reference's own cuBLAS MLP (pillar_modules.py:19-26)
 
+    def _fused_ok(self, pt_feature) -> bool:
+        """Eval without gradients and the single 32-channel layer every shipped config uses (hgsfusion_vod.yaml:107-108):
+        the whole reader is one native launch after the index generation."""
+        if self.training or len(self.shared_mlps) != 3:
+            return False
+        lin = self.shared_mlps[0]
+        if lin.out_features != 32 or lin.in_features > 40 or lin.in_features != pt_feature.shape[1] + 6:
+            return False
+        return not (torch.is_grad_enabled() and any(p.requires_grad for p in self.shared_mlps.parameters()))
+
+    @torch.no_grad()
+    def _forward_fused(self, xyz, xyz_batch_cnt, pt_feature):
+        from .ops import PfnWeights
+        _need_cuda(pt_feature, "pt_feature", torch.float32)
+        g = self.groups
+        r = gen_indice_pairs_flat(xyz, xyz_batch_cnt, g.pillar_size, g.spatial_shape)
+        pillars, point_idx, pillar_idx = r["pillars"], r["point_set_indices"], r["pillar_set_indices"]
+        lin, bn = self.shared_mlps[0], self.shared_mlps[1]
+        pfn = PfnWeights(weight=lin.weight.detach(), bn_weight=bn.weight.detach(), bn_bias=bn.bias.detach(),
+                         running_mean=bn.running_mean, running_var=bn.running_var, eps=bn.eps)
+        pf = pfn.to_struct()
+        M, L = int(pillars.shape[0]), int(point_idx.shape[0])
+        out = torch.empty((M, 32), dtype=torch.float32, device=xyz.device)
+        st = _lib.load().hgsf_pillarnet_reader(_p(xyz), _p(pt_feature), int(pt_feature.shape[1]), _p(point_idx), _p(pillar_idx), L,
+                                               _p(pillars), M, float(g.pillar_size), float(g.z_center), C.byref(pf), _p(out), _s())
+        _lib.check(st, "hgsf_pillarnet_reader")
+        return pillars, out
+
     def forward(self, xyz, xyz_batch_cnt, pt_feature):
         B = xyz_batch_cnt.shape[0]
-        pillar_indices, pillar_set_indices, group_features = self.groups(xyz, xyz_batch_cnt, pt_feature)
-        group_features = self.shared_mlps(group_features)
-        group_features = group_features.transpose(1, 0).contiguous()
-        pillar_features = scatter_max(group_features, pillar_set_indices, pillar_indices.shape[0])
-        pillar_features = pillar_features.transpose(1, 0)
+        if self._fused_ok(pt_feature):
+            pillar_indices, pillar_features = self._forward_fused(xyz, xyz_batch_cnt, pt_feature)
+        else:
+            pillar_indices, pillar_set_indices, group_features = self.groups(xyz, xyz_batch_cnt, pt_feature)
+            group_features = self.shared_mlps(group_features)
+            group_features = group_features.transpose(1, 0).contiguous()
+            pillar_features = scatter_max(group_features, pillar_set_indices, pillar_indices.shape[0])
+            pillar_features = pillar_features.transpose(1, 0)
         try:
             try:
                 import spconv.pytorch as spconv

@@ -223,6 +223,17 @@ HGSF_API int hgsf_split_encode(const float *points, int64_t n_rows, int32_t Fin,
                                float *xyz, float *pt_features, int32_t *xyz_batch_cnt, int32_t *info,
                                hgsf_stream_t stream);
 
+/* The PillarNet reader's forward in ONE launch, eval mode: PillarQueryAndGroup's gathers and centre offsets
+ * (pcdet/ops/pillar_ops/pillar_utils.py:31-54), the shared MLP Linear(no bias) + BatchNorm1d + ReLU
+ * (pillar_modules.py:19-26,76) and scatter_max (scatter_ops_gpu.cu:13-25), without materialising group_features, the
+ * MLP output or its transpose.  point_idx / pillar_idx / pillars come from hgsf_pillarnet_indices; pfn->weight is
+ * shared_mlps.0.weight [32, Cf+6] (out_channels must be 32, in_channels Cf+6 <= 40), bn_* are shared_mlps.1.*;
+ * z_center = (zmax + zmin) / 2 of the range (pillar_utils.py:28); pillar_features [M, 32] is initialised here. */
+HGSF_API int hgsf_pillarnet_reader(const float *xyz, const float *pt_features, int32_t num_point_features,
+                                   const int32_t *point_idx, const int32_t *pillar_idx, int64_t L,
+                                   const int32_t *pillars, int64_t M, float bev_size, float z_center,
+                                   const hgsf_pfn *pfn, float *pillar_features, hgsf_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * Training through the path.  The reference trains PillarVFE with torch autograd over
  * PFNLayer.forward (pillar_vfe.py:29-49): BatchNorm1d in train mode normalises with the statistics of ALL M*P rows of a
