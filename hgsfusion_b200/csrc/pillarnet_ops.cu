@@ -420,10 +420,10 @@ template <int CIN4>   // Cin padded to a multiple of 4, in float4s
 __global__ void __launch_bounds__(RD_WARPS * 32) k_reader_fused(const ReaderParams q) {
     constexpr int CINP = CIN4 * 4;
     __shared__ __align__(16) float s_rows[RD_WARPS][32][CINP];
-    __shared__ int s_pid[RD_WARPS][32];
+    __shared__ int s_pid[RD_WARPS][32], s_pt[RD_WARPS][32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float(*rows)[CINP] = s_rows[warp];
-    int *pid = s_pid[warp];
+    int *pid = s_pid[warp], *spt = s_pt[warp];
     const int Cf = q.Cf, Cin = Cf + 6;
     float w[CINP];
 #pragma unroll
@@ -439,10 +439,14 @@ __global__ void __launch_bounds__(RD_WARPS * 32) k_reader_fused(const ReaderPara
         int my_pt = 0, my_pid = -1;
         if (lane < np) { my_pt = __ldg(q.point_idx + l0 + lane); my_pid = __ldg(q.pillar_idx + l0 + lane); }
         pid[lane] = my_pid;
-        for (int r = 0; r < np; ++r) {                       // feature rows: one coalesced read per point
-            const int pt = __shfl_sync(FULL, my_pt, r);
-            const float *src = q.feat + (size_t)pt * Cf;
-            for (int k = lane; k < Cf; k += 32) rows[r][k] = __ldg(src + k);
+        spt[lane] = my_pt;
+        __syncwarp();
+        // feature rows: the 32 x Cf elements as one flat index space, so that the loads are independent and batch up
+        const int total = np * Cf;
+#pragma unroll 4
+        for (int e = lane; e < total; e += 32) {
+            const int r = e / Cf, k = e - r * Cf;
+            rows[r][k] = __ldg(q.feat + (size_t)spt[r] * Cf + k);
         }
         if (lane < np) {
             const float x = __ldg(q.xyz + (size_t)my_pt * 3), y = __ldg(q.xyz + (size_t)my_pt * 3 + 1), z = __ldg(q.xyz + (size_t)my_pt * 3 + 2);
@@ -487,7 +491,7 @@ int launch_reader_fused(const ReaderParams &q, cudaStream_t s, int *launches) {
     if (q.L == 0 || q.M == 0) return HGSF_OK;
     const int cin4 = (q.Cf + 6 + 3) / 4;
     const long long chunks = (q.L + 31) / 32;
-    const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>((chunks + RD_WARPS - 1) / RD_WARPS, 148 * 4));
+    const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>((chunks + RD_WARPS - 1) / RD_WARPS, 148 * 3));
     switch (cin4) {
 #define HGSF_RD(N) case N: k_reader_fused<N><<<grid, RD_WARPS * 32, 0, s>>>(q); break;
         HGSF_RD(2) HGSF_RD(3) HGSF_RD(4) HGSF_RD(5) HGSF_RD(6) HGSF_RD(7) HGSF_RD(8) HGSF_RD(9) HGSF_RD(10)
