@@ -884,25 +884,24 @@ k_emit(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtenso
         v0 = max(v0, __float_as_int(y0)); v1 = max(v1, __float_as_int(y1));
         v2 = max(v2, __float_as_int(y2)); v3 = max(v3, __float_as_int(y3));
     };
-    // a point row: from the staging buffer (rel >= 0: row index in it) or from global memory (rel < 0: -1 - CSR row)
+    // a point row: from the staging buffer (rel >= 0: row index in it) or from global memory (rel < 0: -1 - CSR row),
+    // read through ONE generic pointer so that the two sources do not become two divergent code paths
     auto load_row = [&](const float *stg, int rel, int pos, float (&row)[RWc]) {
-        if (rel >= 0) {
-            const float4 *r4 = reinterpret_cast<const float4 *>(stg + (size_t)(rel + pos) * RWc);
+        const float *base = (rel >= 0) ? stg + (size_t)rel * RWc : grows + (size_t)(-1 - rel) * RWc;
+        const float4 *r4 = reinterpret_cast<const float4 *>(base + (size_t)pos * RWc);
 #pragma unroll
-            for (int v = 0; v < NV; ++v) { const float4 t4 = r4[v]; row[4 * v] = t4.x; row[4 * v + 1] = t4.y; row[4 * v + 2] = t4.z; row[4 * v + 3] = t4.w; }
-        } else {
-            const float4 *r4 = reinterpret_cast<const float4 *>(grows + (size_t)(-1 - rel + pos) * RWc);
-#pragma unroll
-            for (int v = 0; v < NV; ++v) { const float4 t4 = __ldg(r4 + v); row[4 * v] = t4.x; row[4 * v + 1] = t4.y; row[4 * v + 2] = t4.z; row[4 * v + 3] = t4.w; }
-        }
+        for (int v = 0; v < NV; ++v) { const float4 t4 = r4[v]; row[4 * v] = t4.x; row[4 * v + 1] = t4.y; row[4 * v + 2] = t4.z; row[4 * v + 3] = t4.w; }
     };
+    // channel c0+i of cell `cell` sits at tile[(c0+i)*32 + (((cell>>2) ^ ((c0+i)&7)) << 2 | (cell&3))] (128-byte swizzle);
+    // with c0 = 4*(lane&15): (c0+i)&7 = ((lane&1)<<2) ^ i, so the lane-constant part is folded once
+    float *const tbase = tile + c0 * 32;
+    const int swb = (lane & 1) << 2;
     auto put_tile = [&](int cell, int v0, int v1, int v2, int v3) {
-        const int xq = cell >> 2, xr = cell & 3;
-        float *t0 = tile + c0 * 32 + xr;
-        t0[0 * 32 + ((xq ^ ((c0 + 0) & 7)) << 2)] = __int_as_float(v0);
-        t0[1 * 32 + ((xq ^ ((c0 + 1) & 7)) << 2)] = __int_as_float(v1);
-        t0[2 * 32 + ((xq ^ ((c0 + 2) & 7)) << 2)] = __int_as_float(v2);
-        t0[3 * 32 + ((xq ^ ((c0 + 3) & 7)) << 2)] = __int_as_float(v3);
+        const int xs = (cell >> 2) ^ swb, xr = cell & 3;
+        tbase[0 * 32 + (((xs ^ 0) << 2) | xr)] = __int_as_float(v0);
+        tbase[1 * 32 + (((xs ^ 1) << 2) | xr)] = __int_as_float(v1);
+        tbase[2 * 32 + (((xs ^ 2) << 2) | xr)] = __int_as_float(v2);
+        tbase[3 * 32 + (((xs ^ 3) << 2) | xr)] = __int_as_float(v3);
     };
 
     // Tiles are handed out DYNAMICALLY in chunks of 4 consecutive tiles (one atomic per chunk, fetched a chunk ahead):
@@ -1089,29 +1088,47 @@ k_emit(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtenso
             // ---- unit phase.  lane l always computes channels c0..c0+3 ----
             const float cy = __fadd_rn(__fmul_rn((float)y, vsy), voy);   // pillar centre: fl(fl(c*v)+off), two roundings,
                                                                          // no FMA (pillar_vfe.py:101-103)
-            // (a) single-point pillars: half-warp h takes list entries 2*j + h
+            // (a) single-point pillars: half-warp h takes list entries 4*j + h and 4*j + 2 + h -- two independent points per
+            //     iteration, so that their FMA chains interleave (the kernel is latency-bound at 12 warps per SM)
+#ifdef HGSF_EXPERIMENT
+            const int n_s_run = (p.dbg & 1) ? 0 : n_s, n_m_run = (p.dbg & 1) ? 0 : n_m;
+#else
+            const int n_s_run = n_s, n_m_run = n_m;
+#endif
 #pragma unroll 1
-            for (int j = 0; 2 * j < n_s; ++j) {
-                const int e = 2 * j + half;
-                if (e < n_s) {
-                    const float4 r0 = rec[e][0], r1 = rec[e][1];
-                    const int meta = __float_as_int(r0.w);
-                    const int cell = (meta >> 8) & 0xFF;
-                    const float cx = __fadd_rn(__fmul_rn((float)(x0 + cell), vsx), vox);
-                    int v0 = 0, v1 = 0, v2 = 0, v3 = 0;
-                    if (1 < Pmax) { v0 = __float_as_int(pv.x); v1 = __float_as_int(pv.y); v2 = __float_as_int(pv.z); v3 = __float_as_int(pv.w); }
-                    float row[RWc];
-                    load_row(stg, __float_as_int(r1.x), meta >> 16, row);
-                    eval_row(row, r0.x, r0.y, r0.z, cx, cy, v0, v1, v2, v3);
-                    if (p.feats)
-                        st_f4_hint(p.feats + (size_t)__float_as_int(r1.y) * C + c0,
-                                   make_float4(__int_as_float(v0), __int_as_float(v1), __int_as_float(v2), __int_as_float(v3)), stream_policy);
-                    put_tile(cell, v0, v1, v2, v3);
+            for (int j = 0; 4 * j < n_s_run; ++j) {
+                const int eA = 4 * j + half;
+                if (eA < n_s) {
+                    const bool okB = eA + 2 < n_s;
+                    const int eB = okB ? eA + 2 : eA;
+                    const float4 rA0 = rec[eA][0], rA1 = rec[eA][1], rB0 = rec[eB][0], rB1 = rec[eB][1];
+                    const int metaA = __float_as_int(rA0.w), metaB = __float_as_int(rB0.w);
+                    const int cellA = (metaA >> 8) & 0xFF, cellB = (metaB >> 8) & 0xFF;
+                    const float cxA = __fadd_rn(__fmul_rn((float)(x0 + cellA), vsx), vox);
+                    const float cxB = __fadd_rn(__fmul_rn((float)(x0 + cellB), vsx), vox);
+                    int a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+                    if (1 < Pmax) { a0 = __float_as_int(pv.x); a1 = __float_as_int(pv.y); a2 = __float_as_int(pv.z); a3 = __float_as_int(pv.w); }
+                    int b0 = a0, b1 = a1, b2 = a2, b3 = a3;
+                    float rowA[RWc], rowB[RWc];
+                    load_row(stg, __float_as_int(rA1.x), metaA >> 16, rowA);
+                    load_row(stg, __float_as_int(rB1.x), metaB >> 16, rowB);
+                    eval_row(rowA, rA0.x, rA0.y, rA0.z, cxA, cy, a0, a1, a2, a3);
+                    eval_row(rowB, rB0.x, rB0.y, rB0.z, cxB, cy, b0, b1, b2, b3);
+                    if (p.feats) {
+                        st_f4_hint(p.feats + (size_t)__float_as_int(rA1.y) * C + c0,
+                                   make_float4(__int_as_float(a0), __int_as_float(a1), __int_as_float(a2), __int_as_float(a3)), stream_policy);
+                        if (okB)
+                            st_f4_hint(p.feats + (size_t)__float_as_int(rB1.y) * C + c0,
+                                       make_float4(__int_as_float(b0), __int_as_float(b1), __int_as_float(b2), __int_as_float(b3)), stream_policy);
+                    }
+                    put_tile(cellA, a0, a1, a2, a3);
+                    if (okB) put_tile(cellB, b0, b1, b2, b3);
                 }
             }
-            // (b) multi-point pillars: both half-warps on the same pillar, half h takes slots h, h+2, ...; max-combined
+            // (b) multi-point pillars: both half-warps on the same pillar, half h takes slots h, h+2, ... (two per iteration);
+            //     max-combined
 #pragma unroll 1
-            for (int j = 0; j < n_m; ++j) {
+            for (int j = 0; j < n_m_run; ++j) {
                 const float4 r0 = rec[31 - j][0], r1 = rec[31 - j][1];
                 const int meta = __float_as_int(r0.w);
                 const int nk = meta & 0xFF, cell = (meta >> 8) & 0xFF;
@@ -1119,12 +1136,17 @@ k_emit(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtenso
                 const float cx = __fadd_rn(__fmul_rn((float)(x0 + cell), vsx), vox);
                 int v0 = 0, v1 = 0, v2 = 0, v3 = 0;
                 if (nk < Pmax) { v0 = __float_as_int(pv.x); v1 = __float_as_int(pv.y); v2 = __float_as_int(pv.z); v3 = __float_as_int(pv.w); }
+                int u0 = v0, u1 = v1, u2 = v2, u3 = v3;
 #pragma unroll 1
-                for (int s2 = half; s2 < nk; s2 += 2) {
-                    float row[RWc];
-                    load_row(stg, relp, perm[cell][s2], row);
-                    eval_row(row, r0.x, r0.y, r0.z, cx, cy, v0, v1, v2, v3);
+                for (int s2 = half; s2 < nk; s2 += 4) {
+                    const int s3 = (s2 + 2 < nk) ? s2 + 2 : s2;        // the last odd one is evaluated twice: max is idempotent
+                    float rowA[RWc], rowB[RWc];
+                    load_row(stg, relp, perm[cell][s2], rowA);
+                    load_row(stg, relp, perm[cell][s3], rowB);
+                    eval_row(rowA, r0.x, r0.y, r0.z, cx, cy, v0, v1, v2, v3);
+                    eval_row(rowB, r0.x, r0.y, r0.z, cx, cy, u0, u1, u2, u3);
                 }
+                v0 = max(v0, u0); v1 = max(v1, u1); v2 = max(v2, u2); v3 = max(v3, u3);
                 v0 = max(v0, __shfl_xor_sync(FULL, v0, 16)); v1 = max(v1, __shfl_xor_sync(FULL, v1, 16));
                 v2 = max(v2, __shfl_xor_sync(FULL, v2, 16)); v3 = max(v3, __shfl_xor_sync(FULL, v3, 16));
                 if (half == 0) {
@@ -1201,7 +1223,11 @@ k_emit(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtenso
             if (TMA) {
                 fence_proxy_async_smem();
                 __syncwarp();
+#ifdef HGSF_EXPERIMENT
+                if (lane == 0 && !(p.dbg & 2)) { tma_store_3d_hint(&tmap, tile, x0, y, b * C, stream_policy); tma_commit(); }
+#else
                 if (lane == 0) { tma_store_3d_hint(&tmap, tile, x0, y, b * C, stream_policy); tma_commit(); }
+#endif
                 store_pending = true;
             } else if (STORE == 1) {
                 __syncwarp();
@@ -1387,8 +1413,12 @@ int emit_timing_collect(float *ms, int n) {
     return out;
 }
 
-int launch_pillar_path(const PathParams &p, bool with_pfn, bool abs_xyz, bool dist, size_t zero_bytes, void *zero_base,
+int launch_pillar_path(const PathParams &p_in, bool with_pfn, bool abs_xyz, bool dist, size_t zero_bytes, void *zero_base,
                        cudaStream_t stream, int *launches) {
+    PathParams p = p_in;
+#ifdef HGSF_EXPERIMENT
+    { static const int dbg = getenv("HGSF_DBG") ? atoi(getenv("HGSF_DBG")) : 0; p.dbg = dbg; }
+#endif
     int nl = 0;
     (void)zero_bytes; (void)zero_base;      // the cell table is zeroed by k_front itself
     {
