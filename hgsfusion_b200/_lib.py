@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libhgsfusion_b200.so")
+# HGSF_LIB: experiment builds of the same library (scripts/variants.sh); the product always loads the in-tree default
+LIB_PATH = os.environ.get("HGSF_LIB") or os.path.join(_HERE, "libhgsfusion_b200.so")
 
 OK, ERR_INVALID_ARG, ERR_UNSUPPORTED, ERR_WORKSPACE, ERR_DRIVER = 0, -1, -2, -3, -4
 
