@@ -196,3 +196,44 @@ def test_density_stress_shape(cuda):
     assert np.array_equal(got["voxel_coords"].cpu().numpy(), ref["voxel_coords"])
     assert np.array_equal(got["voxel_num_points"].cpu().numpy(), ref["voxel_num_points"])
     assert bits_equal(got["pillar_features"].cpu().numpy(), ref["pillar_features"])
+
+
+@pytest.mark.parametrize("seed", range(16))
+def test_random_configurations_bit_exact(cuda, seed):
+    """Seeded sweep over geometry, limits and input pathologies; every output bit-compared with the oracle."""
+    rng = np.random.default_rng(1000 + seed)
+    F = int(rng.choice([4, 5, 6, 7, 8]))
+    nx, ny = int(rng.integers(3, 200)), int(rng.integers(1, 120))
+    if seed % 3 == 0:
+        nx = int(rng.choice([32, 64, 96, 128]))                   # TMA store path (nx % 4 == 0) with whole tiles
+    vs = [float(rng.choice([0.1, 0.16, 0.25, 0.5])), float(rng.choice([0.1, 0.16, 0.4])), 4.0]
+    x0, y0 = float(rng.uniform(-20, 5)), float(rng.uniform(-30, 0))
+    pc_range = [x0, y0, -3.0, x0 + nx * vs[0], y0 + ny * vs[1], 1.0]
+    geom = oracle.Geometry(pc_range, vs)
+    if geom.grid[2] != 1:
+        pytest.skip("rounding of the synthetic range gave nz != 1")
+    B = int(rng.integers(1, 6))
+    P = int(rng.choice([1, 2, 3, 5, 10, 20, 32]))
+    mv = int(rng.choice([1, 7, 50, 400, 40000]))
+    counts = [int(rng.integers(0, 2500)) if rng.random() > 0.15 else 0 for _ in range(B)]
+    rows = []
+    for b, nb in enumerate(counts):
+        p = np.empty((nb, 1 + F), dtype=np.float32)
+        p[:, 0] = b
+        lo, hi = np.array(pc_range[:3]), np.array(pc_range[3:])
+        p[:, 1:4] = (lo + (hi - lo) * (rng.random((nb, 3)) * 1.1 - 0.05)).astype(np.float32)   # some outside
+        k = nb // 2                                                                         # half the points in a few cells
+        if k:
+            hot = lo[:2] + (hi - lo)[:2] * rng.random((3, 2))
+            p[:k, 1:3] = (hot[rng.integers(0, 3, k)] + rng.normal(0, 0.2, (k, 2))).astype(np.float32)
+        p[:, 4:] = rng.standard_normal((nb, F - 3)).astype(np.float32)
+        if nb > 10:
+            p[rng.integers(0, nb, 3), 1] = [np.nan, np.inf, -np.inf]        # rejected by the range test
+            p[rng.integers(0, nb)] = p[rng.integers(0, nb)]                 # an exact duplicate point
+            p[rng.integers(0, nb), 1:4] = [pc_range[0], pc_range[1], pc_range[2]]   # exactly on the lower corner: inside
+            p[rng.integers(0, nb), 1] = pc_range[3]                         # exactly on the upper bound: outside
+            p[:, 0] = b
+        rows.append(p[rng.permutation(nb)])
+    pts = np.concatenate(rows) if rows else np.zeros((0, 1 + F), np.float32)
+    offs = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
+    both(pts, offs, pc_range, vs, P, mv, F, cuda, seed=seed, want_voxels=bool(seed & 1), frame_offsets=bool(seed & 2))
