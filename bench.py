@@ -228,22 +228,25 @@ def main_ours(args):
     counts_host = [torch.empty(1 + B, dtype=torch.int32).pin_memory() for _ in range(2)]
     main_stream = torch.cuda.current_stream()
 
-    def e2e_loop(steps, with_canvas=False, canvas_host=None):
+    def e2e_loop(steps, with_canvas=False, canvas_host=None, srcs=None, stages=None, call=None):
+        srcs = pinned if srcs is None else srcs
+        stages = stage if stages is None else stages
+        call = (lambda pts_dev: path.points_to_bev(pts_dev, B, pfn, out=res)) if call is None else call
         for s in consumed:
             s.record(main_stream)
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(consumed[0])
-            stage[0].copy_(pinned[0], non_blocking=True)
+            stages[0].copy_(srcs[0], non_blocking=True)
             ready[0].record(copy_stream)
         for i in range(steps):
             cur, nxt = i & 1, (i + 1) & 1
             if i + 1 < steps:
                 with torch.cuda.stream(copy_stream):
                     copy_stream.wait_event(consumed[nxt])
-                    stage[nxt].copy_(pinned[(i + 1) % ring], non_blocking=True)
+                    stages[nxt].copy_(srcs[(i + 1) % ring], non_blocking=True)
                     ready[nxt].record(copy_stream)
             main_stream.wait_event(ready[cur])
-            path.points_to_bev(stage[cur], B, pfn, out=res)
+            call(stages[cur])
             consumed[cur].record(main_stream)
             counts_host[cur].copy_(res.num_pillars, non_blocking=True)
             if with_canvas:
@@ -260,6 +263,20 @@ def main_ours(args):
     assert int(counts_host[(e2e_steps - 1) & 1][0]) > 0
     h2d = int(pinned[0].numel() * 4)
     d2h = int((1 + B) * 4)
+    # the same call fed with the frames' own rows [sum N, F] plus frame offsets (hgsf_points.frame_offsets) instead of the
+    # collated [sum N, 1+F] layout: what a collate hook that does not add the batch column would ship over PCIe
+    pinned_nf = [torch.from_numpy(np.ascontiguousarray(h[:, 1:])).pin_memory() for h in host]
+    stage_nf = [torch.empty((pinned_nf[0].shape[0], F), dtype=torch.float32, device=dev) for _ in range(2)]
+    offs_dev = torch.arange(0, (B + 1) * n, n, dtype=torch.int32, device=dev)
+    call_nf = lambda pts_dev: path.points_to_bev(pts_dev, B, pfn, xyz_col=0, frame_offsets=offs_dev, out=res)
+    e2e_loop(3, srcs=pinned_nf, stages=stage_nf, call=call_nf)
+    barrier()
+    e0.record()
+    e2e_loop(e2e_steps, srcs=pinned_nf, stages=stage_nf, call=call_nf)
+    e1.record()
+    barrier()
+    ms_e2e_nf = sharding.reduce_max(e0.elapsed_time(e1), dev)
+    assert int(counts_host[(e2e_steps - 1) & 1][0]) > 0
     # the same with the whole canvas also copied to the host every step (PCIe bound; for the record only)
     canvas_steps = 5
     canvas_host = torch.empty(res.spatial_features.shape, dtype=torch.float32).pin_memory()
@@ -309,6 +326,9 @@ def main_ours(args):
                          steps=e2e_steps,
                          note="pinned host points -> H2D -> hgsf_points_to_bev -> D2H pillar counts; canvas stays on device as "
                               "spatial_features does in the reference",
+                         per_frame_rows_layout=dict(value=frames * e2e_steps / (ms_e2e_nf * 1e-3), unit=UNIT,
+                                                    h2d_bytes_per_step=int(pinned_nf[0].numel() * 4),
+                                                    note="points as [sum N, F] + frame_offsets (no batch column)"),
                          with_canvas_d2h=dict(value=frames * canvas_steps / (ms_e2e_canvas * 1e-3), unit=UNIT,
                                               d2h_bytes_per_step=int(res.spatial_features.numel() * 4) + d2h)),
                 gpu_launches=launches_per_step * args.steps, gpu_launches_per_step=launches_per_step,
