@@ -850,6 +850,11 @@ k_emit(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtenso
     const float *__restrict__ grows = p.sorted_rows;
     const unsigned lt = (1u << lane) - 1u;
     const uint64_t stream_policy = l2_policy_evict_first();   // canvas: written once, never re-read here
+#ifdef HGSF_EXPERIMENT
+    const uint64_t feats_policy = (p.dbg & 8) ? l2_policy_evict_last() : ((p.dbg & 16) ? l2_policy_evict_normal() : stream_policy);
+#else
+    const uint64_t feats_policy = stream_policy;
+#endif
 
     // one point through decorate + Linear + BN, folded into the running max (integer max on the float bits: exact for
     // the non-negative post-ReLU values, drops negatives and -0 = the ReLU, lets a NaN 0x7fffffff win as torch.max does)
@@ -904,9 +909,16 @@ k_emit(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtenso
         tbase[3 * 32 + (((xs ^ 3) << 2) | xr)] = __int_as_float(v3);
     };
 
-    // Tiles are handed out DYNAMICALLY in chunks of 4 consecutive tiles (one atomic per chunk, fetched a chunk ahead):
-    // a dense tile costs ten times a sparse one, and a static assignment leaves the unlucky warps running alone at the end.
-    constexpr int CHUNK = 4;
+    // Tiles are handed out DYNAMICALLY, one ticket per tile, fetched a tile ahead: a dense tile costs ten times a sparse
+    // one, and a static assignment leaves the unlucky warps running alone at the end.  One tile per ticket (rather than a
+    // run of consecutive tiles per warp) also keeps x-adjacent tiles -- adjacent 128-byte pieces of the same canvas rows --
+    // in flight at the same time on different warps, which the DRAM write stream rewards (measured: runs of 10 / 4 / 2 / 1
+    // tiles -> 0.195 / 0.178 / 0.169 / 0.167 ms per step).
+#ifdef HGSF_CHUNK
+    constexpr int CHUNK = HGSF_CHUNK;
+#else
+    constexpr int CHUNK = 1;
+#endif
     const int n_tiles = n_rows * tiles_per_row;
     // the ticket stays in lane 0's register until the chunk is actually started: broadcasting it right away would
     // stall the whole warp on the atomic's round trip
@@ -952,9 +964,7 @@ k_emit(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtenso
     // the tile's rows are sorted_rows[row0, row0 + total): one cooperative async copy of (at most STAGE_W of) them
     auto issue_stage = [&](const uint4 e, float *stg) {
         const int row0 = __shfl_sync(FULL, (int)e.z, 0);
-        int total = (int)e.y;
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) total += __shfl_xor_sync(FULL, total, d);
+        const int total = (int)__reduce_add_sync(FULL, e.y);      // one REDUX instead of a shuffle tree
         const int chunks = min(total, STAGE_W) * NV;
         const float *src = grows + (size_t)row0 * RWc;
         for (int c = lane; c < chunks; c += 32) cp_async16(stg + 4 * c, src + 4 * c);
@@ -1010,7 +1020,32 @@ k_emit(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtenso
             }
             cp_async_wait<1>();          // this tile's rows have landed (this lane's copies) ...
             __syncwarp();                // ... and every other lane's
-            // ---- order the pillar's points by input index ----
+            // ---- order the pillar's points by input index; mean of the kept points (torch CPU sum order) ----
+            const bool live = occ && cnt <= 32;
+            float mx = 0.f, my = 0.f, mz = 0.f;
+            // the common tile has only 1- and 2-point pillars: a warp-uniform short cut for it (one compare instead of the
+            // 6-way ranking, no summation loop, and x/2 as the exact x*0.5 instead of the IEEE division routine)
+            const unsigned multi_bal = __ballot_sync(FULL, occ && cnt > 1);
+            const unsigned pair_bal = __ballot_sync(FULL, occ && cnt == 2 && staged);
+            const bool pairs_only = (multi_bal == pair_bal) && Pmax >= 2;
+            if (pairs_only) {
+                if (occ && cnt == 2) {
+                    const float *r0p = stg + (size_t)rel * RWc, *r1p = r0p + RWc;
+                    const int first = (__float_as_uint(r1p[F]) < __float_as_uint(r0p[F])) ? 1 : 0;
+                    perm[lane][0] = (unsigned char)first; perm[lane][1] = (unsigned char)(first ^ 1);
+                    const float4 a = *reinterpret_cast<const float4 *>(first ? r1p : r0p);
+                    const float4 c = *reinterpret_cast<const float4 *>(first ? r0p : r1p);
+                    SlotSum sum;
+                    sum.add(0, P4, a.x, a.y, a.z);
+                    sum.add(1, P4, c.x, c.y, c.z);
+                    mx = __fmul_rn(sum.sx(), 0.5f); my = __fmul_rn(sum.sy(), 0.5f); mz = __fmul_rn(sum.sz(), 0.5f);
+                } else if (occ) {
+                    float row[RWc];
+                    load_row(stg, rel, 0, row);
+                    mx = row[0]; my = row[1]; mz = row[2];       // mean of one point is the point (x/1 is exact)
+                }
+                __syncwarp();
+            } else {
             if (occ && cnt > 1 && cnt <= SMALL_CNT) {
                 uint32_t idx[SMALL_CNT];
 #pragma unroll
@@ -1040,9 +1075,6 @@ k_emit(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtenso
                 if (lane < cnt_o) perm[o][rank] = (unsigned char)lane;
             }
             __syncwarp();
-            // ---- mean of the kept points (torch CPU sum order) by the owning lane; the two work lists ----
-            const bool live = occ && cnt <= 32;
-            float mx = 0.f, my = 0.f, mz = 0.f;
             if (live) {
                 float row[RWc];
                 if (cnt == 1) {
@@ -1057,6 +1089,7 @@ k_emit(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtenso
                     const float fn = (float)n_keep;
                     mx = __fdiv_rn(sum.sx(), fn); my = __fdiv_rn(sum.sy(), fn); mz = __fdiv_rn(sum.sz(), fn);
                 }
+            }
             }
             const unsigned sbal = __ballot_sync(FULL, live && n_keep == 1);
             const unsigned mbal = __ballot_sync(FULL, live && n_keep > 1);
@@ -1116,10 +1149,10 @@ k_emit(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtenso
                     eval_row(rowB, rB0.x, rB0.y, rB0.z, cxB, cy, b0, b1, b2, b3);
                     if (p.feats) {
                         st_f4_hint(p.feats + (size_t)__float_as_int(rA1.y) * C + c0,
-                                   make_float4(__int_as_float(a0), __int_as_float(a1), __int_as_float(a2), __int_as_float(a3)), stream_policy);
+                                   make_float4(__int_as_float(a0), __int_as_float(a1), __int_as_float(a2), __int_as_float(a3)), feats_policy);
                         if (okB)
                             st_f4_hint(p.feats + (size_t)__float_as_int(rB1.y) * C + c0,
-                                       make_float4(__int_as_float(b0), __int_as_float(b1), __int_as_float(b2), __int_as_float(b3)), stream_policy);
+                                       make_float4(__int_as_float(b0), __int_as_float(b1), __int_as_float(b2), __int_as_float(b3)), feats_policy);
                     }
                     put_tile(cellA, a0, a1, a2, a3);
                     if (okB) put_tile(cellB, b0, b1, b2, b3);
@@ -1152,7 +1185,7 @@ k_emit(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtenso
                 if (half == 0) {
                     if (p.feats)
                         st_f4_hint(p.feats + (size_t)__float_as_int(r1.y) * C + c0,
-                                   make_float4(__int_as_float(v0), __int_as_float(v1), __int_as_float(v2), __int_as_float(v3)), stream_policy);
+                                   make_float4(__int_as_float(v0), __int_as_float(v1), __int_as_float(v2), __int_as_float(v3)), feats_policy);
                     put_tile(cell, v0, v1, v2, v3);
                 }
             }
@@ -1194,7 +1227,7 @@ k_emit(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtenso
                 if (half == 0) {
                     if (p.feats)
                         st_f4_hint(p.feats + (size_t)f_o * C + c0,
-                                   make_float4(__int_as_float(v0), __int_as_float(v1), __int_as_float(v2), __int_as_float(v3)), stream_policy);
+                                   make_float4(__int_as_float(v0), __int_as_float(v1), __int_as_float(v2), __int_as_float(v3)), feats_policy);
                     put_tile(o, v0, v1, v2, v3);
                 }
                 __syncwarp();
@@ -1224,7 +1257,7 @@ k_emit(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtenso
                 fence_proxy_async_smem();
                 __syncwarp();
 #ifdef HGSF_EXPERIMENT
-                if (lane == 0 && !(p.dbg & 2)) { tma_store_3d_hint(&tmap, tile, x0, y, b * C, stream_policy); tma_commit(); }
+                if (lane == 0 && !(p.dbg & 2)) { if (p.dbg & 4) tma_store_3d(&tmap, tile, x0, y, b * C); else tma_store_3d_hint(&tmap, tile, x0, y, b * C, stream_policy); tma_commit(); }
 #else
                 if (lane == 0) { tma_store_3d_hint(&tmap, tile, x0, y, b * C, stream_policy); tma_commit(); }
 #endif
@@ -1352,8 +1385,11 @@ static int launch_emit_t(const PathParams &p, cudaStream_t stream) {
         if (st == HGSF_OK) st = make_canvas_map(&zmap, p.canvas, p.B, C, p.ny, p.nx, C / 4);
         if (st != HGSF_OK) return st;
     }
-    const size_t smem = 1024 + sizeof(float) * (EMIT_WARPS * C * 32 + (C / 4) * 32 + EMIT_WARPS * 2 * STAGE_W * RWc) +
-                        sizeof(int) * 2 * (size_t)(p.B + 1);
+    size_t smem = 1024 + sizeof(float) * (EMIT_WARPS * C * 32 + (C / 4) * 32 + EMIT_WARPS * 2 * STAGE_W * RWc) +
+                  sizeof(int) * 2 * (size_t)(p.B + 1);
+#ifdef HGSF_EXPERIMENT
+    if (const char *ex = getenv("HGSF_EXTRA_SMEM")) smem += (size_t)atoi(ex);      // occupancy experiments: fewer CTAs per SM
+#endif
     const long long n_tiles = (long long)p.B * p.ny * ((p.nx + 31) / 32);
     if (n_tiles == 0) return HGSF_OK;
     const bool bn = p.bn_w != nullptr;
