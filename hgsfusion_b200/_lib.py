@@ -20,7 +20,8 @@ EXPORTS = ["hgsf_abi_version", "hgsf_status_string", "hgsf_pillar_capacity", "hg
            "hgsf_pillarnet_workspace_size", "hgsf_pillarnet_indices", "hgsf_gather_feature", "hgsf_gather_feature_grad",
            "hgsf_scatter_max", "hgsf_scatter_max_grad", "hgsf_split_encode", "hgsf_pillarnet_reader",
            "hgsf_train_stats_doubles", "hgsf_train_scratch_doubles", "hgsf_pillar_vfe_batch_stats",
-           "hgsf_pillar_vfe_backward", "hgsf_pointpillar_scatter_backward"]
+           "hgsf_pillar_vfe_backward", "hgsf_pointpillar_scatter_backward", "hgsf_hybrid_workspace_size",
+           "hgsf_assemble_hybrid_points"]
 
 
 class Geometry(C.Structure):
@@ -45,6 +46,13 @@ class PillarOutputs(C.Structure):
     _fields_ = [("voxel_coords", C.c_void_p), ("voxel_num_points", C.c_void_p), ("voxels", C.c_void_p),
                 ("pillar_features", C.c_void_p), ("spatial_features", C.c_void_p), ("num_pillars", C.c_void_p),
                 ("pillar_capacity", C.c_int64)]
+
+
+class HybridInputs(C.Structure):
+    _fields_ = [("real", C.c_void_p), ("gt_real", C.c_void_p), ("virt", C.c_void_p), ("real_offsets", C.c_void_p),
+                ("gt_offsets", C.c_void_p), ("virt_offsets", C.c_void_p), ("n_candidates", C.c_int64),
+                ("real_features", C.c_int32), ("hybrid_features", C.c_int32), ("batch_size", C.c_int32),
+                ("no_dup", C.c_int32), ("dup_threshold", C.c_double)]
 
 
 class HgsfError(RuntimeError):
@@ -104,6 +112,9 @@ def load():
                                                         C.c_void_p]
     lib.hgsf_pointpillar_scatter_backward.argtypes = [C.POINTER(Geometry), C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int32,
                                                       C.c_int32, C.c_void_p, C.c_void_p]
+    lib.hgsf_hybrid_workspace_size.argtypes = [C.c_int64, C.POINTER(C.c_size_t)]
+    lib.hgsf_assemble_hybrid_points.argtypes = [C.POINTER(HybridInputs), C.c_void_p, C.POINTER(C.c_double), C.c_void_p, C.c_size_t,
+                                                C.c_void_p, C.c_void_p, C.c_void_p]
     lib.hgsf_emit_timing_begin.argtypes = [C.c_int]
     lib.hgsf_emit_timing_collect.argtypes = [C.POINTER(C.c_float), C.c_int]
     for name in EXPORTS:

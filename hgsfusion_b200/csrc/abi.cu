@@ -1,6 +1,7 @@
 // abi.cu -- the extern "C" surface declared in include/hgsfusion_b200.h.
 // Validation, parameter packing, workspace carving; no allocation, no host synchronisation.
 #include "contract_ops.cuh"
+#include "hybrid_points.cuh"
 #include "pillar_path.cuh"
 #include "pillarnet_ops.cuh"
 #include "train_ops.cuh"
@@ -349,6 +350,34 @@ int hgsf_pointpillar_scatter_backward(const hgsf_geometry *g, const float *grad_
                                        static_cast<cudaStream_t>(stream));
     if (st == HGSF_OK) g_last_launches = M > 0;
     return st;
+}
+
+int hgsf_hybrid_workspace_size(int64_t n_candidates, size_t *bytes) {
+    if (n_candidates < 0 || !bytes) return HGSF_ERR_INVALID_ARG;
+    *bytes = hybrid_workspace_bytes(n_candidates);
+    return HGSF_OK;
+}
+
+int hgsf_assemble_hybrid_points(const hgsf_hybrid_inputs *in, const float *calib, const double *range_xy, void *ws,
+                                size_t ws_bytes, float *points_out, int32_t *frame_offsets_out, hgsf_stream_t stream) {
+    g_last_launches = 0;
+    if (!in || !frame_offsets_out || in->n_candidates < 0 || in->batch_size <= 0 || in->real_features < 3 ||
+        !in->real_offsets)
+        return HGSF_ERR_INVALID_ARG;
+    const bool hybrid = in->hybrid_features != 0;
+    if (hybrid && (in->hybrid_features < in->real_features || !in->gt_offsets || !in->virt_offsets)) return HGSF_ERR_INVALID_ARG;
+    if (in->n_candidates > 0 && (!points_out || !ws)) return HGSF_ERR_INVALID_ARG;
+    if (in->n_candidates >= (int64_t)INT_MAX || in->batch_size > 32767) return HGSF_ERR_UNSUPPORTED;
+    HybridParams q{};
+    q.real = in->real; q.gt = hybrid ? in->gt_real : nullptr; q.virt = hybrid ? in->virt : nullptr;
+    q.real_off = in->real_offsets; q.gt_off = in->gt_offsets; q.virt_off = in->virt_offsets;
+    q.calib = calib;
+    q.Fr = in->real_features; q.W = in->hybrid_features; q.B = in->batch_size; q.n = in->n_candidates;
+    q.no_dup = hybrid ? in->no_dup : 0; q.dup_threshold = in->dup_threshold;
+    q.mask_range = range_xy != nullptr;
+    for (int j = 0; j < 4; ++j) q.range_xy[j] = range_xy ? range_xy[j] : 0.0;
+    q.out = points_out; q.frame_offsets_out = frame_offsets_out;
+    return launch_hybrid(q, ws, ws_bytes, static_cast<cudaStream_t>(stream), &g_last_launches);
 }
 
 }  // extern "C"

@@ -278,6 +278,47 @@ HGSF_API int hgsf_pointpillar_scatter_backward(const hgsf_geometry *geom, const 
                                                int32_t C, int32_t batch_size, float *grad_pillar_features,
                                                hgsf_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Hybrid point assembly on the device -- the step in front of the path.  Replaces, per batch and
+ * without a host sync, what the reference does per sample in float64 numpy inside DataLoader workers:
+ *   pcdet/datasets/kitti/vod_dataset.py:498-522 / tj4d_dataset.py:588-610   raw sweep + mask points + virtual points ->
+ *        [N, W+2] with the two flag columns: sweep rows (1,1) and 1 in the 8 label columns, mask rows (0,0), virtual rows
+ *        (0,1); a frame without mask points keeps only its sweep; with mask points but no virtual points every row gets 1
+ *        in the last column (the reference's points[-0:, -1] = 1)
+ *   vod_dataset.py:13-19,511-514     NO_DUP: sweep rows whose squared distance to a mask point is <= dup_threshold dropped
+ *   vod_dataset.py:181-197,525-528 + pcdet/utils/calibration_kitti.py:68-88   FOV_POINTS_ONLY
+ *   pcdet/utils/common_utils.py:78-81 (data_processor.py:83-85)               x/y range mask, both ends inclusive
+ *   pcdet/datasets/dataset.py:237-244, pcdet/models/__init__.py:23-36         batch-index column, float32
+ * Inputs are float32 device arrays, the frames concatenated, with [batch_size+1] int32 device offsets each:
+ *   real [sum Nr, real_features] (7 VoD, 8 TJ4D); gt_real / virt [.., hybrid_features] with hybrid_features =
+ *   real_features + 8, or hybrid_features = 0 and NULL arrays for USE_VIRTUAL_POINTS False (output rows = the sweep).
+ *   calib: NULL (FOV_POINTS_ONLY False) or [batch_size, 26] float32 per frame: the [4,3] lidar->rect matrix V2C^T.R0^T
+ *   (row major, the float32 product calibration_kitti.py:74 forms), P2 [3,4] row major, image height, image width.
+ *   range_xy: NULL (no range mask) or {xmin, ymin, xmax, ymax} as DOUBLES -- the reference compares float64 points with
+ *   the Python floats of POINT_CLOUD_RANGE, which differs from a float32 compare for points on the boundary.
+ * The filters are evaluated in double in the reference's order; the kept set and the row order are identical.
+ * points_out [n_candidates, 1 + F] (F = hybrid_features + 2, or real_features) receives the kept rows, frame after frame
+ * in input order, column 0 = frame index -- the collated layout hgsf_points_to_bev / hgsf_split_encode take;
+ * frame_offsets_out [batch_size+1] int32 (device) = row offset of every frame, last entry = rows kept. */
+typedef struct hgsf_hybrid_inputs {
+    const float   *real;
+    const float   *gt_real;
+    const float   *virt;
+    const int32_t *real_offsets;
+    const int32_t *gt_offsets;
+    const int32_t *virt_offsets;
+    int64_t        n_candidates;     /* sum Nr + sum Ng + sum Nv */
+    int32_t        real_features;
+    int32_t        hybrid_features;
+    int32_t        batch_size;
+    int32_t        no_dup;
+    double         dup_threshold;    /* 0.001 in the reference */
+} hgsf_hybrid_inputs;
+HGSF_API int hgsf_hybrid_workspace_size(int64_t n_candidates, size_t *bytes);
+HGSF_API int hgsf_assemble_hybrid_points(const hgsf_hybrid_inputs *in, const float *calib, const double *range_xy,
+                                         void *workspace, size_t workspace_bytes, float *points_out,
+                                         int32_t *frame_offsets_out, hgsf_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
