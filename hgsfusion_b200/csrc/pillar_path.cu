@@ -117,29 +117,61 @@ __device__ __forceinline__ void count_finish(const PathParams &p, int i, int key
     }
 }
 
-// phase 3 body
-__device__ __forceinline__ void fill_point(const PathParams &p, int i) {
-    const int key = p.key[i];
-    if (key < 0) return;
-    const int b = key / p.cells;
-    const int local = (int)(p.cell_tag[key] - 1u) - p.frame_raw_base[b];
-    if (local >= p.max_voxels) return;            // pillar beyond max_voxels: never created
-    const size_t pos = (size_t)p.cell_start[key] + p.arrival[i];
-    const float *src = p.pts + (size_t)i * p.stride + p.xyz_col;
-    float4 *dst = reinterpret_cast<float4 *>(p.sorted_rows + pos * p.RW);
+// phase 3 body: U independent points per thread, staged by hand (keys -> table entries -> source rows -> stores) so that
+// the dependent loads of the U points overlap; the compiler cannot hoist them itself across the early exits and stores
+template <int U>
+__device__ __forceinline__ void fill_points(const PathParams &p, long long i0, long long step) {
+    int idx[U], key[U];
+    bool on[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const long long i = i0 + u * step;
+        on[u] = i < p.n;
+        idx[u] = (int)i;
+        key[u] = on[u] ? p.key[i] : -1;
+    }
+    uint32_t tag[U], start[U], arr[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        on[u] = on[u] && key[u] >= 0;
+        tag[u] = start[u] = arr[u] = 0u;
+        if (on[u]) { tag[u] = p.cell_tag[key[u]]; start[u] = p.cell_start[key[u]]; arr[u] = p.arrival[idx[u]]; }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        if (on[u]) {
+            const int b = key[u] / p.cells;
+            const int local = (int)(tag[u] - 1u) - p.frame_raw_base[b];
+            on[u] = local < p.max_voxels;             // pillar beyond max_voxels: never created
+        }
+    }
     for (int k = 0; k < p.RW; k += 4) {
-        float4 v;
-        // F features, then the point index (slot F) that k_pfn orders the pillar by
-        const float fi = __int_as_float(i);
-        v.x = (k + 0 < p.F) ? __ldg(src + k + 0) : (k + 0 == p.F ? fi : 0.f);
-        v.y = (k + 1 < p.F) ? __ldg(src + k + 1) : (k + 1 == p.F ? fi : 0.f);
-        v.z = (k + 2 < p.F) ? __ldg(src + k + 2) : (k + 2 == p.F ? fi : 0.f);
-        v.w = (k + 3 < p.F) ? __ldg(src + k + 3) : (k + 3 == p.F ? fi : 0.f);
-        dst[k >> 2] = v;
+        float4 v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (!on[u]) continue;
+            const float *src = p.pts + (size_t)idx[u] * p.stride + p.xyz_col;
+            // F features, then the point index (slot F) that k_emit / k_pfn order the pillar by
+            const float fi = __int_as_float(idx[u]);
+            v[u].x = (k + 0 < p.F) ? __ldg(src + k + 0) : (k + 0 == p.F ? fi : 0.f);
+            v[u].y = (k + 1 < p.F) ? __ldg(src + k + 1) : (k + 1 == p.F ? fi : 0.f);
+            v[u].z = (k + 2 < p.F) ? __ldg(src + k + 2) : (k + 2 == p.F ? fi : 0.f);
+            v[u].w = (k + 3 < p.F) ? __ldg(src + k + 3) : (k + 3 == p.F ? fi : 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (!on[u]) continue;
+            const size_t pos = (size_t)start[u] + arr[u];
+            reinterpret_cast<float4 *>(p.sorted_rows + pos * p.RW)[k >> 2] = v[u];
+        }
     }
 }
 
 constexpr int FRONT_THREADS = 256;
+#ifndef HGSF_FRONT_ILP
+#define HGSF_FRONT_ILP 2
+#endif
+constexpr int FRONT_ILP = HGSF_FRONT_ILP;         // independent points per thread in the count and fill phases
 constexpr int SCAN_ITEMS = SCAN_TILE / FRONT_THREADS;   // 4
 __device__ __forceinline__ uint64_t pack2(uint32_t pillars, uint32_t points) { return ((uint64_t)pillars << 32) | points; }
 
@@ -181,17 +213,25 @@ __global__ void __launch_bounds__(FRONT_THREADS) k_front(const PathParams p) {
     // ---- phase 1: count ----
     {
         const long long n_pad = ((long long)p.n + 31) & ~31ll;
-        for (long long i = gtid; i < n_pad; i += 2 * nthr) {
-            const long long i2 = i + nthr;                     // a second, independent point: its loads and atomics overlap the first's
-            const bool two = i2 < n_pad;                       // warp-uniform (n_pad and nthr are multiples of 32)
-            const int k1 = point_key(p, (int)i);
-            const int k2 = two ? point_key(p, (int)i2) : -1;
-            int l1, r1, l2 = 0, r2 = 0;
-            const unsigned b1 = count_issue(p, (int)i, k1, lane, l1, r1);
-            unsigned b2 = 0;
-            if (two) b2 = count_issue(p, (int)i2, k2, lane, l2, r2);
-            count_finish(p, (int)i, k1, b1, l1, r1);
-            if (two) count_finish(p, (int)i2, k2, b2, l2, r2);
+        // FRONT_ILP independent points per thread: their loads, divides and atomics overlap (the phase is a chain of L2 round
+        // trips).  `on` is warp-uniform (n_pad and nthr are multiples of 32), so the warp-wide match stays convergent.
+        for (long long i = gtid; i < n_pad; i += FRONT_ILP * nthr) {
+            int k[FRONT_ILP], l[FRONT_ILP], r[FRONT_ILP];
+            unsigned bs[FRONT_ILP];
+            bool on[FRONT_ILP];
+#pragma unroll
+            for (int u = 0; u < FRONT_ILP; ++u) {
+                on[u] = i + u * nthr < n_pad;
+                k[u] = on[u] ? point_key(p, (int)(i + u * nthr)) : -1;
+            }
+#pragma unroll
+            for (int u = 0; u < FRONT_ILP; ++u) {
+                l[u] = 0; r[u] = 0; bs[u] = 0;
+                if (on[u]) bs[u] = count_issue(p, (int)(i + u * nthr), k[u], lane, l[u], r[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < FRONT_ILP; ++u)
+                if (on[u]) count_finish(p, (int)(i + u * nthr), k[u], bs[u], l[u], r[u]);
         }
     }
     grid.sync();
@@ -346,10 +386,7 @@ __global__ void __launch_bounds__(FRONT_THREADS) k_front(const PathParams p) {
     grid.sync();
     stamp(4);
     // ---- phase 3: fill ----
-    for (long long i = gtid; i < p.n; i += 2 * nthr) {
-        fill_point(p, (int)i);
-        if (i + nthr < p.n) fill_point(p, (int)(i + nthr));
-    }
+    for (long long i = gtid; i < p.n; i += FRONT_ILP * nthr) fill_points<FRONT_ILP>(p, i, nthr);
     stamp(5);
 }
 
