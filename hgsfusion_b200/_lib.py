@@ -21,7 +21,7 @@ EXPORTS = ["hgsf_abi_version", "hgsf_status_string", "hgsf_pillar_capacity", "hg
            "hgsf_scatter_max", "hgsf_scatter_max_grad", "hgsf_split_encode", "hgsf_pillarnet_reader",
            "hgsf_train_stats_doubles", "hgsf_train_scratch_doubles", "hgsf_pillar_vfe_batch_stats",
            "hgsf_pillar_vfe_backward", "hgsf_pointpillar_scatter_backward", "hgsf_hybrid_workspace_size",
-           "hgsf_assemble_hybrid_points"]
+           "hgsf_assemble_hybrid_points", "hgsf_sparse_to_dense_workspace_size", "hgsf_sparse_to_dense"]
 
 
 class Geometry(C.Structure):
@@ -115,6 +115,9 @@ def load():
     lib.hgsf_hybrid_workspace_size.argtypes = [C.c_int64, C.POINTER(C.c_size_t)]
     lib.hgsf_assemble_hybrid_points.argtypes = [C.POINTER(HybridInputs), C.c_void_p, C.POINTER(C.c_double), C.c_void_p, C.c_size_t,
                                                 C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.hgsf_sparse_to_dense_workspace_size.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_size_t)]
+    lib.hgsf_sparse_to_dense.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
+                                         C.c_size_t, C.c_void_p, C.c_void_p]
     lib.hgsf_emit_timing_begin.argtypes = [C.c_int]
     lib.hgsf_emit_timing_collect.argtypes = [C.POINTER(C.c_float), C.c_int]
     for name in EXPORTS:

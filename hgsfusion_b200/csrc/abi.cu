@@ -170,7 +170,7 @@ int hgsf_pointpillar_scatter(const hgsf_geometry *g, const float *feats, const v
     if (ws_bytes < need || (reinterpret_cast<uintptr_t>(ws) & 255)) return HGSF_ERR_WORKSPACE;
     if ((int64_t)g->grid[0] * g->grid[1] * B > INT_MAX || M >= UINT_MAX) return HGSF_ERR_UNSUPPORTED;
     ScatterParams q{};
-    q.feats = feats; q.coords = coords; q.coords_float = coords_are_float; q.M = M; q.C = C; q.B = B;
+    q.feats = feats; q.coords = coords; q.coords_float = coords_are_float; q.coord_cols = 4; q.M = M; q.C = C; q.B = B;
     q.ny = g->grid[1]; q.nx = g->grid[0]; q.plane = (long long)g->grid[0] * g->grid[1];
     q.map = static_cast<unsigned *>(ws); q.canvas = canvas;
     return launch_scatter(q, static_cast<cudaStream_t>(stream), &g_last_launches);
@@ -378,6 +378,29 @@ int hgsf_assemble_hybrid_points(const hgsf_hybrid_inputs *in, const float *calib
     for (int j = 0; j < 4; ++j) q.range_xy[j] = range_xy ? range_xy[j] : 0.0;
     q.out = points_out; q.frame_offsets_out = frame_offsets_out;
     return launch_hybrid(q, ws, ws_bytes, static_cast<cudaStream_t>(stream), &g_last_launches);
+}
+
+int hgsf_sparse_to_dense_workspace_size(int32_t B, int32_t ny, int32_t nx, size_t *bytes) {
+    if (!bytes || B <= 0 || ny <= 0 || nx <= 0) return HGSF_ERR_INVALID_ARG;
+    *bytes = align_up(sizeof(unsigned) * (size_t)B * ny * nx, 256);
+    return HGSF_OK;
+}
+
+int hgsf_sparse_to_dense(const float *features, const int32_t *indices, int64_t M, int32_t C, int32_t B, int32_t ny,
+                         int32_t nx, void *ws, size_t ws_bytes, float *dense, hgsf_stream_t stream) {
+    g_last_launches = 0;
+    if (M < 0 || B <= 0 || C <= 0 || ny <= 0 || nx <= 0 || !dense || !ws) return HGSF_ERR_INVALID_ARG;
+    if (M > 0 && (!features || !indices)) return HGSF_ERR_INVALID_ARG;
+    if (C % 32 != 0 || C > 256) return HGSF_ERR_UNSUPPORTED;
+    if ((int64_t)nx * ny * B > INT_MAX || M >= UINT_MAX || ny > 65535 || nx > 65535) return HGSF_ERR_UNSUPPORTED;
+    size_t need = 0;
+    hgsf_sparse_to_dense_workspace_size(B, ny, nx, &need);
+    if (ws_bytes < need || (reinterpret_cast<uintptr_t>(ws) & 255)) return HGSF_ERR_WORKSPACE;
+    ScatterParams q{};
+    q.feats = features; q.coords = indices; q.coords_float = 0; q.coord_cols = 3; q.M = M; q.C = C; q.B = B;
+    q.ny = ny; q.nx = nx; q.plane = (long long)nx * ny;
+    q.map = static_cast<unsigned *>(ws); q.canvas = dense;
+    return launch_scatter(q, static_cast<cudaStream_t>(stream), &g_last_launches);
 }
 
 }  // extern "C"

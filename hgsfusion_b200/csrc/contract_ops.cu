@@ -101,6 +101,13 @@ __global__ void __launch_bounds__(256) k_scatter_map(const ScatterParams q) {
         // indices = c1 + c2 * nx + c3 evaluated in fp32 like the reference (pointpillar_scatter.py:31-32)
         idx = (long long)__fadd_rn(__fadd_rn(c.y, __fmul_rn(c.z, (float)q.nx)), c.w);
         if (!(c.x >= 0.f) || !(c.x < (float)q.B)) return;
+    } else if (q.coord_cols == 3) {
+        // SparseConvTensor indices (b, y, x) -- the .dense() of the PillarNet branch (lss_fpn.py:111-113)
+        const int *c = reinterpret_cast<const int *>(q.coords) + 3 * m;
+        const int y = __ldg(c + 1), x = __ldg(c + 2);
+        b = __ldg(c);
+        if (b < 0 || b >= q.B || y < 0 || y >= q.ny || x < 0 || x >= q.nx) return;
+        idx = (long long)y * q.nx + x;
     } else {
         const int4 c = __ldg(reinterpret_cast<const int4 *>(q.coords) + m);
         b = c.x;

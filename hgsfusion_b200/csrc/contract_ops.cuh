@@ -21,6 +21,7 @@ struct ScatterParams {
     const float *feats;       // [M, C]
     const void *coords;       // [M, 4]
     int coords_float;
+    int coord_cols;           // 4 (b, z, y, x) or 3 (b, y, x; int32 only)
     long long M;
     int C, B, ny, nx;
     long long plane;          // nz*ny*nx (nz == 1)

@@ -221,6 +221,28 @@ class PillarMaxPooling(nn.Module):
             return pillar_features, pillar_indices, (self.bev_height, self.bev_width), B
 
 
+def sparse_to_dense(features, indices, spatial_shape, batch_size: int):
+    """`SparseConvTensor(features [M,C], indices [M,3] int32 (b, y, x), spatial_shape (Ny, Nx), batch_size).dense()` ->
+    [B, C, Ny, Nx], as the PillarNet branch calls it on its backbone outputs (pillarnet_modules/lss_fpn.py:111-113,
+    rpn.py:243-247) -- one pass over the dense tensor through hgsf_sparse_to_dense (zeros included).  Forward only."""
+    _need_cuda(features, "features", torch.float32)
+    _need_cuda(indices, "indices", torch.int32)
+    if features.dim() != 2 or indices.dim() != 2 or indices.shape[1] != 3 or indices.shape[0] != features.shape[0]:
+        raise ValueError("features [M,C] and indices [M,3] expected")
+    lib = _lib.load()
+    M, Cc = int(features.shape[0]), int(features.shape[1])
+    ny, nx = int(spatial_shape[0]), int(spatial_shape[1])
+    need = C.c_size_t(0)
+    _lib.check(lib.hgsf_sparse_to_dense_workspace_size(int(batch_size), ny, nx, C.byref(need)), "hgsf_sparse_to_dense_workspace_size")
+    ws = torch.empty(need.value + 256, dtype=torch.uint8, device=features.device)
+    ws_ptr = (ws.data_ptr() + 255) // 256 * 256
+    dense = torch.empty((int(batch_size), Cc, ny, nx), dtype=torch.float32, device=features.device)
+    st = lib.hgsf_sparse_to_dense(_p(features), _p(indices), M, Cc, int(batch_size), ny, nx, C.c_void_p(ws_ptr), need.value,
+                                  _p(dense), _s())
+    _lib.check(st, "hgsf_sparse_to_dense")
+    return dense
+
+
 _ENCODINGS = {"split": 0, "mixed": 1, "direct": 2}
 _SPLIT_N = {"vod": 12, "tj4d": 13}          # dynamic_pillar_encoder.py:72-76
 

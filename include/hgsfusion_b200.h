@@ -319,6 +319,16 @@ HGSF_API int hgsf_assemble_hybrid_points(const hgsf_hybrid_inputs *in, const flo
                                          void *workspace, size_t workspace_bytes, float *points_out,
                                          int32_t *frame_offsets_out, hgsf_stream_t stream);
 
+/* SparseConvTensor.dense() of the PillarNet branch (pcdet/models/backbones_3d/vfe/pillarnet_modules/lss_fpn.py:111-113,
+ * rpn.py:243-247; spconv's scatter of [M,C] features at int32 indices [M,3] = (b, y, x) into zeros [B, C, ny, nx]):
+ * SURVEY.md 8(a) row a16.  The same tile writer as hgsf_pointpillar_scatter (one pass over the dense tensor, zeros
+ * included, TMA tile stores); rows whose index falls outside are ignored; duplicate indices resolve to the last row
+ * (spconv's indices are unique).  C must be a multiple of 32, <= 256.  dense is written completely. */
+HGSF_API int hgsf_sparse_to_dense_workspace_size(int32_t batch_size, int32_t ny, int32_t nx, size_t *bytes);
+HGSF_API int hgsf_sparse_to_dense(const float *features, const int32_t *indices, int64_t num_rows, int32_t C,
+                                  int32_t batch_size, int32_t ny, int32_t nx, void *workspace, size_t workspace_bytes,
+                                  float *dense, hgsf_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

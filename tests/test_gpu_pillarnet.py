@@ -257,3 +257,25 @@ def test_fused_reader_entry_point(cuda, Cf, dataset):
     np.maximum.at(exp, qi, np.maximum(y, 0))
     assert feats.shape == exp.shape
     assert np.allclose(feats, exp, rtol=1e-5, atol=2e-6 * np.abs(exp).max())
+
+
+@pytest.mark.parametrize("C,ny,nx,B", [(32, 320, 320, 2), (64, 160, 160, 3), (128, 80, 80, 2), (256, 40, 40, 1), (64, 62, 54, 2)])
+def test_sparse_to_dense(C, ny, nx, B):
+    """the .dense() of the PillarNet branch (lss_fpn.py:111-113) at strides 1/2/4/8."""
+    import torch
+    from hgsfusion_b200 import pillar_ops
+    from oracle import pathb_oracle
+    rng = np.random.default_rng(C + nx)
+    cells = rng.choice(B * ny * nx, size=min(B * ny * nx // 5, 20000), replace=False)
+    idx = np.stack([cells // (ny * nx), (cells % (ny * nx)) // nx, cells % nx], 1).astype(np.int32)
+    feats = rng.normal(0, 1, (len(idx), C)).astype(np.float32)
+    dev = torch.device("cuda:0")
+    got = pillar_ops.sparse_to_dense(torch.from_numpy(feats).to(dev), torch.from_numpy(idx).to(dev), (ny, nx), B)
+    torch.cuda.synchronize()
+    ref = pathb_oracle.sparse_to_dense(feats, idx, (ny, nx), B)
+    assert np.array_equal(got.cpu().numpy().view(np.uint32), ref.view(np.uint32))
+    # empty tensor and out-of-range rows
+    got = pillar_ops.sparse_to_dense(torch.zeros((0, C), device=dev), torch.zeros((0, 3), dtype=torch.int32, device=dev), (ny, nx), B)
+    assert float(got.abs().max()) == 0.0
+    with pytest.raises(Exception):
+        pillar_ops.sparse_to_dense(torch.zeros((4, 48), device=dev), torch.zeros((4, 3), dtype=torch.int32, device=dev), (ny, nx), B)
