@@ -202,7 +202,7 @@ __global__ void __launch_bounds__(FRONT_THREADS) k_front(const PathParams p) {
     const long long gtid = (long long)blockIdx.x * FRONT_THREADS + tid, nthr = (long long)gridDim.x * FRONT_THREADS;
 
     // ---- phase 0: zero the cell table (and k_pfn's chunk ticket) ----
-    if (gtid == 0) { p.ticket[0] = 0u; p.ticket[1] = 0u; }     // k_pfn's chunk ticket, k_emit's tile-chunk ticket
+    if (gtid == 0) { p.ticket[0] = 0u; p.ticket[32] = 0u; }     // k_pfn's chunk ticket, k_emit's tile ticket (own 128-byte line)
     {
         uint4 *t4 = reinterpret_cast<uint4 *>(p.cell_tag);  // tag, cnt, start: three arrays back to back
         const long long n4 = (long long)(p.table_bytes >> 4);
@@ -789,8 +789,11 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-template <int F, bool ABS, bool DIST, bool BN, int STORE>
-__global__ void __launch_bounds__(EMIT_THREADS, 3)
+#ifndef HGSF_EMIT_MINB
+#define HGSF_EMIT_MINB 3
+#endif
+template <int F, bool ABS, bool DIST, bool BN, int STORE, int CHUNK>
+__global__ void __launch_bounds__(EMIT_THREADS, HGSF_EMIT_MINB)
 k_emit(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap zmap, const PathParams p) {
     constexpr int C = 64;
     constexpr int CIN = (ABS ? F : F - 3) + 6 + (DIST ? 1 : 0);
@@ -951,17 +954,21 @@ k_emit(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtenso
     // run of consecutive tiles per warp) also keeps x-adjacent tiles -- adjacent 128-byte pieces of the same canvas rows --
     // in flight at the same time on different warps, which the DRAM write stream rewards (measured: runs of 10 / 4 / 2 / 1
     // tiles -> 0.195 / 0.178 / 0.169 / 0.167 ms per step).
-#ifdef HGSF_CHUNK
-    constexpr int CHUNK = HGSF_CHUNK;
-#else
-    constexpr int CHUNK = 1;
-#endif
+    // A ticket covers CHUNK consecutive tiles (chosen by the launcher, a compile-time constant: as a run-time value it cost
+    // the dense workloads 3 %): 1 for the usual density, 2 for sparse
+    // scenes.  With mostly empty tiles (two thirds of TJ4D's at 30 000 points per frame) an iteration is shorter than the
+    // round trip of the same-address atomic under load and the warps wait for tickets (ncu: the atomic was the top stall,
+    // k_emit 0.374 ms against 0.239 ms with two tiles per ticket).  Tried instead and measured worse: several ticket
+    // counters over separate tile ranges (cure the stall but split the write stream: VoD uniform 0.169 -> 0.188 ms with 16
+    // queues), more tickets in flight per warp (no effect on the stall, tiles leave further out of order), tile order
+    // interleaved over the frames, a static round-robin assignment (loses the balancing).
     const int n_tiles = n_rows * tiles_per_row;
+    constexpr int chunk = CHUNK;
     // the ticket stays in lane 0's register until the chunk is actually started: broadcasting it right away would
     // stall the whole warp on the atomic's round trip
-    auto fetch_chunk_raw = [&]() -> int {
+    auto fetch_raw = [&]() -> int {
         int v = 0;
-        if (lane == 0) v = (int)atomicAdd(p.ticket + 1, 1u);
+        if (lane == 0) v = (int)atomicAdd(p.ticket + 32, 1u);
         return v;
     };
     auto decode = [&](int t) -> TilePos {
@@ -971,17 +978,17 @@ k_emit(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtenso
         q.b = q.r / rows_per_frame; q.zy = q.r - q.b * rows_per_frame;
         return q;
     };
-    int seq_left = CHUNK, seq_next_raw = 0;               // tiles left in the current chunk; ticket of the prefetched next chunk (lane 0)
-    TilePos seq = decode(__shfl_sync(FULL, fetch_chunk_raw(), 0) * CHUNK);   // the furthest tile handed to the pipeline so far
-    seq_next_raw = fetch_chunk_raw();
+    int seq_left = chunk, next_raw = 0;           // tiles left in the current chunk; ticket of the prefetched next chunk (lane 0)
+    TilePos seq = decode(__shfl_sync(FULL, fetch_raw(), 0) * chunk);   // the furthest tile handed to the pipeline so far
+    next_raw = fetch_raw();
     auto next_tile = [&]() -> TilePos {
         if (seq_left > 1 && seq.r < n_rows) {
             --seq_left;
             if (++seq.xt == tiles_per_row) { seq.xt = 0; ++seq.r; if (++seq.zy == rows_per_frame) { seq.zy = 0; ++seq.b; } }
         } else {
-            seq = decode(__shfl_sync(FULL, seq_next_raw, 0) * CHUNK);
-            seq_left = CHUNK;
-            if (seq.r < n_rows) seq_next_raw = fetch_chunk_raw();
+            seq = decode(__shfl_sync(FULL, next_raw, 0) * chunk);
+            seq_left = chunk;
+            if (seq.r < n_rows) next_raw = fetch_raw();
         }
         return seq;
     };
@@ -1028,7 +1035,9 @@ k_emit(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtenso
         if (bal_occ == 0u) {
             // empty tile: four stores of the shared zero tile
             if (TMA) {
-                if (lane == 0) {
+                // issued by lane 1: bulk async-groups are per thread, so lane 0's wait for its tile store to have read the
+                // tile buffer (below) does not also wait for the zero stores of the empty tiles that came after it
+                if (lane == 1) {
 #pragma unroll
                     for (int q4 = 0; q4 < 4; ++q4) tma_store_3d_hint(&zmap, zerobuf, x0, y, b * C + q4 * ZC, stream_policy);
                     tma_commit();
@@ -1065,6 +1074,17 @@ k_emit(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtenso
             const unsigned multi_bal = __ballot_sync(FULL, occ && cnt > 1);
             const unsigned pair_bal = __ballot_sync(FULL, occ && cnt == 2 && staged);
             const bool pairs_only = (multi_bal == pair_bal) && Pmax >= 2;
+#ifdef HGSF_EXPERIMENT
+            // ablation (WRONG results, timing only): as if the rows arrived ordered and the mean were precomputed
+            if (p.dbg & 32) {
+                if (live) {
+                    if (!(p.dbg & 64)) for (int j = 0; j < n_keep; ++j) perm[lane][j] = (unsigned char)j;
+                    const float4 a = *reinterpret_cast<const float4 *>((rel >= 0) ? stg + (size_t)rel * RWc : grows + (size_t)(-1 - rel) * RWc);
+                    mx = a.x; my = a.y; mz = a.z;
+                }
+                __syncwarp();
+            } else
+#endif
             if (pairs_only) {
                 if (occ && cnt == 2) {
                     const float *r0p = stg + (size_t)rel * RWc, *r1p = r0p + RWc;
@@ -1133,7 +1153,11 @@ k_emit(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtenso
             const int n_s = __popc(sbal), n_m = __popc(mbal);
             if (live) {
                 const int slot = (n_keep == 1) ? __popc(sbal & lt) : 31 - __popc(mbal & lt);   // singles from the front, multis from the back
+#ifdef HGSF_EXPERIMENT
+                const int pos0 = (cnt == 1 || (p.dbg & 64)) ? 0 : (int)perm[lane][0];
+#else
                 const int pos0 = (cnt == 1) ? 0 : (int)perm[lane][0];   // the one evaluated point (rank 0 when P == 1 truncated)
+#endif
                 rec[slot][0] = make_float4(mx, my, mz, __int_as_float(n_keep | (lane << 8) | (pos0 << 16)));
                 rec[slot][1] = make_float4(__int_as_float(rel), __int_as_float(f), 0.f, 0.f);
             }
@@ -1211,8 +1235,13 @@ k_emit(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtenso
                 for (int s2 = half; s2 < nk; s2 += 4) {
                     const int s3 = (s2 + 2 < nk) ? s2 + 2 : s2;        // the last odd one is evaluated twice: max is idempotent
                     float rowA[RWc], rowB[RWc];
+#ifdef HGSF_EXPERIMENT
+                    load_row(stg, relp, (p.dbg & 64) ? s2 : (int)perm[cell][s2], rowA);
+                    load_row(stg, relp, (p.dbg & 64) ? s3 : (int)perm[cell][s3], rowB);
+#else
                     load_row(stg, relp, perm[cell][s2], rowA);
                     load_row(stg, relp, perm[cell][s3], rowB);
+#endif
                     eval_row(rowA, r0.x, r0.y, r0.z, cx, cy, v0, v1, v2, v3);
                     eval_row(rowB, r0.x, r0.y, r0.z, cx, cy, u0, u1, u2, u3);
                 }
@@ -1323,7 +1352,7 @@ k_emit(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtenso
         cur = nxt; nxt = nxt2; nxt2 = next_tile();
     }
     cp_async_wait<0>();
-    if (TMA && lane == 0) tma_wait_read<0>();
+    if (TMA && lane <= 1) tma_wait_read<0>();        // shared memory must outlive the stores that read it
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1429,6 +1458,11 @@ static int launch_emit_t(const PathParams &p, cudaStream_t stream) {
 #endif
     const long long n_tiles = (long long)p.B * p.ny * ((p.nx + 31) / 32);
     if (n_tiles == 0) return HGSF_OK;
+    // tiles per ticket (see k_emit): sparse scenes -- fewer than 6 points per 32-cell tile on average, most tiles empty -- take 2
+    // (measured, ms per step at chunk 1 / 2 / 4: VoD 2 000 points per frame 0.138 / 0.116 / 0.119, VoD 10 000 0.142 / 0.134 /
+    // 0.138, TJ4D 30 000 clustered 0.429 / 0.310 / 0.324; VoD 30 000 0.182 / 0.195 / 0.203)
+    int chunk = ((long long)p.n < 6 * n_tiles) ? 2 : 1;
+    if (const char *tc = getenv("HGSF_TILE_CHUNK")) chunk = atoi(tc) >= 2 ? 2 : 1;
     const bool bn = p.bn_w != nullptr;
     auto go = [&](auto kern) -> int {
         int grid = 1;
@@ -1437,9 +1471,10 @@ static int launch_emit_t(const PathParams &p, cudaStream_t stream) {
         kern<<<(unsigned)grid, EMIT_THREADS, smem, stream>>>(map, zmap, p);
         return (int)cudaGetLastError();
     };
-    if (tma) return bn ? go(k_emit<F, ABS, DIST, true, 0>) : go(k_emit<F, ABS, DIST, false, 0>);
-    if (vec_ok) return bn ? go(k_emit<F, ABS, DIST, true, 1>) : go(k_emit<F, ABS, DIST, false, 1>);
-    return bn ? go(k_emit<F, ABS, DIST, true, 2>) : go(k_emit<F, ABS, DIST, false, 2>);
+    if (tma && chunk == 2) return bn ? go(k_emit<F, ABS, DIST, true, 0, 2>) : go(k_emit<F, ABS, DIST, false, 0, 2>);
+    if (tma) return bn ? go(k_emit<F, ABS, DIST, true, 0, 1>) : go(k_emit<F, ABS, DIST, false, 0, 1>);
+    if (vec_ok) return bn ? go(k_emit<F, ABS, DIST, true, 1, 1>) : go(k_emit<F, ABS, DIST, false, 1, 1>);
+    return bn ? go(k_emit<F, ABS, DIST, true, 2, 1>) : go(k_emit<F, ABS, DIST, false, 2, 1>);
 }
 
 static int launch_emit(const PathParams &p, bool abs_xyz, bool dist, cudaStream_t s) {

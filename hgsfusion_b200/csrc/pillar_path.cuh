@@ -16,7 +16,7 @@ struct PathParams {
     // ---- limits ----
     int P, max_voxels;
     // ---- workspace ----
-    uint32_t *ticket;                  // [1]      zeroed
+    uint32_t *ticket;                  // [64] zeroed by k_front: word 0 = k_pfn's chunk ticket, word 32 = k_emit's tile ticket
     uint64_t *scan_desc;               // [tiles]  zeroed
     int32_t *frame_raw_base;           // [B+1]    zeroed; raw (pre max_voxels) pillar id at each frame start
     uint32_t *cell_tag, *cell_cnt, *cell_start;   // [B*cells] each (padded to 16 entries), back to back; zeroed by k_front
@@ -52,7 +52,7 @@ inline WorkspaceLayout workspace_layout(int64_t n, int B, int64_t cells, int F) 
     size_t o = 0;
     w.scan_tiles = (int)((n + SCAN_TILE - 1) / SCAN_TILE);
     w.RW = (F + 1 + 3) / 4 * 4;   // F features + the point index
-    w.off_ticket = o;      o = align_up(o + 16, 256);
+    w.off_ticket = o;      o = align_up(o + 256, 256);                        // two counters, one 128-byte line each
     w.off_desc = o;        o = align_up(o + sizeof(uint64_t) * 4096, 256);          // per-CTA slice totals of k_front's scan
     w.off_raw_base = o;    o = align_up(o + sizeof(int32_t) * (size_t)(B + 1), 256);
     w.cell_array_bytes = align_up(sizeof(uint32_t) * ((size_t)B * (size_t)cells + 16), 256);
