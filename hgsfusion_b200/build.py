@@ -13,7 +13,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libhgsfusion_b200.so")
-SOURCES = ["pillar_path.cu", "contract_ops.cu", "pillarnet_ops.cu", "train_ops.cu", "hybrid_points.cu", "abi.cu"]
+SOURCES = ["pillar_path.cu", "contract_ops.cu", "pillarnet_ops.cu", "train_ops.cu", "hybrid_points.cu", "subm_conv.cu", "abi.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
               "-Xcompiler", "-fPIC,-fvisibility=hidden", "-Xptxas", "-v"]
 

@@ -4,6 +4,7 @@
 #include "hybrid_points.cuh"
 #include "pillar_path.cuh"
 #include "pillarnet_ops.cuh"
+#include "subm_conv.cuh"
 #include "train_ops.cuh"
 
 #include <climits>
@@ -401,6 +402,39 @@ int hgsf_sparse_to_dense(const float *features, const int32_t *indices, int64_t 
     q.ny = ny; q.nx = nx; q.plane = (long long)nx * ny;
     q.map = static_cast<unsigned *>(ws); q.canvas = dense;
     return launch_scatter(q, static_cast<cudaStream_t>(stream), &g_last_launches);
+}
+
+int hgsf_subm_neighbors(const int32_t *bev, const int32_t *pillars, int64_t M, const int32_t *m_dev, int32_t B, int32_t H,
+                        int32_t W, int32_t *nbr, hgsf_stream_t stream) {
+    g_last_launches = 0;
+    if (M < 0 || B <= 0 || H <= 0 || W <= 0) return HGSF_ERR_INVALID_ARG;
+    if (M > 0 && (!bev || !pillars || !nbr)) return HGSF_ERR_INVALID_ARG;
+    if ((int64_t)B * H * W > INT_MAX || M > INT_MAX / 9) return HGSF_ERR_UNSUPPORTED;
+    SubmNeighborParams q{};
+    q.bev = bev; q.pillars = pillars; q.m_dev = m_dev; q.M = M; q.B = B; q.H = H; q.W = W; q.nbr = nbr;
+    const int st = launch_subm_neighbors(q, static_cast<cudaStream_t>(stream));
+    if (st == HGSF_OK && M > 0) g_last_launches = 1;
+    return st;
+}
+
+int hgsf_subm_conv3x3(const hgsf_subm_conv *conv, const float *features, const int32_t *nbr, int64_t M, const int32_t *m_dev,
+                      const float *residual, float *out, hgsf_stream_t stream) {
+    g_last_launches = 0;
+    if (!conv || !conv->weight || M < 0 || conv->in_channels <= 0 || conv->out_channels <= 0) return HGSF_ERR_INVALID_ARG;
+    if (M > 0 && (!features || !nbr || !out)) return HGSF_ERR_INVALID_ARG;
+    if (conv->weight_layout != HGSF_WEIGHT_KRSC && conv->weight_layout != HGSF_WEIGHT_RSCK) return HGSF_ERR_INVALID_ARG;
+    const int n_bn = (conv->bn_weight != nullptr) + (conv->bn_bias != nullptr) + (conv->bn_mean != nullptr) + (conv->bn_var != nullptr);
+    if (n_bn != 0 && n_bn != 4) return HGSF_ERR_INVALID_ARG;
+    if (out == features && M > 0) return HGSF_ERR_INVALID_ARG;            // neighbours' rows are read by other CTAs
+    if (M > INT_MAX / 9) return HGSF_ERR_UNSUPPORTED;
+    SubmConvParams q{};
+    q.in = features; q.nbr = nbr; q.m_dev = m_dev; q.M = M; q.Cin = conv->in_channels; q.Cout = conv->out_channels;
+    q.W = conv->weight; q.layout = conv->weight_layout; q.bias = conv->bias;
+    q.bn_w = conv->bn_weight; q.bn_b = conv->bn_bias; q.bn_m = conv->bn_mean; q.bn_v = conv->bn_var; q.eps = conv->bn_eps;
+    q.residual = residual; q.relu = conv->relu; q.out = out;
+    const int st = launch_subm_conv(q, static_cast<cudaStream_t>(stream));
+    if (st == HGSF_OK && M > 0) g_last_launches = 1;
+    return st;
 }
 
 }  // extern "C"

@@ -1,0 +1,37 @@
+// subm_conv.cuh -- parameter blocks and launchers of the pillar-list consumer: the submanifold
+// 3x3 convolutions of SpMiddlePillarEncoder18.conv1 (pillarnet_modules/pcnres18.py:82-106,108-188,212-215) evaluated on
+// the pillar list the reader produced instead of on a dense canvas.
+#pragma once
+#include "common.cuh"
+
+namespace hgsf {
+
+struct SubmNeighborParams {
+    const int *bev;          // [B, H, W] pillar id per cell, -1 none (hgsf_pillarnet_indices)
+    const int *pillars;      // [M, 3] (b, y, x)
+    const int *m_dev;        // optional device row count (counts[0] of hgsf_pillarnet_indices); null = M
+    long long M;
+    int B, H, W;
+    int *nbr;                // [M, 9] pillar id at (y + ky - 1, x + kx - 1), tap = ky * 3 + kx; -1 none
+};
+
+struct SubmConvParams {
+    const float *in;         // [M, Cin]
+    const int *nbr;          // [M, 9]
+    const int *m_dev;        // optional device row count
+    long long M;
+    int Cin, Cout;
+    const float *W;          // see layout
+    int layout;              // 0: [Cout, 3, 3, Cin] (spconv 2.x), 1: [3, 3, Cin, Cout] (spconv 1.x)
+    const float *bias;       // [Cout] or null
+    const float *bn_w, *bn_b, *bn_m, *bn_v;   // BatchNorm1d eval or null
+    float eps;
+    const float *residual;   // [M, Cout] or null, added after the BatchNorm
+    int relu;
+    float *out;              // [M, Cout]
+};
+
+int launch_subm_neighbors(const SubmNeighborParams &q, cudaStream_t stream);
+int launch_subm_conv(const SubmConvParams &q, cudaStream_t stream);
+
+}  // namespace hgsf

@@ -329,6 +329,45 @@ HGSF_API int hgsf_sparse_to_dense(const float *features, const int32_t *indices,
                                   int32_t batch_size, int32_t ny, int32_t nx, void *workspace, size_t workspace_bytes,
                                   float *dense, hgsf_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * The pillar-list consumer: the submanifold 3x3 convolutions of SpMiddlePillarEncoder18.conv1
+ * (pcdet/models/backbones_3d/vfe/pillarnet_modules/pcnres18.py:82-95 conv2D3x3 with stride 1 -> spconv.SubMConv2d,
+ * :108-151 Sparse2DBasicBlockV, :154-188 Sparse2DBasicBlock, :212-215 conv1) evaluated on the reader's pillar list
+ * (pillar_modules.py:82) instead of on a dense canvas.
+ *
+ * hgsf_subm_neighbors: the rule book of one indice_key -- neighbors [num_rows, 9] int32, entry tap = ky*3 + kx holds the
+ *   pillar id at (y + ky - 1, x + kx - 1) of the same frame or -1 -- from pillar_bev_indices [B,H,W] and pillars [M,3]
+ *   (b, y, x), both outputs of hgsf_pillarnet_indices.  Built once and reused by every convolution sharing the key.
+ * hgsf_subm_conv3x3: out[m] = act( BN( bias + sum_tap W[tap] . in[neighbors[m][tap]] ) + residual[m] ), absent
+ *   neighbours contributing nothing: the cross-correlation spconv.SubMConv2d(kernel 3, padding 1) computes on the active
+ *   set.  fp32 FMA in (tap, input channel) order.  weight_layout HGSF_WEIGHT_KRSC: [Cout, 3, 3, Cin] (spconv 2.x),
+ *   HGSF_WEIGHT_RSCK: [3, 3, Cin, Cout] (spconv 1.x).  bias, the four bn_* (BatchNorm1d eval, all or none) and residual
+ *   [num_rows, Cout] may be NULL.  (Cin, Cout) in {(32,32), (32,64), (64,64)}.  out must not alias features;
+ *   out == residual is allowed (each element is read and written by the same thread).
+ * num_rows_dev: optional device int32 holding the row count (counts[0] of hgsf_pillarnet_indices) so that no host sync is
+ *   needed; rows >= min(num_rows, *num_rows_dev) are left untouched. */
+#define HGSF_WEIGHT_KRSC 0
+#define HGSF_WEIGHT_RSCK 1
+typedef struct hgsf_subm_conv {
+    const float *weight;
+    int32_t      weight_layout;
+    const float *bias;          /* [Cout] or NULL */
+    const float *bn_weight;     /* [Cout] or NULL */
+    const float *bn_bias;
+    const float *bn_mean;
+    const float *bn_var;
+    float        bn_eps;
+    int32_t      in_channels;
+    int32_t      out_channels;
+    int32_t      relu;
+} hgsf_subm_conv;
+HGSF_API int hgsf_subm_neighbors(const int32_t *pillar_bev_indices, const int32_t *pillars, int64_t num_rows,
+                                 const int32_t *num_rows_dev, int32_t batch_size, int32_t H, int32_t W,
+                                 int32_t *neighbors, hgsf_stream_t stream);
+HGSF_API int hgsf_subm_conv3x3(const hgsf_subm_conv *conv, const float *features, const int32_t *neighbors,
+                               int64_t num_rows, const int32_t *num_rows_dev, const float *residual, float *out,
+                               hgsf_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
