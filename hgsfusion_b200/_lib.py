@@ -21,7 +21,8 @@ EXPORTS = ["hgsf_abi_version", "hgsf_status_string", "hgsf_pillar_capacity", "hg
            "hgsf_scatter_max", "hgsf_scatter_max_grad", "hgsf_split_encode", "hgsf_pillarnet_reader",
            "hgsf_train_stats_doubles", "hgsf_train_scratch_doubles", "hgsf_pillar_vfe_batch_stats",
            "hgsf_pillar_vfe_backward", "hgsf_pointpillar_scatter_backward", "hgsf_hybrid_workspace_size",
-           "hgsf_assemble_hybrid_points", "hgsf_sparse_to_dense_workspace_size", "hgsf_sparse_to_dense"]
+           "hgsf_assemble_hybrid_points", "hgsf_sparse_to_dense_workspace_size", "hgsf_sparse_to_dense",
+           "hgsf_subm_neighbors", "hgsf_subm_conv3x3"]
 
 
 class Geometry(C.Structure):
@@ -53,6 +54,12 @@ class HybridInputs(C.Structure):
                 ("gt_offsets", C.c_void_p), ("virt_offsets", C.c_void_p), ("n_candidates", C.c_int64),
                 ("real_features", C.c_int32), ("hybrid_features", C.c_int32), ("batch_size", C.c_int32),
                 ("no_dup", C.c_int32), ("dup_threshold", C.c_double)]
+
+
+class SubmConv(C.Structure):
+    _fields_ = [("weight", C.c_void_p), ("weight_layout", C.c_int32), ("bias", C.c_void_p), ("bn_weight", C.c_void_p),
+                ("bn_bias", C.c_void_p), ("bn_mean", C.c_void_p), ("bn_var", C.c_void_p), ("bn_eps", C.c_float),
+                ("in_channels", C.c_int32), ("out_channels", C.c_int32), ("relu", C.c_int32)]
 
 
 class HgsfError(RuntimeError):
@@ -118,6 +125,10 @@ def load():
     lib.hgsf_sparse_to_dense_workspace_size.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_size_t)]
     lib.hgsf_sparse_to_dense.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                                          C.c_size_t, C.c_void_p, C.c_void_p]
+    lib.hgsf_subm_neighbors.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
+                                        C.c_void_p]
+    lib.hgsf_subm_conv3x3.argtypes = [C.POINTER(SubmConv), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_void_p]
     lib.hgsf_emit_timing_begin.argtypes = [C.c_int]
     lib.hgsf_emit_timing_collect.argtypes = [C.POINTER(C.c_float), C.c_int]
     for name in EXPORTS:

@@ -9,24 +9,35 @@
 //
 //   k_subm_neighbors : one thread per (pillar, tap): the rule book [M, 9] from the reader's pillar_bev_indices table; built
 //                      once per indice_key ("res1") and reused by all five convolutions, as spconv caches its indice pairs
-//   k_subm_conv      : persistent CTAs; a tile = 64 pillars x Cout.  The whole weight tensor (9 x Cin x Cout fp32: 36 KB
-//                      for 32 -> 32) stays in shared memory for the kernel's lifetime; per tap the 64 neighbour rows are
-//                      gathered with cp.async (16-byte pieces, zero rows for absent neighbours) into a double buffer
-//                      while the previous tap is being contracted; a thread holds a 4-pillar x (Cout/16)-channel
-//                      accumulator tile.  fp32 FMA on the CUDA cores in (tap, ci) order: spconv's default arithmetic
-//                      for fp32 features is fp32 (no TF32), so this is the faithful precision; the epilogue fuses bias,
-//                      BatchNorm1d (eval), the residual add and the ReLU, so a block's activations cross HBM once.
+//   k_subm_conv      : persistent CTAs of 128 threads; a tile = 64 pillars x Cout.  The whole weight tensor (9 x Cin x Cout
+//                      fp32: 36 KB for 32 -> 32) stays in shared memory for the kernel's lifetime; per tap the 64 neighbour
+//                      rows are gathered with cp.async (16-byte pieces, zero rows for absent neighbours; the neighbour ids
+//                      are read one gather early so no dependent shared-memory load sits in front of the copies) into a
+//                      three-stage ring, two taps ahead of the contraction, ONE barrier per tap.  A thread holds a
+//                      4-pillar x 4-channel accumulator tile as packed pairs: one FFMA2 (fma.rn.f32x2) per channel pair,
+//                      bit-identical to two fmaf in (tap, ci) order.  spconv's default arithmetic for fp32 features is
+//                      fp32 (no TF32), so CUDA-core FMA is the faithful precision; the epilogue fuses bias, BatchNorm1d
+//                      (eval), the residual add and the ReLU, so a block's activations cross HBM once.
 //
-// Bound: fp32 FMA issue (9 * Cin * Cout FMA per pillar = 9 216 for 32 -> 32 against 2 * 128 B of HBM traffic per pillar,
-// the gathers hit L2).
+// Bound: fp32 FMA (9 * Cin * Cout = 9 216 FMA per pillar for 32 -> 32 against 2 * 128 B of HBM traffic per pillar; the
+// gathers hit L2).  Measured on B200 (config 2, 182 k pillars): 0.103 ms per convolution = 32.8 TFLOP/s, 44 % of the
+// 74.5 TFLOP/s fp32 peak; ncu: shared-memory wavefronts at ~70 % of capacity -- every gathered 16-byte piece is re-read by
+// the 8 threads sharing the pillar, every weight by the 16 thread rows -- so shared-memory bandwidth and FMA issue bound
+// it about equally.  Thread tiles 4x2 / 8x2 / 8x4, tiles of 32 / 128 / 256 pillars and 2 / 4 stages measured within 10 %
+// below this one; a row-owner mapping (a thread owns whole pillars, weights as warp-wide broadcast loads) was built and
+// measured slower (26.8 TFLOP/s: 4 warps per SM at 166 registers).  [Cout,3,3,Cin] weights are transposed by every CTA
+// on the fly (-8 %): convert to [3,3,Cin,Cout] once when the weights are frozen (the Python mirror does).
 #include "subm_conv.cuh"
+
+#include <cstdlib>
+
+#ifndef SUBM_UNROLL
+#define SUBM_UNROLL 2
+#endif
 
 namespace hgsf {
 
 namespace {
-
-constexpr int SUBM_THREADS = 256;
-constexpr int SUBM_TM = 64;      // pillars per tile
 
 __global__ void __launch_bounds__(256) k_subm_neighbors(const SubmNeighborParams q) {
     const long long M = q.m_dev ? min((long long)max(q.m_dev[0], 0), q.M) : q.M;
@@ -49,43 +60,47 @@ __device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_grou
 template <int N>
 __device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-template <int CIN, int COUT>
-struct SubmSmem {
+// PT pillars x NCO output channels per thread; a tile = TM pillars x COUT channels, (COUT / NCO) * (TM / PT) threads
+template <int CIN, int COUT, int PT, int NCO, int TM, int NBUF>
+struct SubmCfg {
+    static constexpr int TXN = COUT / NCO;                   // threads along the channels
+    static constexpr int THREADS = TXN * (TM / PT);
     static constexpr int AS = CIN + 4;                       // padded row of the gathered tile
     static constexpr size_t w_bytes = sizeof(float) * 9 * CIN * COUT;
-    static constexpr size_t a_bytes = sizeof(float) * 2 * SUBM_TM * AS;
-    static constexpr size_t n_bytes = sizeof(int) * SUBM_TM * 9;
+    static constexpr size_t a_bytes = sizeof(float) * NBUF * TM * AS;
+    static constexpr size_t n_bytes = sizeof(int) * TM * 9;
     static constexpr size_t total = w_bytes + a_bytes + n_bytes;
 };
 
-template <int CIN, int COUT>
-__global__ void __launch_bounds__(SUBM_THREADS) k_subm_conv(const SubmConvParams q) {
-    using S = SubmSmem<CIN, COUT>;
-    constexpr int AS = S::AS;
-    constexpr int NCO = COUT / 16;            // output channels per thread
+template <int CIN, int COUT, int PT, int NCO, int TM, int NBUF>
+__global__ void __launch_bounds__(SubmCfg<CIN, COUT, PT, NCO, TM, NBUF>::THREADS) k_subm_conv(const SubmConvParams q) {
+    using S = SubmCfg<CIN, COUT, PT, NCO, TM, NBUF>;
+    constexpr int AS = S::AS, THREADS = S::THREADS, TXN = S::TXN;
     constexpr int C4 = CIN / 4;               // 16-byte pieces per row
+    constexpr int NP = NCO / 2;               // channel pairs per thread (packed fp32: one FFMA2 per pair)
+    static_assert(NCO == 2 || NCO == 4, "channel pairs");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float *Ws = reinterpret_cast<float *>(smem_raw);                        // [9][CIN][COUT]
-    float *As = reinterpret_cast<float *>(smem_raw + S::w_bytes);           // [2][TM][AS]
+    float *As = reinterpret_cast<float *>(smem_raw + S::w_bytes);           // [NBUF][TM][AS]
     int *Ns = reinterpret_cast<int *>(smem_raw + S::w_bytes + S::a_bytes);  // [TM][9]
 
     const int tid = threadIdx.x;
     const long long M = q.m_dev ? min((long long)max(q.m_dev[0], 0), q.M) : q.M;
-    const long long n_tiles = (M + SUBM_TM - 1) / SUBM_TM;
+    const long long n_tiles = (M + TM - 1) / TM;
     if ((long long)blockIdx.x >= n_tiles) return;
 
     // the weights, once per CTA, into [tap][ci][co]
     if (q.layout == 1) {
-        for (int i = tid; i < 9 * CIN * COUT / 4; i += SUBM_THREADS)
+        for (int i = tid; i < 9 * CIN * COUT / 4; i += THREADS)
             reinterpret_cast<float4 *>(Ws)[i] = __ldg(reinterpret_cast<const float4 *>(q.W) + i);
     } else {
-        for (int i = tid; i < 9 * CIN * COUT; i += SUBM_THREADS) {      // source order [co][tap][ci]: coalesced reads
+        for (int i = tid; i < 9 * CIN * COUT; i += THREADS) {      // source order [co][tap][ci]: coalesced reads
             const int ci = i % CIN, k = (i / CIN) % 9, co = i / (9 * CIN);
             Ws[(k * CIN + ci) * COUT + co] = __ldg(q.W + i);
         }
     }
 
-    const int tx = tid & 15, ty = tid >> 4;   // channels tx*NCO .. +NCO-1, pillars ty*4 .. +3 of the tile
+    const int tx = tid % TXN, ty = tid / TXN;   // channels tx*NCO .. +NCO-1, pillars ty*PT .. +PT-1 of the tile
     float bnm[NCO], bni[NCO], bnw[NCO], bnb[NCO], bia[NCO];
 #pragma unroll
     for (int c = 0; c < NCO; ++c) {
@@ -99,78 +114,89 @@ __global__ void __launch_bounds__(SUBM_THREADS) k_subm_conv(const SubmConvParams
         } else { bnm[c] = 0.f; bni[c] = 1.f; bnw[c] = 1.f; bnb[c] = 0.f; }
     }
 
-    auto gather = [&](int k, int buf) {
-        float *dst = As + (size_t)buf * SUBM_TM * AS;
+    constexpr int UNR = SUBM_UNROLL;
+    constexpr int CH = TM * C4 / THREADS;      // 16-byte pieces a thread copies per tap
+    static_assert(TM * C4 % THREADS == 0, "whole pieces per thread");
+    int nbn[CH];                               // neighbour ids of the NEXT gather, read one gather early (no dependent LDS in front of the copies)
+    auto load_nb = [&](int k) {
 #pragma unroll
-        for (int c = tid; c < SUBM_TM * C4; c += SUBM_THREADS) {
+        for (int i = 0; i < CH; ++i) nbn[i] = Ns[((tid + i * THREADS) / C4) * 9 + k];
+    };
+    auto gather = [&](int k, int buf) {
+        float *dst = As + (size_t)buf * TM * AS;
+#pragma unroll
+        for (int i = 0; i < CH; ++i) {
+            const int c = tid + i * THREADS;
             const int row = c / C4, col = c - row * C4;
-            const int nb = Ns[row * 9 + k];
             float *d = dst + row * AS + col * 4;
-            if (nb >= 0) cp_async16(d, q.in + (size_t)nb * CIN + col * 4);
+            if (nbn[i] >= 0) cp_async16(d, q.in + (size_t)nbn[i] * CIN + col * 4);
             else *reinterpret_cast<float4 *>(d) = make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        cp_commit();
+        if (k + 1 < 9) load_nb(k + 1);
     };
 
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const long long row0 = tile * SUBM_TM;
+        const long long row0 = tile * TM;
         __syncthreads();                       // the previous tile's buffers and rule-book slice are free; Ws is written
-        for (int i = tid; i < SUBM_TM * 9; i += SUBM_THREADS) {
+        for (int i = tid; i < TM * 9; i += THREADS) {
             const long long g = row0 * 9 + i;
             Ns[i] = (g < M * 9) ? q.nbr[g] : -1;
         }
         __syncthreads();
-        float acc[4][NCO];
+        uint64_t acc[PT][NP];
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < PT; ++i)
 #pragma unroll
-            for (int c = 0; c < NCO; ++c) acc[i][c] = 0.f;
+            for (int c = 0; c < NP; ++c) acc[i][c] = 0ull;       // (+0.f, +0.f)
 
-        gather(0, 0);
+        // NBUF-stage pipeline over the taps, one barrier per tap: the gather of tap k + NBUF - 1 is issued right after the
+        // barrier that proves every warp has finished tap k - 1, into the buffer tap k - 1 used
+        load_nb(0);
+#pragma unroll
+        for (int t = 0; t < NBUF - 1; ++t) { gather(t, t); cp_commit(); }
 #pragma unroll 1
         for (int k = 0; k < 9; ++k) {
-            if (k + 1 < 9) { gather(k + 1, (k + 1) & 1); cp_wait<1>(); } else cp_wait<0>();
-            __syncthreads();
-            const float *a0 = As + (size_t)(k & 1) * SUBM_TM * AS + (ty * 4) * AS;
+            cp_wait<NBUF - 2>();               // this thread's pieces of tap k have landed
+            __syncthreads();                   // ... and everybody's; tap k - 1 is done with its buffer
+            if (k + NBUF - 1 < 9) gather(k + NBUF - 1, (k + NBUF - 1) % NBUF);
+            cp_commit();                       // (an empty group at the end keeps the group count uniform)
+            const float *a0 = As + (size_t)(k % NBUF) * TM * AS + (ty * PT) * AS;
             const float *wk = Ws + (size_t)k * CIN * COUT + tx * NCO;
-#pragma unroll 2
+#pragma unroll UNR
             for (int c4 = 0; c4 < C4; ++c4) {
-                float4 a[4];
+                float4 a[PT];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) a[i] = *reinterpret_cast<const float4 *>(a0 + i * AS + c4 * 4);
+                for (int i = 0; i < PT; ++i) a[i] = *reinterpret_cast<const float4 *>(a0 + i * AS + c4 * 4);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    float w[NCO];
-                    if (NCO == 2) {
-                        const float2 t = *reinterpret_cast<const float2 *>(wk + (c4 * 4 + j) * COUT);
-                        w[0] = t.x; w[1] = t.y;
-                    } else {
-#pragma unroll
-                        for (int c = 0; c < NCO; c += 4) {
-                            const float4 t = *reinterpret_cast<const float4 *>(wk + (c4 * 4 + j) * COUT + c);
-                            w[c] = t.x; w[c + 1] = t.y; w[c + 2] = t.z; w[c + 3] = t.w;
-                        }
+                    uint64_t w[NP];
+                    if (NP == 1) w[0] = *reinterpret_cast<const uint64_t *>(wk + (c4 * 4 + j) * COUT);
+                    else {
+                        const ulonglong2 t = *reinterpret_cast<const ulonglong2 *>(wk + (c4 * 4 + j) * COUT);
+                        w[0] = t.x; w[NP - 1] = t.y;
                     }
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
+                    for (int i = 0; i < PT; ++i) {
                         const float av = (j == 0) ? a[i].x : (j == 1) ? a[i].y : (j == 2) ? a[i].z : a[i].w;
+                        const uint64_t a2 = pack_f2(av, av);
 #pragma unroll
-                        for (int c = 0; c < NCO; ++c) acc[i][c] = fmaf(av, w[c], acc[i][c]);
+                        for (int c = 0; c < NP; ++c) acc[i][c] = fma2_rn(a2, w[c], acc[i][c]);   // two fmaf, bit-identical
                     }
                 }
             }
-            __syncthreads();                   // buffer k & 1 is refilled by the gather of tap k + 2
         }
 
         // epilogue: bias, BatchNorm1d (eval), residual, ReLU
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const long long row = row0 + ty * 4 + i;
+        for (int i = 0; i < PT; ++i) {
+            const long long row = row0 + ty * PT + i;
             if (row >= M) continue;
             float v[NCO];
 #pragma unroll
+            for (int c = 0; c < NP; ++c) unpack_f2(acc[i][c], v[2 * c], v[2 * c + 1]);
+#pragma unroll
             for (int c = 0; c < NCO; ++c) {
-                float t = __fadd_rn(acc[i][c], bia[c]);
+                float t = __fadd_rn(v[c], bia[c]);
                 if (q.bn_w) t = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(t, bnm[c]), bni[c]), bnw[c]), bnb[c]);
                 v[c] = t;
             }
@@ -184,28 +210,25 @@ __global__ void __launch_bounds__(SUBM_THREADS) k_subm_conv(const SubmConvParams
                 for (int c = 0; c < NCO; ++c) v[c] = (v[c] > 0.f || v[c] != v[c]) ? v[c] : 0.f;   // NaN propagates like torch's ReLU
             }
             if (NCO == 2) *reinterpret_cast<float2 *>(q.out + o) = make_float2(v[0], v[1]);
-            else {
-#pragma unroll
-                for (int c = 0; c < NCO; c += 4) *reinterpret_cast<float4 *>(q.out + o + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
-            }
+            else *reinterpret_cast<float4 *>(q.out + o) = make_float4(v[0], v[1], v[NCO - 2], v[NCO - 1]);
         }
     }
 }
 
-template <int CIN, int COUT>
+template <int CIN, int COUT, int PT, int NCO, int TM, int NBUF>
 int launch_conv_t(const SubmConvParams &q, cudaStream_t stream) {
-    using S = SubmSmem<CIN, COUT>;
-    auto kern = k_subm_conv<CIN, COUT>;
+    using S = SubmCfg<CIN, COUT, PT, NCO, TM, NBUF>;
+    auto kern = k_subm_conv<CIN, COUT, PT, NCO, TM, NBUF>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::total);
     if (e != cudaSuccess) return (int)e;
     int dev = 0, sms = 0, per_sm = 0;
     if ((e = cudaGetDevice(&dev)) != cudaSuccess) return (int)e;
     if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return (int)e;
-    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, SUBM_THREADS, S::total)) != cudaSuccess) return (int)e;
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, S::THREADS, S::total)) != cudaSuccess) return (int)e;
     if (per_sm < 1) return HGSF_ERR_UNSUPPORTED;
-    const long long tiles = (q.M + SUBM_TM - 1) / SUBM_TM;
+    const long long tiles = (q.M + TM - 1) / TM;
     const long long grid = tiles < (long long)sms * per_sm ? tiles : (long long)sms * per_sm;
-    kern<<<(unsigned)grid, SUBM_THREADS, S::total, stream>>>(q);
+    kern<<<(unsigned)grid, S::THREADS, S::total, stream>>>(q);
     return (int)cudaGetLastError();
 }
 
@@ -222,9 +245,22 @@ int launch_subm_neighbors(const SubmNeighborParams &q, cudaStream_t stream) {
 
 int launch_subm_conv(const SubmConvParams &q, cudaStream_t stream) {
     if (q.M == 0) return HGSF_OK;
-    if (q.Cin == 32 && q.Cout == 32) return launch_conv_t<32, 32>(q, stream);
-    if (q.Cin == 64 && q.Cout == 64) return launch_conv_t<64, 64>(q, stream);
-    if (q.Cin == 32 && q.Cout == 64) return launch_conv_t<32, 64>(q, stream);
+    if (q.Cin == 32 && q.Cout == 32) {
+#ifdef HGSF_EXPERIMENT
+        const char *v = getenv("HGSF_SUBM_VARIANT");
+        const int var = v ? atoi(v) : 0;
+        if (var == 1) return launch_conv_t<32, 32, 8, 2, 128, 2>(q, stream);
+        if (var == 2) return launch_conv_t<32, 32, 8, 2, 128, 3>(q, stream);
+        if (var == 3) return launch_conv_t<32, 32, 4, 4, 64, 2>(q, stream);
+        if (var == 4) return launch_conv_t<32, 32, 4, 4, 64, 4>(q, stream);
+        if (var == 5) return launch_conv_t<32, 32, 4, 2, 64, 3>(q, stream);
+        if (var == 6) return launch_conv_t<32, 32, 8, 4, 128, 3>(q, stream);
+        if (var == 7) return launch_conv_t<32, 32, 4, 4, 32, 3>(q, stream);
+#endif
+        return launch_conv_t<32, 32, 4, 4, 64, 3>(q, stream);
+    }
+    if (q.Cin == 64 && q.Cout == 64) return launch_conv_t<64, 64, 4, 4, 64, 2>(q, stream);
+    if (q.Cin == 32 && q.Cout == 64) return launch_conv_t<32, 64, 4, 4, 64, 3>(q, stream);
     return HGSF_ERR_UNSUPPORTED;
 }
 

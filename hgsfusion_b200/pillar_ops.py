@@ -321,3 +321,127 @@ class DynamicPillarFeatureNet(nn.Module):
         xyz, cnt, feat = split_encode(points, self.pc_range, self.num_input, self.virtual, self.encoding_type, self.dataset,
                                       batch_size)
         return self.pfn_layers(xyz, cnt, feat)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# The pillar-list consumer: SpMiddlePillarEncoder18.conv1 on the reader's pillar list
+# ---------------------------------------------------------------------------------------------------------------
+
+@torch.no_grad()
+def subm_neighbors(pillar_bev_indices, pillars, num_rows_dev=None):
+    """The rule book of one `indice_key` for 3x3 submanifold convolutions: [M, 9] int32, entry ky*3+kx = pillar id at
+    (y+ky-1, x+kx-1) or -1.  pillar_bev_indices [B,H,W] and pillars [M,3] (b,y,x) come from gen_indice_pairs_flat /
+    PillarMaxPooling.  num_rows_dev: optional device int32 row count (capacity-sized `pillars`, no host sync)."""
+    _need_cuda(pillar_bev_indices, "pillar_bev_indices", torch.int32)
+    _need_cuda(pillars, "pillars", torch.int32)
+    B, H, W = (int(v) for v in pillar_bev_indices.shape)
+    M = int(pillars.shape[0])
+    nbr = torch.empty((M, 9), dtype=torch.int32, device=pillars.device)
+    st = _lib.load().hgsf_subm_neighbors(_p(pillar_bev_indices), _p(pillars), M, _p(num_rows_dev), B, H, W, _p(nbr), _s())
+    _lib.check(st, "hgsf_subm_neighbors")
+    return nbr
+
+
+@torch.no_grad()
+def subm_conv3x3(features, neighbors, weight, bias=None, bn=None, residual=None, relu=False, weight_layout="KRSC",
+                 num_rows_dev=None, out=None):
+    """act(BN(SubMConv2d_3x3(features)) + residual) on the pillar list (hgsf_subm_conv3x3).  weight [Cout,3,3,Cin]
+    ("KRSC", spconv 2.x) or [3,3,Cin,Cout] ("RSCK", spconv 1.x); bn = an eval-mode nn.BatchNorm1d or None."""
+    _need_cuda(features, "features", torch.float32)
+    _need_cuda(neighbors, "neighbors", torch.int32)
+    _need_cuda(weight, "weight", torch.float32)
+    if weight_layout not in ("KRSC", "RSCK") or weight.dim() != 4:
+        raise ValueError("weight must be [Cout,3,3,Cin] (KRSC) or [3,3,Cin,Cout] (RSCK)")
+    Cout, Cin = (int(weight.shape[0]), int(weight.shape[3])) if weight_layout == "KRSC" else (int(weight.shape[3]), int(weight.shape[2]))
+    M = int(features.shape[0])
+    if features.shape[1] != Cin or tuple(neighbors.shape) != (M, 9):
+        raise ValueError("features [M,Cin] and neighbors [M,9] expected")
+    if bn is not None and bn.training:
+        raise NotImplementedError("the pillar-list consumer is an inference path: BatchNorm must be in eval mode")
+    if residual is not None:
+        _need_cuda(residual, "residual", torch.float32)
+    if out is None:
+        out = torch.empty((M, Cout), dtype=torch.float32, device=features.device)
+    cv = _lib.SubmConv()
+    cv.weight = weight.data_ptr(); cv.weight_layout = 0 if weight_layout == "KRSC" else 1
+    cv.bias = bias.data_ptr() if bias is not None else None
+    if bn is not None:
+        cv.bn_weight, cv.bn_bias = bn.weight.data_ptr(), bn.bias.data_ptr()
+        cv.bn_mean, cv.bn_var, cv.bn_eps = bn.running_mean.data_ptr(), bn.running_var.data_ptr(), float(bn.eps)
+    cv.in_channels, cv.out_channels, cv.relu = Cin, Cout, int(bool(relu))
+    st = _lib.load().hgsf_subm_conv3x3(C.byref(cv), _p(features), _p(neighbors), M, _p(num_rows_dev), _p(residual), _p(out), _s())
+    _lib.check(st, "hgsf_subm_conv3x3")
+    return out
+
+
+class SubMConv2d(nn.Module):
+    """Parameter holder with spconv.SubMConv2d's names and spconv 2.x's weight layout [Cout, 3, 3, Cin] (kernel 3,
+    stride 1, padding 1: what conv2D3x3 builds, pcnres18.py:82-95), so a reference checkpoint's `*.weight` / `*.bias` load."""
+
+    def __init__(self, in_channels, out_channels, bias=True):
+        super().__init__()
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.weight = nn.Parameter(torch.empty(out_channels, 3, 3, in_channels))
+        nn.init.kaiming_uniform_(self.weight, a=5 ** 0.5)
+        self.bias = nn.Parameter(torch.zeros(out_channels)) if bias else None
+        if bias:
+            bound = 1.0 / (9 * in_channels) ** 0.5
+            nn.init.uniform_(self.bias, -bound, bound)
+        self._rsck = None
+
+    def rsck(self):
+        """The weight as [3, 3, Cin, Cout], the kernel's native layout (a straight copy into shared memory; the KRSC layout
+        is transposed on the fly by every CTA, ~8 % slower at config 2).  Cached until the parameter changes."""
+        key = (self.weight.data_ptr(), self.weight._version)
+        if self._rsck is None or self._rsck[0] != key:
+            self._rsck = (key, self.weight.detach().permute(1, 2, 3, 0).contiguous())
+        return self._rsck[1]
+
+
+def _conv_bn(inp, out):
+    return nn.Sequential(SubMConv2d(inp, out, bias=True), nn.BatchNorm1d(out, eps=1e-3, momentum=0.01))
+
+
+class Sparse2DBasicBlockV(nn.Module):
+    """pcnres18.py:108-151 with the same sub-module names (conv0.0 / conv0.1 ...); forward(features, neighbors) ->
+    features.  Three fused launches: conv0+BN+ReLU, conv1+BN+ReLU, conv2+BN+identity+ReLU."""
+
+    def __init__(self, inplanes, planes):
+        super().__init__()
+        self.conv0, self.conv1, self.conv2 = _conv_bn(inplanes, planes), _conv_bn(planes, planes), _conv_bn(planes, planes)
+
+    def forward(self, features, neighbors, num_rows_dev=None):
+        f = lambda seq, x, res: subm_conv3x3(x, neighbors, seq[0].rsck(), seq[0].bias, seq[1], residual=res, relu=True,
+                                             weight_layout="RSCK", num_rows_dev=num_rows_dev)
+        identity = f(self.conv0, features, None)
+        out = f(self.conv1, identity, None)
+        return f(self.conv2, out, identity)
+
+
+class Sparse2DBasicBlock(nn.Module):
+    """pcnres18.py:154-188; two fused launches."""
+
+    def __init__(self, inplanes, planes):
+        super().__init__()
+        self.conv1, self.conv2 = _conv_bn(planes, planes), _conv_bn(planes, planes)
+
+    def forward(self, features, neighbors, num_rows_dev=None):
+        f = lambda seq, x, res: subm_conv3x3(x, neighbors, seq[0].rsck(), seq[0].bias, seq[1], residual=res, relu=True,
+                                             weight_layout="RSCK", num_rows_dev=num_rows_dev)
+        return f(self.conv2, f(self.conv1, features, None), features)
+
+
+class PillarEncoderConv1(nn.Module):
+    """`SpMiddlePillarEncoder18.conv1` (pcnres18.py:212-215: Sparse2DBasicBlockV(32,32) + Sparse2DBasicBlock(32,32), indice
+    key "res1") on the pillar list: one rule-book launch + five fused convolution launches, no dense canvas.  The
+    sub-modules are named `0` and `1` like the reference's SparseSequential, so `conv1.*` checkpoint keys load."""
+
+    def __init__(self, planes=32):
+        super().__init__()
+        self.add_module("0", Sparse2DBasicBlockV(planes, planes))
+        self.add_module("1", Sparse2DBasicBlock(planes, planes))
+
+    def forward(self, pillar_features, pillars, pillar_bev_indices, num_rows_dev=None):
+        nbr = subm_neighbors(pillar_bev_indices, pillars, num_rows_dev)
+        x = getattr(self, "0")(pillar_features, nbr, num_rows_dev)
+        return getattr(self, "1")(x, nbr, num_rows_dev)

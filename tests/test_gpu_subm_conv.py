@@ -1,0 +1,177 @@
+"""GPU parity of the pillar-list consumer: hgsf_subm_neighbors / hgsf_subm_conv3x3 and the
+SpMiddlePillarEncoder18.conv1 mirror against the numpy oracle (itself pinned against torch's dense conv2d on the active set,
+tests/test_pathb_oracle.py), and at full size against cuDNN's dense fp32 convolution on the same GPU.
+
+Tolerance: 1e-5 of the largest output (fp32; the summation order of a 288-term dot product differs between
+implementations)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from hgsfusion_b200 import _lib, pillar_ops as po
+from oracle import pathb_oracle as pb
+from test_pathb_oracle import _random_pillars
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+def _close(got, ref):
+    return np.abs(got - ref).max() <= TOL * max(1.0, np.abs(ref).max())
+
+
+def _bn(rng, Cc, dev):
+    bn = torch.nn.BatchNorm1d(Cc, eps=1e-3, momentum=0.01).to(dev).eval()
+    with torch.no_grad():
+        bn.weight.copy_(torch.from_numpy(rng.uniform(0.5, 1.5, Cc).astype(np.float32)))
+        bn.bias.copy_(torch.from_numpy(rng.normal(0, 0.5, Cc).astype(np.float32)))
+        bn.running_mean.copy_(torch.from_numpy(rng.normal(0, 1, Cc).astype(np.float32)))
+        bn.running_var.copy_(torch.from_numpy(rng.uniform(0.5, 2, Cc).astype(np.float32)))
+    return bn
+
+
+def _bn_np(bn):
+    return tuple(t.detach().cpu().numpy() for t in (bn.weight, bn.bias, bn.running_mean, bn.running_var))
+
+
+@pytest.mark.parametrize("B,H,W,M_per", [(2, 40, 40, 500), (3, 17, 33, 561), (1, 1, 1, 1), (2, 64, 64, 70)])
+def test_neighbors_bit_exact(cuda, B, H, W, M_per):
+    rng = np.random.default_rng(B * 100 + H)
+    pillars, bev = _random_pillars(rng, B, H, W, M_per)
+    got = po.subm_neighbors(torch.from_numpy(bev).to(cuda), torch.from_numpy(pillars).to(cuda))
+    assert np.array_equal(got.cpu().numpy(), pb.subm_neighbors(bev, pillars))
+
+
+@pytest.mark.parametrize("Cin,Cout", [(32, 32), (64, 64), (32, 64)])
+@pytest.mark.parametrize("layout", ["KRSC", "RSCK"])
+@pytest.mark.parametrize("opts", [dict(), dict(bias=True), dict(bias=True, bn=True, relu=True), dict(bias=True, bn=True, res=True, relu=True)])
+def test_conv_matches_oracle(cuda, Cin, Cout, layout, opts):
+    rng = np.random.default_rng(Cin * 7 + Cout + len(opts))
+    pillars, bev = _random_pillars(rng, 2, 37, 29, 333)       # M = 666: ragged last tile
+    M = pillars.shape[0]
+    feats = rng.normal(size=(M, Cin)).astype(np.float32)
+    w = (rng.normal(size=(Cout, 3, 3, Cin)) * 0.1).astype(np.float32)
+    bias = rng.normal(size=Cout).astype(np.float32) if opts.get("bias") else None
+    bn = _bn(rng, Cout, cuda) if opts.get("bn") else None
+    res = rng.normal(size=(M, Cout)).astype(np.float32) if opts.get("res") else None
+    nbr = pb.subm_neighbors(bev, pillars)
+    ref = pb.subm_conv3x3(feats, nbr, w, bias=bias, bn=_bn_np(bn) if bn else None, residual=res, relu=bool(opts.get("relu")))
+    wt = torch.from_numpy(w if layout == "KRSC" else np.ascontiguousarray(w.transpose(1, 2, 3, 0))).to(cuda)
+    got = po.subm_conv3x3(torch.from_numpy(feats).to(cuda), torch.from_numpy(nbr).to(cuda), wt,
+                          bias=None if bias is None else torch.from_numpy(bias).to(cuda), bn=bn,
+                          residual=None if res is None else torch.from_numpy(res).to(cuda), relu=bool(opts.get("relu")),
+                          weight_layout=layout)
+    assert _close(got.cpu().numpy(), ref)
+
+
+def test_isolated_pillars_and_empty(cuda):
+    """A pillar without neighbours sees only its centre tap; M = 0 launches nothing."""
+    rng = np.random.default_rng(5)
+    pillars = np.array([[0, 0, 0], [0, 5, 5], [1, 9, 9]], dtype=np.int32)
+    bev = np.full((2, 10, 10), -1, dtype=np.int32)
+    bev[pillars[:, 0], pillars[:, 1], pillars[:, 2]] = np.arange(3)
+    feats = rng.normal(size=(3, 32)).astype(np.float32)
+    w = rng.normal(size=(32, 3, 3, 32)).astype(np.float32)
+    nbr = po.subm_neighbors(torch.from_numpy(bev).to(cuda), torch.from_numpy(pillars).to(cuda))
+    got = po.subm_conv3x3(torch.from_numpy(feats).to(cuda), nbr, torch.from_numpy(w).to(cuda)).cpu().numpy()
+    assert _close(got, feats @ w[:, 1, 1, :].T)
+    e = po.subm_conv3x3(torch.zeros((0, 32), device=cuda), torch.zeros((0, 9), dtype=torch.int32, device=cuda), torch.from_numpy(w).to(cuda))
+    assert e.shape == (0, 32) and _lib.load().hgsf_last_launch_count() == 0
+
+
+def test_device_row_count_leaves_the_tail_untouched(cuda):
+    rng = np.random.default_rng(6)
+    pillars, bev = _random_pillars(rng, 2, 20, 20, 100)
+    M = pillars.shape[0]
+    cap = M + 77
+    pad = np.zeros((cap, 3), dtype=np.int32); pad[:M] = pillars; pad[M:] = -7          # garbage rows past the count
+    feats = rng.normal(size=(cap, 32)).astype(np.float32)
+    w = (rng.normal(size=(32, 3, 3, 32)) * 0.1).astype(np.float32)
+    m_dev = torch.tensor([M], dtype=torch.int32, device=cuda)
+    nbr = torch.full((cap, 9), -5, dtype=torch.int32, device=cuda)
+    lib = _lib.load()
+    bev_t, pad_t = torch.from_numpy(bev).to(cuda), torch.from_numpy(pad).to(cuda)
+    st = lib.hgsf_subm_neighbors(C.c_void_p(bev_t.data_ptr()), C.c_void_p(pad_t.data_ptr()), cap, C.c_void_p(m_dev.data_ptr()), 2, 20, 20, C.c_void_p(nbr.data_ptr()), po._s())
+    assert st == 0
+    assert np.array_equal(nbr[:M].cpu().numpy(), pb.subm_neighbors(bev, pillars)) and (nbr[M:] == -5).all()
+    out = torch.full((cap, 32), 123.0, device=cuda)
+    po.subm_conv3x3(torch.from_numpy(feats).to(cuda), nbr, torch.from_numpy(w).to(cuda), num_rows_dev=m_dev, out=out)
+    assert _close(out[:M].cpu().numpy(), pb.subm_conv3x3(feats[:M], pb.subm_neighbors(bev, pillars), w)) and (out[M:] == 123.0).all()
+
+
+def _conv1_oracle(enc, feats, nbr):
+    """Sparse2DBasicBlockV.forward + Sparse2DBasicBlock.forward (pcnres18.py:139-151,176-187) composed from the oracle's convolution."""
+    def cb(seq, x, res):
+        return pb.subm_conv3x3(x, nbr, seq[0].weight.detach().cpu().numpy(), bias=seq[0].bias.detach().cpu().numpy(), bn=_bn_np(seq[1]),
+                               residual=res, relu=True)
+    b0, b1 = getattr(enc, "0"), getattr(enc, "1")
+    identity = cb(b0.conv0, feats, None)
+    x = cb(b0.conv2, cb(b0.conv1, identity, None), identity)
+    return cb(b1.conv2, cb(b1.conv1, x, None), x)
+
+
+def test_encoder_conv1_on_the_reader_output(cuda):
+    """points -> hgsf_pillarnet_indices -> (random reader features) -> conv1 stage, against the oracle's composition."""
+    from test_gpu_pillarnet import make_points
+    rng = np.random.default_rng(11)
+    xyz, cnt = make_points(2, 3000, seed=4)
+    r = po.gen_indice_pairs_flat(torch.from_numpy(xyz).to(cuda), torch.from_numpy(cnt).to(cuda), 0.16, (320, 320))
+    pillars, bev = r["pillars"], r["pillar_bev_indices"]
+    M = int(pillars.shape[0])
+    feats = np.abs(rng.normal(size=(M, 32))).astype(np.float32)
+    torch.manual_seed(0)
+    enc = po.PillarEncoderConv1(32).to(cuda).eval()
+    for m in enc.modules():
+        if isinstance(m, torch.nn.BatchNorm1d):
+            src = _bn(rng, 32, cuda)
+            m.load_state_dict(src.state_dict())
+    keys = set(enc.state_dict().keys())
+    assert {"0.conv0.0.weight", "0.conv0.0.bias", "0.conv0.1.running_var", "0.conv2.1.weight", "1.conv1.0.weight", "1.conv2.1.bias"} <= keys
+    got = enc(torch.from_numpy(feats).to(cuda), pillars, bev).cpu().numpy()
+    ref = _conv1_oracle(enc, feats, pb.subm_neighbors(bev.cpu().numpy(), pillars.cpu().numpy()))
+    assert got.shape == (M, 32) and _close(got, ref)
+
+
+def test_full_size_against_cudnn_dense_fp32(cuda):
+    """Config-2 size (16 frames, ~11k pillars each): the kernel against cuDNN's dense fp32 convolution (TF32 off) of the
+    densified input, sampled at the active cells, on the same GPU."""
+    import torch.nn.functional as F
+    rng = np.random.default_rng(21)
+    B, H, W = 16, 320, 320
+    pillars, bev = _random_pillars(rng, B, H, W, 11400)
+    pillars_t, bev_t = torch.from_numpy(pillars).to(cuda), torch.from_numpy(bev).to(cuda)
+    M = pillars.shape[0]
+    feats = torch.from_numpy(rng.normal(size=(M, 32)).astype(np.float32)).to(cuda)
+    w = torch.from_numpy((rng.normal(size=(32, 3, 3, 32)) * 0.1).astype(np.float32)).to(cuda)
+    bias = torch.from_numpy(rng.normal(size=32).astype(np.float32)).to(cuda)
+    got = po.subm_conv3x3(feats, po.subm_neighbors(bev_t, pillars_t), w, bias=bias)
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        dense = po.sparse_to_dense(feats, pillars_t, (H, W), B)
+        ref = F.conv2d(dense, w.permute(0, 3, 1, 2).contiguous(), bias, padding=1)
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    idx = pillars_t.long()
+    ref = ref[idx[:, 0], :, idx[:, 1], idx[:, 2]]
+    assert (got - ref).abs().max().item() <= TOL * max(1.0, ref.abs().max().item())
+
+
+def test_invalid_arguments(cuda):
+    lib = _lib.load()
+    cv = _lib.SubmConv()
+    w = torch.zeros((48, 3, 3, 48), device=cuda)
+    f = torch.zeros((4, 48), device=cuda)
+    n = torch.zeros((4, 9), dtype=torch.int32, device=cuda)
+    o = torch.zeros((4, 48), device=cuda)
+    cv.weight, cv.in_channels, cv.out_channels = w.data_ptr(), 48, 48
+    args = lambda feat, out: (C.byref(cv), C.c_void_p(feat.data_ptr()), C.c_void_p(n.data_ptr()), 4, None, None, C.c_void_p(out.data_ptr()), po._s())
+    assert lib.hgsf_subm_conv3x3(*args(f, o)) == _lib.ERR_UNSUPPORTED          # 48 channels: outside the compiled set
+    cv.in_channels = cv.out_channels = 32
+    assert lib.hgsf_subm_conv3x3(*args(f, f)) == _lib.ERR_INVALID_ARG          # in-place
+    cv.bn_weight = w.data_ptr()
+    assert lib.hgsf_subm_conv3x3(*args(f, o)) == _lib.ERR_INVALID_ARG          # BatchNorm pointers: all or none
+    with pytest.raises(ValueError):
+        po.subm_conv3x3(f.cpu(), n, w)                                         # no CPU path

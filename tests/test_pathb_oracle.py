@@ -104,3 +104,48 @@ def test_split_encode_hand_case():
     assert feat[0, 3:15].tolist() == list(range(100, 112)) and not feat[0, 15:27].any() and feat[0, 27:].tolist() == [1, 1]
     assert feat[1, 15:27].tolist() == list(range(100, 112)) and not feat[1, 3:15].any() and feat[1, 27:].tolist() == [0, 1]
     assert feat[2, 15:27].tolist() == list(range(100, 112)) and feat[2, 27:].tolist() == [0, 0]
+
+
+# ---- pillar-list consumer: the oracle's submanifold 3x3 convolution against torch's dense conv2d ----
+
+def _random_pillars(rng, B, H, W, M_per):
+    pillars = []
+    bev = np.full((B, H, W), -1, dtype=np.int32)
+    for b in range(B):
+        cells = np.sort(rng.choice(H * W, size=min(M_per, H * W), replace=False))       # raster order like the reader
+        for c in cells:
+            bev[b, c // W, c % W] = len(pillars)
+            pillars.append((b, c // W, c % W))
+    return np.asarray(pillars, dtype=np.int32).reshape(-1, 3), bev
+
+
+@pytest.mark.parametrize("Cin,Cout,H,W", [(32, 32, 12, 9), (8, 16, 5, 5), (32, 64, 3, 20)])
+def test_subm_conv_oracle_matches_dense_conv2d_on_the_active_set(Cin, Cout, H, W):
+    import torch
+    import torch.nn.functional as F
+    rng = np.random.default_rng(Cin + Cout)
+    pillars, bev = _random_pillars(rng, 2, H, W, H * W // 3)
+    M = pillars.shape[0]
+    feats = rng.normal(size=(M, Cin)).astype(np.float32)
+    w = rng.normal(size=(Cout, 3, 3, Cin)).astype(np.float32) * 0.1
+    bias = rng.normal(size=Cout).astype(np.float32)
+    nbr = pb.subm_neighbors(bev, pillars)
+    assert (nbr[:, 4] == np.arange(M)).all()                      # the centre tap is the pillar itself
+    got = pb.subm_conv3x3(feats, nbr, w, bias=bias)
+    dense = torch.zeros(2, Cin, H, W)
+    dense[pillars[:, 0], :, pillars[:, 1], pillars[:, 2]] = torch.from_numpy(feats)
+    ref = F.conv2d(dense, torch.from_numpy(w).permute(0, 3, 1, 2).contiguous(), torch.from_numpy(bias), padding=1)
+    ref = ref[pillars[:, 0], :, pillars[:, 1], pillars[:, 2]].numpy()
+    assert np.abs(got - ref).max() <= 1e-5 * max(1.0, np.abs(ref).max())
+
+
+def test_subm_neighbors_edges_and_frames():
+    bev = np.full((2, 2, 3), -1, dtype=np.int32)
+    pillars = np.array([[0, 0, 0], [0, 0, 1], [0, 1, 2], [1, 0, 0]], dtype=np.int32)
+    for i, (b, y, x) in enumerate(pillars):
+        bev[b, y, x] = i
+    nbr = pb.subm_neighbors(bev, pillars)
+    assert nbr[0].tolist() == [-1, -1, -1, -1, 0, 1, -1, -1, -1]
+    assert nbr[1].tolist() == [-1, -1, -1, 0, 1, -1, -1, -1, 2]
+    assert nbr[2].tolist() == [1, -1, -1, -1, 2, -1, -1, -1, -1]
+    assert nbr[3].tolist() == [-1, -1, -1, -1, 3, -1, -1, -1, -1]    # other frames are not neighbours
