@@ -22,7 +22,8 @@ EXPORTS = ["hgsf_abi_version", "hgsf_status_string", "hgsf_pillar_capacity", "hg
            "hgsf_train_stats_doubles", "hgsf_train_scratch_doubles", "hgsf_pillar_vfe_batch_stats",
            "hgsf_pillar_vfe_backward", "hgsf_pointpillar_scatter_backward", "hgsf_hybrid_workspace_size",
            "hgsf_assemble_hybrid_points", "hgsf_sparse_to_dense_workspace_size", "hgsf_sparse_to_dense",
-           "hgsf_subm_neighbors", "hgsf_subm_conv3x3"]
+           "hgsf_subm_neighbors", "hgsf_subm_conv3x3", "hgsf_sparse_conv_s2_workspace_size",
+           "hgsf_sparse_conv_s2_indices"]
 
 
 class Geometry(C.Structure):
@@ -129,6 +130,10 @@ def load():
                                         C.c_void_p]
     lib.hgsf_subm_conv3x3.argtypes = [C.POINTER(SubmConv), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_void_p]
+    lib.hgsf_sparse_conv_s2_workspace_size.argtypes = [C.c_int64, C.c_int32, C.POINTER(C.c_size_t)]
+    lib.hgsf_sparse_conv_s2_indices.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_size_t,
+                                                C.c_void_p]
     lib.hgsf_emit_timing_begin.argtypes = [C.c_int]
     lib.hgsf_emit_timing_collect.argtypes = [C.POINTER(C.c_float), C.c_int]
     for name in EXPORTS:

@@ -411,7 +411,7 @@ int hgsf_subm_neighbors(const int32_t *bev, const int32_t *pillars, int64_t M, c
     if (M > 0 && (!bev || !pillars || !nbr)) return HGSF_ERR_INVALID_ARG;
     if ((int64_t)B * H * W > INT_MAX || M > INT_MAX / 9) return HGSF_ERR_UNSUPPORTED;
     SubmNeighborParams q{};
-    q.bev = bev; q.pillars = pillars; q.m_dev = m_dev; q.M = M; q.B = B; q.H = H; q.W = W; q.nbr = nbr;
+    q.bev = bev; q.pillars = pillars; q.m_dev = m_dev; q.M = M; q.B = B; q.H = H; q.W = W; q.stride = 1; q.nbr = nbr;
     const int st = launch_subm_neighbors(q, static_cast<cudaStream_t>(stream));
     if (st == HGSF_OK && M > 0) g_last_launches = 1;
     return st;
@@ -434,6 +434,57 @@ int hgsf_subm_conv3x3(const hgsf_subm_conv *conv, const float *features, const i
     q.residual = residual; q.relu = conv->relu; q.out = out;
     const int st = launch_subm_conv(q, static_cast<cudaStream_t>(stream));
     if (st == HGSF_OK && M > 0) g_last_launches = 1;
+    return st;
+}
+
+int hgsf_sparse_conv_s2_workspace_size(int64_t M, int32_t B, size_t *bytes) {
+    if (!bytes || M < 0 || B <= 0) return HGSF_ERR_INVALID_ARG;
+    size_t pn = 0;
+    hgsf_pillarnet_workspace_size(4 * M, &pn);
+    *bytes = align_up(sizeof(float) * 12 * (size_t)M, 256) + align_up(sizeof(int) * (size_t)B, 256) +
+             2 * align_up(sizeof(int) * 4 * (size_t)M, 256) + align_up(pn, 256);
+    return HGSF_OK;
+}
+
+int hgsf_sparse_conv_s2_indices(const int32_t *bev, const int32_t *pillars, int64_t M, const int32_t *m_dev, int32_t B, int32_t H,
+                                int32_t W, int32_t *out_bev, int32_t *out_pillars, int32_t *out_counts, int32_t *nbr,
+                                int64_t out_capacity, void *ws, size_t ws_bytes, hgsf_stream_t stream) {
+    g_last_launches = 0;
+    if (M < 0 || B <= 0 || H <= 0 || W <= 0 || !out_bev || !out_counts || !ws || out_capacity < 0) return HGSF_ERR_INVALID_ARG;
+    if (M > 0 && (!bev || !pillars || !out_pillars || !nbr)) return HGSF_ERR_INVALID_ARG;
+    const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+    const int64_t cells_o = (int64_t)B * Ho * Wo;
+    if ((int64_t)B * H * W > INT_MAX || 4 * M > INT_MAX / 9 || B > 1024) return HGSF_ERR_UNSUPPORTED;
+    if (out_capacity < (4 * M < cells_o ? 4 * M : cells_o)) return HGSF_ERR_INVALID_ARG;
+    size_t need = 0;
+    hgsf_sparse_conv_s2_workspace_size(M, B, &need);
+    if (ws_bytes < need || (reinterpret_cast<uintptr_t>(ws) & 255)) return HGSF_ERR_WORKSPACE;
+    uint8_t *w = static_cast<uint8_t *>(ws);
+    float *cand = reinterpret_cast<float *>(w);            w += align_up(sizeof(float) * 12 * (size_t)M, 256);
+    int *cnt = reinterpret_cast<int *>(w);                 w += align_up(sizeof(int) * (size_t)B, 256);
+    int *point_idx = reinterpret_cast<int *>(w);           w += align_up(sizeof(int) * 4 * (size_t)M, 256);
+    int *pillar_idx = reinterpret_cast<int *>(w);          w += align_up(sizeof(int) * 4 * (size_t)M, 256);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    cudaError_t e = cudaMemsetAsync(cnt, 0, sizeof(int) * (size_t)B, s);
+    if (e != cudaSuccess) return (int)e;
+    Stride2CandidateParams c{};
+    c.pillars = pillars; c.m_dev = m_dev; c.M = M; c.B = B; c.Ho = Ho; c.Wo = Wo; c.cand = cand; c.cnt = cnt;
+    int st = launch_stride2_candidates(c, s);
+    if (st != HGSF_OK) return st;
+    PillarNetParams q{};
+    q.xyz = cand; q.cnt = cnt; q.N = 4 * M; q.B = B; q.H = Ho; q.W = Wo; q.bev_size = 1.f;
+    q.bev = out_bev; q.pillars = out_pillars; q.pairs = nullptr; q.point_idx = point_idx; q.pillar_idx = pillar_idx;
+    q.counts = out_counts;
+    q.key = reinterpret_cast<int *>(w);
+    q.partial = reinterpret_cast<uint32_t *>(w + align_up(sizeof(int) * 4 * (size_t)M, 256));
+    st = launch_pillarnet_indices(q, s);
+    if (st != HGSF_OK) return st;
+    g_last_launches = M > 0 ? 2 : 1;
+    if (out_capacity == 0) return HGSF_OK;
+    SubmNeighborParams n{};
+    n.bev = bev; n.pillars = out_pillars; n.m_dev = out_counts; n.M = out_capacity; n.B = B; n.H = H; n.W = W; n.stride = 2; n.nbr = nbr;
+    st = launch_subm_neighbors(n, s);
+    if (st == HGSF_OK) g_last_launches += 1;
     return st;
 }
 

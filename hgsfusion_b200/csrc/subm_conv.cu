@@ -46,10 +46,42 @@ __global__ void __launch_bounds__(256) k_subm_neighbors(const SubmNeighborParams
         const long long m = i / 9;
         const int k = (int)(i - m * 9);
         const int b = q.pillars[m * 3], y = q.pillars[m * 3 + 1], x = q.pillars[m * 3 + 2];
-        const int yy = y + k / 3 - 1, xx = x + k % 3 - 1;
+        const int yy = y * q.stride + k / 3 - 1, xx = x * q.stride + k % 3 - 1;
         int v = -1;
         if (b >= 0 && b < q.B && yy >= 0 && yy < q.H && xx >= 0 && xx < q.W) v = q.bev[((long long)b * q.H + yy) * q.W + xx];
         q.nbr[i] = v;
+    }
+}
+
+// SparseConv2d(kernel 3, stride 2, padding 1): output cell (yo, xo) is active iff an input pillar lies in rows 2yo-1 .. 2yo+1 and
+// columns 2xo-1 .. 2xo+1, i.e. an input pillar at an even coordinate reaches one output coordinate (y / 2) and at an odd one two
+// ((y - 1) / 2 and (y + 1) / 2).  Every input pillar emits the centres of the (up to four) output cells it reaches as candidate
+// "points"; hgsf_pillarnet_indices' machinery then turns them into the raster-ordered output pillar list and its cell table.
+__global__ void __launch_bounds__(256) k_stride2_candidates(const Stride2CandidateParams q) {
+    const long long M = q.m_dev ? min((long long)max(q.m_dev[0], 0), q.M) : q.M;
+    const long long m_pad = (q.M + 31) & ~31ll;
+    for (long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x; m < m_pad; m += (long long)gridDim.x * blockDim.x) {
+        const bool live = m < M;
+        int b = -1, y = 0, x = 0;
+        if (live) { b = q.pillars[m * 3]; y = q.pillars[m * 3 + 1]; x = q.pillars[m * 3 + 2]; }
+        const bool ok = live && b >= 0 && b < q.B && y >= 0 && x >= 0;
+        if (m < q.M) {
+            const int y0 = (y & 1) ? (y - 1) / 2 : y / 2, x0 = (x & 1) ? (x - 1) / 2 : x / 2;
+            const int y1 = (y & 1) ? (y + 1) / 2 : -1, x1 = (x & 1) ? (x + 1) / 2 : -1;
+            const int ys[2] = {y0, y1}, xs[2] = {x0, x1};
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+                const int yo = ys[s >> 1], xo = xs[s & 1];
+                const bool v = ok && yo >= 0 && yo < q.Ho && xo >= 0 && xo < q.Wo;
+                float *c = q.cand + (m * 4 + s) * 3;
+                c[0] = v ? (float)xo + 0.5f : -10.f;
+                c[1] = v ? (float)yo + 0.5f : -10.f;
+                c[2] = 0.f;
+            }
+        }
+        // 4 candidate slots per pillar of frame b: one atomic per distinct frame in the warp
+        const unsigned peers = __match_any_sync(FULL, ok ? b : -1);
+        if (ok && (threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(q.cnt + b, 4 * __popc(peers));
     }
 }
 
@@ -240,6 +272,14 @@ int launch_subm_neighbors(const SubmNeighborParams &q, cudaStream_t stream) {
     long long grid = (total + 255) / 256;
     if (grid > 148 * 16) grid = 148 * 16;
     k_subm_neighbors<<<(unsigned)grid, 256, 0, stream>>>(q);
+    return (int)cudaGetLastError();
+}
+
+int launch_stride2_candidates(const Stride2CandidateParams &q, cudaStream_t stream) {
+    if (q.M == 0) return HGSF_OK;
+    long long grid = (q.M + 255) / 256;
+    if (grid > 148 * 8) grid = 148 * 8;
+    k_stride2_candidates<<<(unsigned)grid, 256, 0, stream>>>(q);
     return (int)cudaGetLastError();
 }
 

@@ -11,8 +11,18 @@ struct SubmNeighborParams {
     const int *pillars;      // [M, 3] (b, y, x)
     const int *m_dev;        // optional device row count (counts[0] of hgsf_pillarnet_indices); null = M
     long long M;
-    int B, H, W;
-    int *nbr;                // [M, 9] pillar id at (y + ky - 1, x + kx - 1), tap = ky * 3 + kx; -1 none
+    int B, H, W;             // of the INPUT table
+    int stride;              // 1: submanifold (pillars = the input's own); 2: pillars = the output cells of a stride-2 convolution
+    int *nbr;                // [M, 9] input pillar id at (y * stride + ky - 1, x * stride + kx - 1), tap = ky * 3 + kx; -1 none
+};
+
+struct Stride2CandidateParams {
+    const int *pillars;      // [M, 3] (b, y, x) of the input, frames contiguous
+    const int *m_dev;
+    long long M;
+    int B, Ho, Wo;
+    float *cand;             // [4 M, 3] centres of the output cells each input pillar reaches, (-10, -10) for unused slots
+    int *cnt;                // [B] zeroed; receives 4 x pillars per frame (xyz_batch_cnt of the candidates)
 };
 
 struct SubmConvParams {
@@ -33,5 +43,6 @@ struct SubmConvParams {
 
 int launch_subm_neighbors(const SubmNeighborParams &q, cudaStream_t stream);
 int launch_subm_conv(const SubmConvParams &q, cudaStream_t stream);
+int launch_stride2_candidates(const Stride2CandidateParams &q, cudaStream_t stream);
 
 }  // namespace hgsf

@@ -353,9 +353,9 @@ def subm_conv3x3(features, neighbors, weight, bias=None, bn=None, residual=None,
     if weight_layout not in ("KRSC", "RSCK") or weight.dim() != 4:
         raise ValueError("weight must be [Cout,3,3,Cin] (KRSC) or [3,3,Cin,Cout] (RSCK)")
     Cout, Cin = (int(weight.shape[0]), int(weight.shape[3])) if weight_layout == "KRSC" else (int(weight.shape[3]), int(weight.shape[2]))
-    M = int(features.shape[0])
-    if features.shape[1] != Cin or tuple(neighbors.shape) != (M, 9):
-        raise ValueError("features [M,Cin] and neighbors [M,9] expected")
+    M = int(neighbors.shape[0])          # output rows; a stride-2 rule book (sparse_conv_s2_indices) has its own row count
+    if features.dim() != 2 or features.shape[1] != Cin or neighbors.dim() != 2 or neighbors.shape[1] != 9:
+        raise ValueError("features [M_in,Cin] and neighbors [M_out,9] expected")
     if bn is not None and bn.training:
         raise NotImplementedError("the pillar-list consumer is an inference path: BatchNorm must be in eval mode")
     if residual is not None:
@@ -445,3 +445,63 @@ class PillarEncoderConv1(nn.Module):
         nbr = subm_neighbors(pillar_bev_indices, pillars, num_rows_dev)
         x = getattr(self, "0")(pillar_features, nbr, num_rows_dev)
         return getattr(self, "1")(x, nbr, num_rows_dev)
+
+
+@torch.no_grad()
+def sparse_conv_s2_indices(pillar_bev_indices, pillars, num_rows_dev=None, sync=True):
+    """Indices of `SparseConv2d(kernel 3, stride 2, padding 1)` (the first layer of conv2 / conv3 / conv4, pcnres18.py:217-221)
+    from the input's cell table and pillar list: dict(pillars [Mo,3] raster order, pillar_bev_indices [B,Ho,Wo], neighbors [Mo,9]
+    (input pillar ids), counts).  `sync=True` reads Mo once to slice; `sync=False` leaves the outputs capacity-sized."""
+    _need_cuda(pillar_bev_indices, "pillar_bev_indices", torch.int32)
+    _need_cuda(pillars, "pillars", torch.int32)
+    B, H, W = (int(v) for v in pillar_bev_indices.shape)
+    M = int(pillars.shape[0])
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    dev = pillars.device
+    cap = min(4 * M, B * Ho * Wo)
+    lib = _lib.load()
+    need = C.c_size_t(0)
+    _lib.check(lib.hgsf_sparse_conv_s2_workspace_size(M, B, C.byref(need)), "hgsf_sparse_conv_s2_workspace_size")
+    ws = torch.empty(need.value + 256, dtype=torch.uint8, device=dev)
+    ws_ptr = (ws.data_ptr() + 255) // 256 * 256
+    out_bev = torch.empty((B, Ho, Wo), dtype=torch.int32, device=dev)
+    out_pillars = torch.empty((cap, 3), dtype=torch.int32, device=dev)
+    nbr = torch.empty((cap, 9), dtype=torch.int32, device=dev)
+    counts = torch.empty((2,), dtype=torch.int32, device=dev)
+    st = lib.hgsf_sparse_conv_s2_indices(_p(pillar_bev_indices), _p(pillars), M, _p(num_rows_dev), B, H, W, _p(out_bev), _p(out_pillars),
+                                         _p(counts), _p(nbr), cap, C.c_void_p(ws_ptr), need.value, _s())
+    _lib.check(st, "hgsf_sparse_conv_s2_indices")
+    if sync:
+        Mo = int(counts[0].item())
+        out_pillars, nbr = out_pillars[:Mo], nbr[:Mo]
+    return dict(pillars=out_pillars, pillar_bev_indices=out_bev, neighbors=nbr, counts=counts)
+
+
+class SparseConv2d(SubMConv2d):
+    """Parameter holder for spconv.SparseConv2d(in, out, 3, 2, padding=1, bias=False) (pcnres18.py:218-220), weight [Cout,3,3,Cin]."""
+
+    def __init__(self, in_channels, out_channels, bias=False):
+        super().__init__(in_channels, out_channels, bias=bias)
+
+
+class PillarEncoderConv2(nn.Module):
+    """`SpMiddlePillarEncoder18.conv2` (pcnres18.py:217-225): SparseConv2d(32, 64, 3, 2, padding 1) + BatchNorm1d + ReLU, then two
+    Sparse2DBasicBlock(64, 64) on the down-sampled active set (indice key "res2").  Sub-modules `0` .. `4` like the reference's
+    SparseSequential (`2` is the parameter-free ReLU).  forward -> (features [Mo,64], pillars [Mo,3], pillar_bev_indices [B,Ho,Wo])."""
+
+    def __init__(self, inplanes=32, planes=64):
+        super().__init__()
+        self.add_module("0", SparseConv2d(inplanes, planes))
+        self.add_module("1", nn.BatchNorm1d(planes, eps=1e-3, momentum=0.01))
+        self.add_module("2", nn.ReLU())
+        self.add_module("3", Sparse2DBasicBlock(planes, planes))
+        self.add_module("4", Sparse2DBasicBlock(planes, planes))
+
+    def forward(self, features, pillars, pillar_bev_indices):
+        r = sparse_conv_s2_indices(pillar_bev_indices, pillars)
+        conv, bn = getattr(self, "0"), getattr(self, "1")
+        x = subm_conv3x3(features, r["neighbors"], conv.rsck(), conv.bias, bn, relu=True, weight_layout="RSCK")
+        nbr = subm_neighbors(r["pillar_bev_indices"], r["pillars"])
+        x = getattr(self, "3")(x, nbr)
+        x = getattr(self, "4")(x, nbr)
+        return x, r["pillars"], r["pillar_bev_indices"]

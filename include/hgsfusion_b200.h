@@ -368,6 +368,21 @@ HGSF_API int hgsf_subm_conv3x3(const hgsf_subm_conv *conv, const float *features
                                int64_t num_rows, const int32_t *num_rows_dev, const float *residual, float *out,
                                hgsf_stream_t stream);
 
+/* The indices of SparseConv2d(kernel 3, stride 2, padding 1) -- the first layer of SpMiddlePillarEncoder18.conv2 / conv3 /
+ * conv4 (pcnres18.py:217-221): the output active set (a cell (yo, xo) of the [Ho, Wo] = [(H-1)/2+1, (W-1)/2+1] grid is
+ * active iff an input pillar lies in rows 2yo-1..2yo+1, columns 2xo-1..2xo+1), as out_pillars [Mo, 3] (b, y, x) in raster
+ * order with its cell table out_bev [B, Ho, Wo] (-1 none) -- spconv's own output order is an implementation detail of its
+ * hash table; raster order is what hgsf_pillarnet_indices gives the reader -- and the rule book neighbors [out_capacity, 9]:
+ * input pillar id at (2yo + ky - 1, 2xo + kx - 1) or -1.  hgsf_subm_conv3x3 then evaluates the convolution from that rule
+ * book (features = the INPUT rows, num_rows = out_capacity, num_rows_dev = out_counts).  out_counts [2] int32 (device):
+ * {Mo, scratch}.  out_capacity >= min(4 * num_rows, B * Ho * Wo).  pillars must list the frames contiguously (the reader's
+ * order).  No host sync. */
+HGSF_API int hgsf_sparse_conv_s2_workspace_size(int64_t num_rows, int32_t batch_size, size_t *bytes);
+HGSF_API int hgsf_sparse_conv_s2_indices(const int32_t *pillar_bev_indices, const int32_t *pillars, int64_t num_rows,
+                                         const int32_t *num_rows_dev, int32_t batch_size, int32_t H, int32_t W,
+                                         int32_t *out_bev, int32_t *out_pillars, int32_t *out_counts, int32_t *neighbors,
+                                         int64_t out_capacity, void *workspace, size_t workspace_bytes, hgsf_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

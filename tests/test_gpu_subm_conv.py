@@ -175,3 +175,72 @@ def test_invalid_arguments(cuda):
     assert lib.hgsf_subm_conv3x3(*args(f, o)) == _lib.ERR_INVALID_ARG          # BatchNorm pointers: all or none
     with pytest.raises(ValueError):
         po.subm_conv3x3(f.cpu(), n, w)                                         # no CPU path
+
+
+@pytest.mark.parametrize("B,H,W,M_per", [(2, 40, 40, 300), (3, 17, 33, 200), (1, 1, 1, 1), (2, 2, 1, 2), (4, 64, 64, 4096), (2, 31, 8, 5)])
+def test_stride2_indices_bit_exact(cuda, B, H, W, M_per):
+    rng = np.random.default_rng(B * 1000 + H * 7 + W)
+    pillars, bev = _random_pillars(rng, B, H, W, M_per)
+    r = po.sparse_conv_s2_indices(torch.from_numpy(bev).to(cuda), torch.from_numpy(pillars).to(cuda))
+    out_pillars, out_bev, nbr = pb.sparse_conv_s2_indices(bev, pillars)
+    assert int(r["counts"][0].item()) == out_pillars.shape[0]
+    assert np.array_equal(r["pillars"].cpu().numpy(), out_pillars)
+    assert np.array_equal(r["pillar_bev_indices"].cpu().numpy(), out_bev)
+    assert np.array_equal(r["neighbors"].cpu().numpy(), nbr)
+
+
+def test_stride2_indices_with_a_device_row_count(cuda):
+    rng = np.random.default_rng(77)
+    pillars, bev = _random_pillars(rng, 2, 20, 20, 90)
+    M = pillars.shape[0]
+    pad = np.full((M + 50, 3), -3, dtype=np.int32); pad[:M] = pillars
+    m_dev = torch.tensor([M], dtype=torch.int32, device=cuda)
+    r = po.sparse_conv_s2_indices(torch.from_numpy(bev).to(cuda), torch.from_numpy(pad).to(cuda), num_rows_dev=m_dev)
+    out_pillars, out_bev, nbr = pb.sparse_conv_s2_indices(bev, pillars)
+    assert np.array_equal(r["pillars"].cpu().numpy(), out_pillars) and np.array_equal(r["neighbors"].cpu().numpy(), nbr)
+
+
+def test_encoder_conv2_against_oracle_and_cudnn(cuda):
+    """conv2 stage (stride-2 SparseConv2d 32 -> 64 + BN + ReLU + two residual blocks at 64 channels) on the reader's pillar list."""
+    import torch.nn.functional as F
+    from test_gpu_pillarnet import make_points
+    rng = np.random.default_rng(13)
+    xyz, cnt = make_points(2, 3000, seed=9)
+    g = po.gen_indice_pairs_flat(torch.from_numpy(xyz).to(cuda), torch.from_numpy(cnt).to(cuda), 0.16, (320, 320))
+    pillars, bev = g["pillars"], g["pillar_bev_indices"]
+    M = int(pillars.shape[0])
+    feats = np.abs(rng.normal(size=(M, 32))).astype(np.float32)
+    torch.manual_seed(1)
+    enc = po.PillarEncoderConv2(32, 64).to(cuda).eval()
+    for m in enc.modules():
+        if isinstance(m, torch.nn.BatchNorm1d):
+            m.load_state_dict(_bn(rng, 64, cuda).state_dict())
+    assert {"0.weight", "1.running_mean", "3.conv1.0.weight", "3.conv1.0.bias", "4.conv2.1.weight"} <= set(enc.state_dict().keys())
+    assert "0.bias" not in enc.state_dict()
+    got, out_pillars, out_bev = enc(torch.from_numpy(feats).to(cuda), pillars, bev)
+    # oracle composition
+    op, ob, nbr2 = pb.sparse_conv_s2_indices(bev.cpu().numpy(), pillars.cpu().numpy())
+    assert np.array_equal(out_pillars.cpu().numpy(), op) and np.array_equal(out_bev.cpu().numpy(), ob)
+    conv, bn = getattr(enc, "0"), getattr(enc, "1")
+    x = pb.subm_conv3x3(feats, nbr2, conv.weight.detach().cpu().numpy(), bn=_bn_np(bn), relu=True)
+    nbr = pb.subm_neighbors(ob, op)
+    def cb(seq, t, res):
+        return pb.subm_conv3x3(t, nbr, seq[0].weight.detach().cpu().numpy(), bias=seq[0].bias.detach().cpu().numpy(), bn=_bn_np(seq[1]),
+                               residual=res, relu=True)
+    for name in ("3", "4"):
+        blk = getattr(enc, name)
+        x = cb(blk.conv2, cb(blk.conv1, x, None), x)
+    assert got.shape == x.shape and _close(got.cpu().numpy(), x)
+    # the stride-2 layer alone against cuDNN's dense fp32 convolution at the active output cells
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        dense = po.sparse_to_dense(torch.from_numpy(feats).to(cuda), pillars, (320, 320), 2)
+        ref = F.conv2d(dense, conv.weight.detach().permute(0, 3, 1, 2).contiguous(), None, stride=2, padding=1)
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    idx = out_pillars.long()
+    ref = ref[idx[:, 0], :, idx[:, 1], idx[:, 2]]
+    r = po.sparse_conv_s2_indices(bev, pillars)
+    one = po.subm_conv3x3(torch.from_numpy(feats).to(cuda), r["neighbors"], conv.weight.detach())
+    assert (one - ref).abs().max().item() <= TOL * max(1.0, ref.abs().max().item())

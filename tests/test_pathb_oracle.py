@@ -149,3 +149,26 @@ def test_subm_neighbors_edges_and_frames():
     assert nbr[1].tolist() == [-1, -1, -1, 0, 1, -1, -1, -1, 2]
     assert nbr[2].tolist() == [1, -1, -1, -1, 2, -1, -1, -1, -1]
     assert nbr[3].tolist() == [-1, -1, -1, -1, 3, -1, -1, -1, -1]    # other frames are not neighbours
+
+
+@pytest.mark.parametrize("H,W", [(12, 9), (7, 7), (2, 1), (16, 16)])
+def test_sparse_conv_s2_oracle_matches_dense_conv2d(H, W):
+    """Active set = where a stride-2 3x3 window holds a pillar (max_pool2d of the occupancy); features = dense conv2d there."""
+    import torch
+    import torch.nn.functional as F
+    rng = np.random.default_rng(H * 31 + W)
+    pillars, bev = _random_pillars(rng, 2, H, W, max(1, H * W // 4))
+    M = pillars.shape[0]
+    feats = rng.normal(size=(M, 32)).astype(np.float32)
+    w = (rng.normal(size=(64, 3, 3, 32)) * 0.1).astype(np.float32)
+    out_pillars, out_bev, nbr = pb.sparse_conv_s2_indices(bev, pillars)
+    occ = torch.from_numpy((bev >= 0).astype(np.float32))[:, None]
+    act = F.max_pool2d(occ, 3, 2, 1)[:, 0].numpy() > 0
+    assert np.array_equal(out_pillars, np.argwhere(act).astype(np.int32))
+    assert np.array_equal(out_bev >= 0, act)
+    got = pb.subm_conv3x3(feats, nbr, w)
+    dense = torch.zeros(2, 32, H, W)
+    dense[pillars[:, 0], :, pillars[:, 1], pillars[:, 2]] = torch.from_numpy(feats)
+    ref = F.conv2d(dense, torch.from_numpy(w).permute(0, 3, 1, 2).contiguous(), None, stride=2, padding=1)
+    ref = ref[out_pillars[:, 0], :, out_pillars[:, 1], out_pillars[:, 2]].numpy()
+    assert np.abs(got - ref).max() <= 1e-5 * max(1.0, np.abs(ref).max())
