@@ -27,6 +27,9 @@
 // below this one; a row-owner mapping (a thread owns whole pillars, weights as warp-wide broadcast loads) was built and
 // measured slower (26.8 TFLOP/s: 4 warps per SM at 166 registers).  [Cout,3,3,Cin] weights are transposed by every CTA
 // on the fly (-8 %): convert to [3,3,Cin,Cout] once when the weights are frozen (the Python mirror does).
+// 64 -> 64 (the weights take 147 KB of the SM's shared memory, one CTA per SM): 8-pillar x 4-channel thread tiles over 128-pillar
+// tiles, 256 threads, 2 stages: 0.278 ms for the 143 k pillars of conv2's active set = 38.0 TFLOP/s, 51 % of the peak (4 x 4 over 64
+// pillars 27.4; 3 stages 30.5; 16 x 4 35.6; 8 x 8 with 128 threads 32.2 -- too few warps).
 #include "subm_conv.cuh"
 
 #include <cstdlib>
@@ -110,7 +113,7 @@ __global__ void __launch_bounds__(SubmCfg<CIN, COUT, PT, NCO, TM, NBUF>::THREADS
     constexpr int AS = S::AS, THREADS = S::THREADS, TXN = S::TXN;
     constexpr int C4 = CIN / 4;               // 16-byte pieces per row
     constexpr int NP = NCO / 2;               // channel pairs per thread (packed fp32: one FFMA2 per pair)
-    static_assert(NCO == 2 || NCO == 4, "channel pairs");
+    static_assert(NCO == 2 || NCO == 4 || NCO == 8, "channel pairs");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float *Ws = reinterpret_cast<float *>(smem_raw);                        // [9][CIN][COUT]
     float *As = reinterpret_cast<float *>(smem_raw + S::w_bytes);           // [NBUF][TM][AS]
@@ -204,8 +207,11 @@ __global__ void __launch_bounds__(SubmCfg<CIN, COUT, PT, NCO, TM, NBUF>::THREADS
                     uint64_t w[NP];
                     if (NP == 1) w[0] = *reinterpret_cast<const uint64_t *>(wk + (c4 * 4 + j) * COUT);
                     else {
-                        const ulonglong2 t = *reinterpret_cast<const ulonglong2 *>(wk + (c4 * 4 + j) * COUT);
-                        w[0] = t.x; w[NP - 1] = t.y;
+#pragma unroll
+                        for (int c = 0; c < NP; c += 2) {
+                            const ulonglong2 t = *reinterpret_cast<const ulonglong2 *>(wk + (c4 * 4 + j) * COUT + c * 2);
+                            w[c] = t.x; w[c + 1 < NP ? c + 1 : c] = t.y;
+                        }
                     }
 #pragma unroll
                     for (int i = 0; i < PT; ++i) {
@@ -242,7 +248,10 @@ __global__ void __launch_bounds__(SubmCfg<CIN, COUT, PT, NCO, TM, NBUF>::THREADS
                 for (int c = 0; c < NCO; ++c) v[c] = (v[c] > 0.f || v[c] != v[c]) ? v[c] : 0.f;   // NaN propagates like torch's ReLU
             }
             if (NCO == 2) *reinterpret_cast<float2 *>(q.out + o) = make_float2(v[0], v[1]);
-            else *reinterpret_cast<float4 *>(q.out + o) = make_float4(v[0], v[1], v[NCO - 2], v[NCO - 1]);
+            else {
+#pragma unroll
+                for (int c = 0; c + 3 < NCO; c += 4) *reinterpret_cast<float4 *>(q.out + o + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+            }
         }
     }
 }
@@ -296,10 +305,25 @@ int launch_subm_conv(const SubmConvParams &q, cudaStream_t stream) {
         if (var == 5) return launch_conv_t<32, 32, 4, 2, 64, 3>(q, stream);
         if (var == 6) return launch_conv_t<32, 32, 8, 4, 128, 3>(q, stream);
         if (var == 7) return launch_conv_t<32, 32, 4, 4, 32, 3>(q, stream);
+        if (var == 8) return launch_conv_t<32, 32, 8, 8, 128, 3>(q, stream);
+        if (var == 9) return launch_conv_t<32, 32, 8, 8, 256, 3>(q, stream);
 #endif
         return launch_conv_t<32, 32, 4, 4, 64, 3>(q, stream);
     }
-    if (q.Cin == 64 && q.Cout == 64) return launch_conv_t<64, 64, 4, 4, 64, 2>(q, stream);
+    if (q.Cin == 64 && q.Cout == 64) {
+#ifdef HGSF_EXPERIMENT
+        const char *v = getenv("HGSF_SUBM_VARIANT");
+        const int var = v ? atoi(v) : 0;
+        if (var == 1) return launch_conv_t<64, 64, 4, 4, 64, 2>(q, stream);
+        if (var == 2) return launch_conv_t<64, 64, 4, 4, 64, 3>(q, stream);
+        if (var == 3) return launch_conv_t<64, 64, 8, 4, 64, 3>(q, stream);
+        if (var == 4) return launch_conv_t<64, 64, 4, 4, 32, 4>(q, stream);
+        if (var == 5) return launch_conv_t<64, 64, 8, 8, 128, 2>(q, stream);
+        if (var == 6) return launch_conv_t<64, 64, 8, 8, 64, 3>(q, stream);
+        if (var == 7) return launch_conv_t<64, 64, 16, 4, 128, 2>(q, stream);
+#endif
+        return launch_conv_t<64, 64, 8, 4, 128, 2>(q, stream);
+    }
     if (q.Cin == 32 && q.Cout == 64) return launch_conv_t<32, 64, 4, 4, 64, 3>(q, stream);
     return HGSF_ERR_UNSUPPORTED;
 }

@@ -66,6 +66,34 @@ with torch.no_grad():
         d = dense_stage()
         got = d[idx[:, 0], :, idx[:, 1], idx[:, 2]]
         res[tf32] = (timed(dense_stage, iters=20, warm=3), (got - ours).abs().max().item())
+    # ---- conv2: SparseConv2d(32, 64, 3, 2, 1) + BN + ReLU + 2 x Sparse2DBasicBlock(64) on the down-sampled active set ----
+    enc2 = po.PillarEncoderConv2(32, 64).to(dev).eval()
+    x2, p2, bev2 = enc2(ours, pillars, bev)
+    M2 = int(p2.shape[0])
+    t_ours2 = timed(lambda: enc2(ours, pillars, bev))
+    t_idx2 = timed(lambda: po.sparse_conv_s2_indices(bev, pillars, sync=False))
+    idx2 = p2.long()
+    mask2 = torch.zeros((B, 1, H // 2, W // 2), device=dev); mask2[idx2[:, 0], 0, idx2[:, 1], idx2[:, 2]] = 1
+    w0 = getattr(enc2, "0").weight.permute(0, 3, 1, 2).contiguous()
+    bn0 = getattr(enc2, "1")
+    s0 = (bn0.weight / torch.sqrt(bn0.running_var + bn0.eps)).view(1, -1, 1, 1)
+    o0 = (bn0.bias.view(1, -1, 1, 1) - bn0.running_mean.view(1, -1, 1, 1) * s0)
+    Q = {k: fold(v) for k, v in dict(a=getattr(enc2, "3").conv1, b=getattr(enc2, "3").conv2, c=getattr(enc2, "4").conv1, d=getattr(enc2, "4").conv2).items()}
+    def cb2(x, p, res=None):
+        y = F.conv2d(x, p[0], p[1], padding=1) * p[2] + p[3]
+        if res is not None: y = y + res
+        return torch.relu(y) * mask2
+    def dense_stage2():
+        x = po.sparse_to_dense(ours, pillars, (H, W), B)
+        x = torch.relu(F.conv2d(x, w0, None, stride=2, padding=1) * s0 + o0) * mask2
+        x = cb2(cb2(x, Q["a"]), Q["b"], x)
+        return cb2(cb2(x, Q["c"]), Q["d"], x)
+    res2 = {}
+    for tf32 in (False, True):
+        torch.backends.cudnn.allow_tf32 = tf32
+        d = dense_stage2()
+        got = d[idx2[:, 0], :, idx2[:, 1], idx2[:, 2]]
+        res2[tf32] = (timed(dense_stage2, iters=20, warm=3), (got - x2).abs().max().item())
 fma = 9 * 32 * 32 * M
 print(json.dumps({"what": "SpMiddlePillarEncoder18.conv1 on the pillar list vs the dense cuDNN formulation, same B200",
                   "workload": f"vod_{mode}_b{B}_n{n}", "pillars": M, "active_fraction": M / (B * H * W),
@@ -73,4 +101,9 @@ print(json.dumps({"what": "SpMiddlePillarEncoder18.conv1 on the pillar list vs t
                   "ours_one_conv_tflops_fp32": 2 * fma / (t_one * 1e-3) / 1e12,
                   "dense_cudnn_fp32_stage_ms": res[False][0], "dense_cudnn_tf32_stage_ms": res[True][0],
                   "max_abs_diff_vs_dense_fp32": res[False][1], "max_abs_diff_vs_dense_tf32": res[True][1],
-                  "speedup_vs_dense_fp32": res[False][0] / t_ours, "speedup_vs_dense_tf32": res[True][0] / t_ours}))
+                  "speedup_vs_dense_fp32": res[False][0] / t_ours, "speedup_vs_dense_tf32": res[True][0] / t_ours,
+                  "conv2": {"what": "SpMiddlePillarEncoder18.conv2 (stride-2 32->64 + BN + ReLU + 2 residual blocks at 64 channels)",
+                            "out_pillars": M2, "ours_stage_ms": t_ours2, "ours_indices_ms": t_idx2,
+                            "dense_cudnn_fp32_stage_ms": res2[False][0], "dense_cudnn_tf32_stage_ms": res2[True][0],
+                            "max_abs_diff_vs_dense_fp32": res2[False][1], "max_abs_diff_vs_dense_tf32": res2[True][1],
+                            "speedup_vs_dense_fp32": res2[False][0] / t_ours2, "speedup_vs_dense_tf32": res2[True][0] / t_ours2}}))

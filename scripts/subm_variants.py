@@ -13,9 +13,13 @@ for mode in ("clustered", "uniform"):
     nbr = po.subm_neighbors(r["pillar_bev_indices"], r["pillars"])
     M = nbr.shape[0]
     torch.manual_seed(0)
-    f = torch.rand((M, 32), device=dev); w = torch.randn((32, 3, 3, 32), device=dev) * 0.1
+    CH = int(os.environ.get("SUBM_CH", "32"))
+    if CH == 64:      # the conv2 stage's active set
+        r2 = po.sparse_conv_s2_indices(r["pillar_bev_indices"], r["pillars"])
+        nbr = po.subm_neighbors(r2["pillar_bev_indices"], r2["pillars"]); M = nbr.shape[0]
+    f = torch.rand((M, CH), device=dev); w = torch.randn((CH, 3, 3, CH), device=dev) * 0.1
     ref = None
-    out = torch.empty((M, 32), device=dev)
+    out = torch.empty((M, CH), device=dev)
     for layout, wt in (("KRSC", w), ("RSCK", w.permute(1, 2, 3, 0).contiguous())):
         for _ in range(5): po.subm_conv3x3(f, nbr, wt, relu=True, out=out, weight_layout=layout)
         torch.cuda.synchronize()
@@ -24,4 +28,4 @@ for mode in ("clustered", "uniform"):
         for _ in range(100): po.subm_conv3x3(f, nbr, wt, relu=True, out=out, weight_layout=layout)
         e1.record(); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 100
-        print(f"variant {os.environ.get('HGSF_SUBM_VARIANT', '0')} {layout} {mode} M={M}: {ms:.4f} ms  {2 * 9216 * M / ms / 1e9:.1f} TFLOP/s  checksum {out.double().sum().item():.6f}")
+        print(f"variant {os.environ.get('HGSF_SUBM_VARIANT', '0')} {layout} {mode} M={M}: {ms:.4f} ms  {2 * 9 * CH * CH * M / ms / 1e9:.1f} TFLOP/s  checksum {out.double().sum().item():.6f}")
