@@ -148,6 +148,7 @@ class PillarQueryAndGroup(nn.Module):
         pillars (M,3) [b y x], pillar_set_indices (L,), group_features (L, C+6)   (pillar_utils.py:31-54)"""
         r = gen_indice_pairs_flat(xyz, xyz_batch_cnt, self.pillar_size, self.spatial_shape)
         pillars, point_set_indices, pillar_set_indices = r["pillars"], r["point_set_indices"], r["pillar_set_indices"]
+        self.last_pillar_bev_indices = r["pillar_bev_indices"]      # the cell table, for the pillar-list consumer (subm_neighbors)
         # pillar centres as the reference builds them (pillar_utils.py:117-121): z centre in absolute coordinates
         pillar_centers = torch.zeros([pillars.shape[0], 3], dtype=torch.float32, device=xyz.device)
         pillar_centers[:, 0] = (pillars[:, 2] + 0.5) * self.pillar_size
@@ -163,6 +164,13 @@ class PillarQueryAndGroup(nn.Module):
 
 
 class PillarMaxPooling(nn.Module):
+    """pillar_modules.py:10-82.  After a forward, `pillar_bev_indices` holds the [B,H,W] cell table (pillar id per cell, -1
+    none) of that call -- what PillarEncoderConv1 / PillarEncoderConv2 need next to the returned features and indices."""
+
+    @property
+    def pillar_bev_indices(self):
+        return getattr(self.groups, "last_pillar_bev_indices", None)
+
     def __init__(self, mlps: List[int], pillar_size: float, point_cloud_range: List[float]):
         super().__init__()
         self.bev_width, self.bev_height = bev_spatial_shape(point_cloud_range, pillar_size)
@@ -190,6 +198,7 @@ class PillarMaxPooling(nn.Module):
         g = self.groups
         r = gen_indice_pairs_flat(xyz, xyz_batch_cnt, g.pillar_size, g.spatial_shape)
         pillars, point_idx, pillar_idx = r["pillars"], r["point_set_indices"], r["pillar_set_indices"]
+        g.last_pillar_bev_indices = r["pillar_bev_indices"]         # the cell table, for the pillar-list consumer (subm_neighbors)
         lin, bn = self.shared_mlps[0], self.shared_mlps[1]
         pfn = PfnWeights(weight=lin.weight.detach(), bn_weight=bn.weight.detach(), bn_bias=bn.bias.detach(),
                          running_mean=bn.running_mean, running_var=bn.running_var, eps=bn.eps)

@@ -244,3 +244,54 @@ def test_encoder_conv2_against_oracle_and_cudnn(cuda):
     r = po.sparse_conv_s2_indices(bev, pillars)
     one = po.subm_conv3x3(torch.from_numpy(feats).to(cuda), r["neighbors"], conv.weight.detach())
     assert (one - ref).abs().max().item() <= TOL * max(1.0, ref.abs().max().item())
+
+
+def test_reader_to_conv1_conv2_to_dense_end_to_end(cuda):
+    """Path B behind the reader: PillarMaxPooling (native) -> conv1 -> conv2 on the pillar list -> dense [B,64,H/2,W/2], against the
+    dense torch composition of the same modules (cuDNN fp32) fed with the reader's densified output."""
+    import torch.nn.functional as F
+    from test_gpu_pillarnet import make_points
+    rng = np.random.default_rng(31)
+    xyz, cnt = make_points(2, 4000, seed=3)
+    N = xyz.shape[0]
+    feat = rng.normal(size=(N, 29)).astype(np.float32)
+    torch.manual_seed(2)
+    reader = po.PillarMaxPooling([35, 32], 0.16, [0, -25.6, -3, 51.2, 25.6, 2]).to(cuda).eval()
+    c1, c2 = po.PillarEncoderConv1(32).to(cuda).eval(), po.PillarEncoderConv2(32, 64).to(cuda).eval()
+    for mod in (reader, c1, c2):
+        for m in mod.modules():
+            if isinstance(m, torch.nn.BatchNorm1d):
+                m.load_state_dict(_bn(rng, m.num_features, cuda).state_dict())
+    with torch.no_grad():
+        out = reader(torch.from_numpy(xyz).to(cuda), torch.from_numpy(cnt).to(cuda), torch.from_numpy(feat).to(cuda))
+        pf, pillars, (H, W), B = out if isinstance(out, tuple) else (out.features, out.indices, out.spatial_shape, out.batch_size)
+        bev = reader.pillar_bev_indices
+        assert bev is not None and tuple(bev.shape) == (B, H, W)
+        x1 = c1(pf, pillars, bev)
+        x2, p2, bev2 = c2(x1, pillars, bev)
+        got = po.sparse_to_dense(x2, p2, (bev2.shape[1], bev2.shape[2]), B)
+        # dense composition
+        old = torch.backends.cudnn.allow_tf32
+        torch.backends.cudnn.allow_tf32 = False
+        try:
+            idx = pillars.long()
+            mask = torch.zeros((B, 1, H, W), device=cuda); mask[idx[:, 0], 0, idx[:, 1], idx[:, 2]] = 1
+            mask2 = (F.max_pool2d(mask, 3, 2, 1) > 0).float()
+            def cb(seq, x, res, msk, stride=1):
+                conv, bn = seq
+                y = F.conv2d(x, conv.weight.permute(0, 3, 1, 2).contiguous(), conv.bias, stride=stride, padding=1)
+                y = F.batch_norm(y, bn.running_mean, bn.running_var, bn.weight, bn.bias, False, 0.0, bn.eps)
+                if res is not None: y = y + res
+                return torch.relu(y) * msk
+            x = po.sparse_to_dense(pf, pillars, (H, W), B)
+            b0, b1 = getattr(c1, "0"), getattr(c1, "1")
+            i = cb(b0.conv0, x, None, mask); x = cb(b0.conv2, cb(b0.conv1, i, None, mask), i, mask)
+            x = cb(b1.conv2, cb(b1.conv1, x, None, mask), x, mask)
+            x = cb((getattr(c2, "0"), getattr(c2, "1")), x, None, mask2, stride=2)
+            for name in ("3", "4"):
+                blk = getattr(c2, name)
+                x = cb(blk.conv2, cb(blk.conv1, x, None, mask2), x, mask2)
+        finally:
+            torch.backends.cudnn.allow_tf32 = old
+    assert got.shape == x.shape
+    assert (got - x).abs().max().item() <= 5e-5 * max(1.0, x.abs().max().item())      # eleven fp32 layers deep
