@@ -674,7 +674,7 @@ __global__ void __launch_bounds__(PFN_THREADS, 4) k_pfn(const PathParams p) {
                     int v0 = 0, v1 = 0, v2 = 0, v3 = 0;
                     if (1 < Pmax) { v0 = __float_as_int(pv.x); v1 = __float_as_int(pv.y); v2 = __float_as_int(pv.z); v3 = __float_as_int(pv.w); }
                     eval_point(grows + ((size_t)__float_as_int(r1.x) + (meta >> 16)) * RWc, r0.x, r0.y, r0.z, cx, cy, cz, v0, v1, v2, v3);
-                    st_f4_hint(p.feats + (size_t)__float_as_int(r1.y) * C + c0,
+                    if (p.feats) st_f4_hint(p.feats + (size_t)__float_as_int(r1.y) * C + c0,
                                make_float4(__int_as_float(v0), __int_as_float(v1), __int_as_float(v2), __int_as_float(v3)), keep_policy);
                 }
             }
@@ -696,7 +696,7 @@ __global__ void __launch_bounds__(PFN_THREADS, 4) k_pfn(const PathParams p) {
                     eval_point(rowb + (size_t)perm[owner][s2] * RWc, r0.x, r0.y, r0.z, cx, cy, cz, v0, v1, v2, v3);
                 v0 = max(v0, __shfl_xor_sync(FULL, v0, 16)); v1 = max(v1, __shfl_xor_sync(FULL, v1, 16));
                 v2 = max(v2, __shfl_xor_sync(FULL, v2, 16)); v3 = max(v3, __shfl_xor_sync(FULL, v3, 16));
-                if (half == 0)
+                if (half == 0 && p.feats)
                     st_f4_hint(p.feats + (size_t)__float_as_int(r1.y) * C + c0,
                                make_float4(__int_as_float(v0), __int_as_float(v1), __int_as_float(v2), __int_as_float(v3)), keep_policy);
             }
@@ -737,7 +737,7 @@ __global__ void __launch_bounds__(PFN_THREADS, 4) k_pfn(const PathParams p) {
                     eval_point(grow_o + (size_t)bperm[s2] * RWc, mx, my, mz, cx, cy, cz, v0, v1, v2, v3);
                 v0 = max(v0, __shfl_xor_sync(FULL, v0, 16)); v1 = max(v1, __shfl_xor_sync(FULL, v1, 16));
                 v2 = max(v2, __shfl_xor_sync(FULL, v2, 16)); v3 = max(v3, __shfl_xor_sync(FULL, v3, 16));
-                if (half == 0)
+                if (half == 0 && p.feats)
                     st_f4_hint(p.feats + (size_t)f_o * C + c0,
                                make_float4(__int_as_float(v0), __int_as_float(v1), __int_as_float(v2), __int_as_float(v3)), keep_policy);
             }

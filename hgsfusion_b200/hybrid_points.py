@@ -97,7 +97,9 @@ def assemble_hybrid_points(real, real_offsets, gt_real=None, gt_offsets=None, vi
         cal_ptr = C.c_void_p(cal.data_ptr())
     rng = None
     if point_cloud_range is not None:
-        r = [float(v) for v in point_cloud_range]
+        # the reference compares against DatasetTemplate.point_cloud_range = np.array(..., dtype=np.float32) (dataset.py:26):
+        # the limits are the float32 roundings of the YAML values, widened exactly to double (float32(51.2) > 51.2)
+        r = [float(np.float32(v)) for v in point_cloud_range]
         rng = (C.c_double * 4)(r[0], r[1], r[3], r[4])
     need = C.c_size_t(0)
     _lib.check(lib.hgsf_hybrid_workspace_size(n, C.byref(need)), "hgsf_hybrid_workspace_size")
@@ -111,7 +113,7 @@ def assemble_hybrid_points(real, real_offsets, gt_real=None, gt_offsets=None, vi
     elif out.points.shape[0] < n or out.points.shape[1] != 1 + F or out.frame_offsets.numel() != B + 1:
         raise ValueError("out: capacity / width mismatch")
     st = lib.hgsf_assemble_hybrid_points(C.byref(s), cal_ptr, rng, C.c_void_p(ws_ptr), need.value, C.c_void_p(out.points.data_ptr()),
-                                         C.c_void_p(out.frame_offsets.data_ptr()), C.c_void_p(torch.cuda.current_stream().cuda_stream))
+                                         C.c_void_p(out.frame_offsets.data_ptr()), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
     _lib.check(st, "hgsf_assemble_hybrid_points")
     del keep
     return out

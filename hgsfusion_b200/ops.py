@@ -25,8 +25,9 @@ def _ptr(t):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
-def _stream():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+def _stream(device=None):
+    """The current stream OF THE TENSORS' DEVICE (not of whatever device happens to be current)."""
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
 def _f32c(t: torch.Tensor, name: str) -> torch.Tensor:
@@ -167,16 +168,17 @@ class PillarPath:
         o.pillar_features = out.pillar_features.data_ptr() if out.pillar_features is not None else None
         o.spatial_features = out.spatial_features.data_ptr() if out.spatial_features is not None else None
         o.pillar_capacity = int(out.voxel_coords.shape[0])
-        if pfn is None:
-            st = self.lib.hgsf_pillarize(C.byref(self.geom), C.byref(ps), self.P, self.max_voxels,
-                                         C.c_void_p(ws_ptr), ws_bytes, C.byref(o), _stream())
-            _lib.check(st, "hgsf_pillarize")
-        else:
-            pf = pfn.to_struct()
-            st = self.lib.hgsf_points_to_bev(C.byref(self.geom), C.byref(ps), C.byref(pf), self.P, self.max_voxels,
-                                             C.c_void_p(ws_ptr), ws_bytes, C.byref(o), _stream())
-            _lib.check(st, "hgsf_points_to_bev")
-        self.last_launches = int(self.lib.hgsf_last_launch_count())
+        with torch.cuda.device(dev):           # the library launches on the current device: make it the tensors' device
+            if pfn is None:
+                st = self.lib.hgsf_pillarize(C.byref(self.geom), C.byref(ps), self.P, self.max_voxels,
+                                             C.c_void_p(ws_ptr), ws_bytes, C.byref(o), _stream(dev))
+                _lib.check(st, "hgsf_pillarize")
+            else:
+                pf = pfn.to_struct()
+                st = self.lib.hgsf_points_to_bev(C.byref(self.geom), C.byref(ps), C.byref(pf), self.P, self.max_voxels,
+                                                 C.c_void_p(ws_ptr), ws_bytes, C.byref(o), _stream(dev))
+                _lib.check(st, "hgsf_points_to_bev")
+            self.last_launches = int(self.lib.hgsf_last_launch_count())
         del keep
         return out
 
@@ -202,8 +204,9 @@ class PillarPath:
         nu, nf = _coords(voxel_num_points, "voxel_num_points")
         pf = pfn.to_struct()
         out = torch.empty((M, int(pfn.weight.shape[0])), dtype=torch.float32, device=vox.device)
-        st = self.lib.hgsf_pillar_vfe(C.byref(self.geom), C.byref(pf), _ptr(vox), _ptr(co), _ptr(nu), cf, nf, M, P, F,
-                                      _ptr(out), _stream())
+        with torch.cuda.device(vox.device):
+            st = self.lib.hgsf_pillar_vfe(C.byref(self.geom), C.byref(pf), _ptr(vox), _ptr(co), _ptr(nu), cf, nf, M, P, F,
+                                      _ptr(out), _stream(vox.device))
         _lib.check(st, "hgsf_pillar_vfe")
         self.last_launches = int(self.lib.hgsf_last_launch_count())
         return out
@@ -226,9 +229,10 @@ class PillarPath:
         stats = torch.empty(int(self.lib.hgsf_train_stats_doubles(Cc, cin)), dtype=torch.float64, device=vox.device)
         mean = torch.empty(Cc, dtype=torch.float32, device=vox.device)
         var = torch.empty(Cc, dtype=torch.float32, device=vox.device)
-        st = self.lib.hgsf_pillar_vfe_batch_stats(C.byref(self.geom), C.byref(pf), _ptr(vox), _ptr(co), _ptr(nu), cf, nf, M, P, F,
+        with torch.cuda.device(vox.device):
+            st = self.lib.hgsf_pillar_vfe_batch_stats(C.byref(self.geom), C.byref(pf), _ptr(vox), _ptr(co), _ptr(nu), cf, nf, M, P, F,
                                                   float(momentum), _ptr(running_mean), _ptr(running_var), _ptr(mean), _ptr(var),
-                                                  _ptr(stats), _stream())
+                                                  _ptr(stats), _stream(vox.device))
         _lib.check(st, "hgsf_pillar_vfe_batch_stats")
         self.last_launches = int(self.lib.hgsf_last_launch_count())
         return mean, var, stats
@@ -245,8 +249,9 @@ class PillarPath:
         dW = torch.empty((Cc, cin), dtype=torch.float32, device=vox.device)
         dg = torch.empty(Cc, dtype=torch.float32, device=vox.device) if pfn.bn_weight is not None else None
         db = torch.empty(Cc, dtype=torch.float32, device=vox.device)
-        st = self.lib.hgsf_pillar_vfe_backward(C.byref(self.geom), C.byref(pf), _ptr(vox), _ptr(co), _ptr(nu), cf, nf, M, P, F,
-                                               _ptr(g), _ptr(stats), _ptr(scratch), _ptr(dW), _ptr(dg), _ptr(db), _stream())
+        with torch.cuda.device(vox.device):
+            st = self.lib.hgsf_pillar_vfe_backward(C.byref(self.geom), C.byref(pf), _ptr(vox), _ptr(co), _ptr(nu), cf, nf, M, P, F,
+                                               _ptr(g), _ptr(stats), _ptr(scratch), _ptr(dW), _ptr(dg), _ptr(db), _stream(vox.device))
         _lib.check(st, "hgsf_pillar_vfe_backward")
         self.last_launches = int(self.lib.hgsf_last_launch_count())
         return dW, dg, db
@@ -256,8 +261,9 @@ class PillarPath:
         co, cf = _coords(voxel_coords, "voxel_coords")
         M, Cc = int(co.shape[0]), int(gc.shape[1])
         out = torch.empty((M, Cc), dtype=torch.float32, device=gc.device)
-        st = self.lib.hgsf_pointpillar_scatter_backward(C.byref(self.geom), _ptr(gc), _ptr(co), cf, M, Cc, int(batch_size),
-                                                        _ptr(out), _stream())
+        with torch.cuda.device(gc.device):
+            st = self.lib.hgsf_pointpillar_scatter_backward(C.byref(self.geom), _ptr(gc), _ptr(co), cf, M, Cc, int(batch_size),
+                                                        _ptr(out), _stream(gc.device))
         _lib.check(st, "hgsf_pointpillar_scatter_backward")
         self.last_launches = int(self.lib.hgsf_last_launch_count())
         return out
@@ -273,8 +279,9 @@ class PillarPath:
         ws = torch.empty(need.value + 256, dtype=torch.uint8, device=pf.device)
         ws_ptr = (ws.data_ptr() + 255) // 256 * 256
         canvas = torch.empty((batch_size, Cc * self.nz, self.ny, self.nx), dtype=torch.float32, device=pf.device)
-        st = self.lib.hgsf_pointpillar_scatter(C.byref(self.geom), _ptr(pf), _ptr(co), cf, M, Cc, batch_size,
-                                               C.c_void_p(ws_ptr), need.value, _ptr(canvas), _stream())
+        with torch.cuda.device(pf.device):
+            st = self.lib.hgsf_pointpillar_scatter(C.byref(self.geom), _ptr(pf), _ptr(co), cf, M, Cc, batch_size,
+                                               C.c_void_p(ws_ptr), need.value, _ptr(canvas), _stream(pf.device))
         _lib.check(st, "hgsf_pointpillar_scatter")
         self.last_launches = int(self.lib.hgsf_last_launch_count())
         return canvas

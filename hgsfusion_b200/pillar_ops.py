@@ -26,12 +26,28 @@ from torch.autograd import Function
 from . import _lib
 
 
-def _s():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+def _s(t=None):
+    """The current stream of tensor `t`'s device (of the current device without a tensor)."""
+    return C.c_void_p(torch.cuda.current_stream(None if t is None else t.device).cuda_stream)
 
 
 def _p(t):
     return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _on_device(fn):
+    """Run `fn` with the device of its first CUDA tensor argument current: the native library launches on the current device
+    and `_s()` then returns that device's current stream (the reference's ops have no device guard at all, cuda_utils.h)."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(*args, **kwargs):
+        for a in list(args) + list(kwargs.values()):
+            if isinstance(a, torch.Tensor) and a.is_cuda:
+                with torch.cuda.device(a.device):
+                    return fn(*args, **kwargs)
+        return fn(*args, **kwargs)
+    return wrapped
 
 
 def _need_cuda(t, name, dtype):
@@ -49,6 +65,7 @@ def bev_spatial_shape(point_cloud_range, pillar_size):
     return int(W), int(H)          # the reference's quirk: (W, H) is then unpacked as `H, W = spatial_shape` (:102)
 
 
+@_on_device
 @torch.no_grad()
 def gen_indice_pairs_flat(xyz, xyz_batch_cnt, pillar_size, spatial_shape, sync=True):
     """xyz [N,3] relative coords, xyz_batch_cnt [B] int32 -> dict(pillars [M,3], pillar_bev_indices [B,H,W],
@@ -86,6 +103,7 @@ def gen_indice_pairs_flat(xyz, xyz_batch_cnt, pillar_size, spatial_shape, sync=T
 
 class GatherFeature(Function):
     @staticmethod
+    @_on_device
     def forward(ctx, features: torch.Tensor, set_indices: torch.Tensor):
         _need_cuda(features, "features", torch.float32)
         _need_cuda(set_indices, "set_indices", torch.int32)
@@ -96,6 +114,7 @@ class GatherFeature(Function):
         return out
 
     @staticmethod
+    @_on_device
     def backward(ctx, grad_out):
         N, Cc, set_indices = ctx.for_backwards
         grad_features = grad_out.new_zeros((N, Cc))
@@ -110,6 +129,7 @@ gather_feature = GatherFeature.apply
 
 class ScatterMaxFunction(Function):
     @staticmethod
+    @_on_device
     def forward(ctx, src: torch.Tensor, index: torch.Tensor, M: int):
         """src (C, L), index (L,) -> out (C, M)"""
         _need_cuda(src, "src", torch.float32)
@@ -123,6 +143,7 @@ class ScatterMaxFunction(Function):
         return out
 
     @staticmethod
+    @_on_device
     def backward(ctx, grad_out):
         Cc, L, arg = ctx.for_backwards
         grad_src = grad_out.new_zeros((Cc, L))
@@ -192,6 +213,7 @@ class PillarMaxPooling(nn.Module):
         return not (torch.is_grad_enabled() and any(p.requires_grad for p in self.shared_mlps.parameters()))
 
     @torch.no_grad()
+    @_on_device
     def _forward_fused(self, xyz, xyz_batch_cnt, pt_feature):
         from .ops import PfnWeights
         _need_cuda(pt_feature, "pt_feature", torch.float32)
@@ -225,11 +247,14 @@ class PillarMaxPooling(nn.Module):
                 import spconv.pytorch as spconv
             except ImportError:
                 import spconv
-            return spconv.SparseConvTensor(pillar_features, pillar_indices, (self.bev_height, self.bev_width), B)
+            # (bev_width, bev_height) as the reference passes it (pillar_modules.py:82): bev_spatial_shape returns (W, H) =
+            # (Ny, Nx), so this is (Ny, Nx) and matches the (b, y, x) indices -- on TJ4D (496, 432)
+            return spconv.SparseConvTensor(pillar_features, pillar_indices, (self.bev_width, self.bev_height), B)
         except ImportError:
-            return pillar_features, pillar_indices, (self.bev_height, self.bev_width), B
+            return pillar_features, pillar_indices, (self.bev_width, self.bev_height), B
 
 
+@_on_device
 def sparse_to_dense(features, indices, spatial_shape, batch_size: int):
     """`SparseConvTensor(features [M,C], indices [M,3] int32 (b, y, x), spatial_shape (Ny, Nx), batch_size).dense()` ->
     [B, C, Ny, Nx], as the PillarNet branch calls it on its backbone outputs (pillarnet_modules/lss_fpn.py:111-113,
@@ -256,6 +281,7 @@ _ENCODINGS = {"split": 0, "mixed": 1, "direct": 2}
 _SPLIT_N = {"vod": 12, "tj4d": 13}          # dynamic_pillar_encoder.py:72-76
 
 
+@_on_device
 @torch.no_grad()
 def split_encode(points, pc_range, num_input, virtual=True, encoding_type="split", dataset="vod", batch_size=None):
     """Collated `points [L, 1+Fin]` (frame index in column 0) -> `(xyz [L',3], xyz_batch_cnt [B] int32, pt_features
@@ -336,6 +362,7 @@ class DynamicPillarFeatureNet(nn.Module):
 # The pillar-list consumer: SpMiddlePillarEncoder18.conv1 on the reader's pillar list
 # ---------------------------------------------------------------------------------------------------------------
 
+@_on_device
 @torch.no_grad()
 def subm_neighbors(pillar_bev_indices, pillars, num_rows_dev=None):
     """The rule book of one `indice_key` for 3x3 submanifold convolutions: [M, 9] int32, entry ky*3+kx = pillar id at
@@ -351,6 +378,7 @@ def subm_neighbors(pillar_bev_indices, pillars, num_rows_dev=None):
     return nbr
 
 
+@_on_device
 @torch.no_grad()
 def subm_conv3x3(features, neighbors, weight, bias=None, bn=None, residual=None, relu=False, weight_layout="KRSC",
                  num_rows_dev=None, out=None):
@@ -456,6 +484,7 @@ class PillarEncoderConv1(nn.Module):
         return getattr(self, "1")(x, nbr, num_rows_dev)
 
 
+@_on_device
 @torch.no_grad()
 def sparse_conv_s2_indices(pillar_bev_indices, pillars, num_rows_dev=None, sync=True):
     """Indices of `SparseConv2d(kernel 3, stride 2, padding 1)` (the first layer of conv2 / conv3 / conv4, pcnres18.py:217-221)

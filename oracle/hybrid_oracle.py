@@ -66,7 +66,7 @@ def assemble_frame(real, gt_real, virt, *, use_virtual=True, no_dup=False, fov=N
         depth = hom[2] - P2[2, 3]
         pts = pts[(u >= 0) & (u < img_w) & (v >= 0) & (v < img_h) & (depth >= 0)]
     if pc_range is not None:
-        r = [float(v) for v in pc_range]
+        r = [float(np.float32(v)) for v in pc_range]      # limit_range is a float32 array in the reference (dataset.py:26)
         pts = pts[(pts[:, 0] >= r[0]) & (pts[:, 0] <= r[3]) & (pts[:, 1] >= r[1]) & (pts[:, 1] <= r[4])]
     return pts.astype(np.float32)
 

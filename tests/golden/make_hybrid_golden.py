@@ -100,7 +100,7 @@ def make_frame(rng, Fr, n_real, n_gt, n_virt, pc_range, dup_fraction=0.3):
     lo = np.array([pc_range[0] - 4, pc_range[1] - 4, pc_range[2]]), np.array([pc_range[3] + 4, pc_range[4] + 4, pc_range[5]])
     real = np.concatenate([rng.uniform(lo[0], lo[1], (n_real, 3)), rng.normal(0, 1, (n_real, Fr - 3))], 1).astype(np.float32)
     if n_real >= 4:
-        # points exactly on the range boundary: float32(limit) differs from the Python float the reference compares with
+        # points exactly on the range boundary: the reference's limits are float32 too (dataset.py:26), so these are kept
         real[0, 0] = np.float32(pc_range[3]); real[1, 1] = np.float32(pc_range[1]); real[2, 1] = np.float32(pc_range[4])
         real[3, 0] = np.float32(pc_range[0])
     gt = np.concatenate([rng.uniform(lo[0], lo[1], (n_gt, 3)), rng.normal(0, 1, (n_gt, Fr - 3)),
@@ -143,7 +143,8 @@ def run_case(name, dataset, Fr, pc_range, frames, fov, no_dup, use_virtual, seed
                                get_virtual_point=lambda idx, v=virt, g=gt: (v, g),
                                get_lidar=lambda idx, r=real: (r - np.zeros(Fr)) / np.ones(Fr))      # float64, as get_lidar's (points - means) / stds
         pts = run_block(self, "00000", calib, img_shape)                 # vod_dataset.py:498-529 / tj4d_dataset.py:588-618
-        pts = pts[mask_by_range(pts, pc_range)]                          # data_processor.py:83-85
+        # data_processor.py:83-85 with self.point_cloud_range = np.array(POINT_CLOUD_RANGE, dtype=np.float32) (dataset.py:26)
+        pts = pts[mask_by_range(pts, np.array(pc_range, dtype=np.float32))]
         out[f"real{b}"], out[f"gt{b}"], out[f"virt{b}"] = real, gt, virt
         out[f"P2_{b}"], out[f"R0_{b}"], out[f"V2C_{b}"] = cal["P2"], cal["R0"], cal["Tr_velo2cam"]
         out[f"points{b}"] = pts.astype(np.float32)                       # load_data_to_gpu: .float()

@@ -237,3 +237,27 @@ def test_random_configurations_bit_exact(cuda, seed):
     pts = np.concatenate(rows) if rows else np.zeros((0, 1 + F), np.float32)
     offs = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
     both(pts, offs, pc_range, vs, P, mv, F, cuda, seed=seed, want_voxels=bool(seed & 1), frame_offsets=bool(seed & 2))
+
+
+def test_pfn_requested_without_feature_or_canvas_outputs(cuda):
+    """hgsf_points_to_bev with pillar_features == NULL and spatial_features == NULL (the header allows any output to be
+    NULL): the pillar-major kernel must not store through the null feature pointer; coords / counts still come out."""
+    cfg = synthetic.CONFIGS["vod"]
+    pts, offs = synthetic.make_batch("vod", 2, 3000, "clustered", seed0=5)
+    w = synthetic.make_pfn(13, 64, 0)
+    path = PillarPath(np.asarray(cfg["pc_range"], dtype=np.float32), cfg["voxel_size"], 32, 40000, 7)
+    dpts = torch.from_numpy(pts).to(cuda)
+    res = path.points_to_bev(dpts, 2, device_pfn(w, cuda), want_features=False, want_canvas=False)
+    torch.cuda.synchronize()
+    got = res.trim()
+    assert res.pillar_features is None and res.spatial_features is None
+    ref = oracle.points_to_bev(pts, offs, oracle.Geometry(cfg["pc_range"], cfg["voxel_size"]), oracle_pfn(w), 32, 40000, F=7, xcol=1)
+    assert got["num_pillars"] == ref["num_pillars"]
+    assert np.array_equal(got["voxel_coords"].cpu().numpy(), ref["voxel_coords"])
+    assert np.array_equal(got["voxel_num_points"].cpu().numpy(), ref["voxel_num_points"])
+    # features only (no canvas): the pillar-major kernel with the PFN
+    res = path.points_to_bev(dpts, 2, device_pfn(w, cuda), want_features=True, want_canvas=False)
+    assert bits_equal(res.trim()["pillar_features"].cpu().numpy(), ref["pillar_features"])
+    # canvas only (no pillar_features rows)
+    res = path.points_to_bev(dpts, 2, device_pfn(w, cuda), want_features=False, want_canvas=True)
+    assert bits_equal(res.trim()["spatial_features"].cpu().numpy(), ref["spatial_features"])

@@ -76,26 +76,43 @@ def test_gather_scatter_forward_backward(cuda):
         assert abs(src_np[c, p] - ref[c, pidx_np[p]]) < 1e-5 and gs[c, p] == gout[c, pidx_np[p]].item()
 
 
-def test_pillar_max_pooling_module(cuda):
-    """PillarMaxPooling (Path B reader, VoD 'split' width 29+6 -> 32) against a plain torch composition."""
+# Path B geometries: VoD (square 320 x 320) and TJ4D (hgsfusion_tj4d.yaml: x 69.12 m -> Nx = 432, y 79.36 m -> Ny = 496; the
+# 'split' encoding gives 29 / 31 point features).  bev_spatial_shape returns (W, H) = (Ny, Nx) and the reference hands exactly
+# that to SparseConvTensor (pillar_modules.py:82), matching the (b, y, x) indices.
+PATHB_GEOM = {
+    "vod": dict(pc_range=[0, -25.6, -3, 51.2, 25.6, 2], Ny=320, Nx=320, Cf=29),
+    "tj4d": dict(pc_range=[0, -39.68, -4, 69.12, 39.68, 2], Ny=496, Nx=432, Cf=31),
+}
+
+
+@pytest.mark.parametrize("geom", ["vod", "tj4d"])
+def test_pillar_max_pooling_module(cuda, geom):
+    """PillarMaxPooling (Path B reader, 'split' width 29+6 / 31+6 -> 32) against a plain torch composition."""
+    gm = PATHB_GEOM[geom]
+    Ny, Nx, Cf = gm["Ny"], gm["Nx"], gm["Cf"]
     rng = np.random.default_rng(5)
-    rng_pc = [0, -25.6, -3, 51.2, 25.6, 2]
-    xyz_np, cnt_np = make_points(2, 4000, 11, spread=1.0)
+    rng_pc = gm["pc_range"]
+    xyz_np, cnt_np = make_points(2, 4000, 11, H=Ny, W=Nx, spread=1.0)
     N = xyz_np.shape[0]
-    pf_np = rng.normal(size=(N, 29)).astype(np.float32)
-    m = po.PillarMaxPooling([35, 32], 0.16, rng_pc).to(cuda).eval()
+    pf_np = rng.normal(size=(N, Cf)).astype(np.float32)
+    m = po.PillarMaxPooling([Cf + 6, 32], 0.16, rng_pc).to(cuda).eval()
+    assert (m.bev_width, m.bev_height) == (Ny, Nx)
     with torch.no_grad():
         m.shared_mlps[1].running_mean.normal_(); m.shared_mlps[1].running_var.uniform_(0.5, 2.0)
         xyz, cnt, pf = torch.from_numpy(xyz_np).to(cuda), torch.from_numpy(cnt_np).to(cuda), torch.from_numpy(pf_np).to(cuda)
         res = m(xyz, cnt, pf)
         feats, pillars, shape, B = res if isinstance(res, tuple) else (res.features, res.indices, res.spatial_shape, res.batch_size)
-        ref = pb.gen_indice_pairs_flat(xyz_np, cnt_np, 0.16, 320, 320)
-        assert np.array_equal(pillars.cpu().numpy(), ref["pillars"]) and tuple(shape) == (320, 320) and B == 2
+        ref = pb.gen_indice_pairs_flat(xyz_np, cnt_np, 0.16, Ny, Nx)
+        assert np.array_equal(pillars.cpu().numpy(), ref["pillars"]) and tuple(shape) == (Ny, Nx) and B == 2
+        # the indices fit the shape the tensor is wrapped with: y < shape[0], x < shape[1] (and both extremes are reached)
+        assert int(pillars[:, 1].max()) < shape[0] and int(pillars[:, 2].max()) < shape[1]
+        assert Ny == Nx or int(pillars[:, 1].max()) >= Nx          # a transposed (Nx, Ny) shape could not hold these rows
+        assert tuple(m.pillar_bev_indices.shape) == (2, Ny, Nx)
         pi = torch.from_numpy(ref["point_set_indices"]).long().to(cuda)
         qi = torch.from_numpy(ref["pillar_set_indices"]).long().to(cuda)
         centers = torch.zeros((ref["M"], 3), device=cuda)
         P = torch.from_numpy(ref["pillars"]).to(cuda)
-        centers[:, 0] = (P[:, 2] + 0.5) * 0.16; centers[:, 1] = (P[:, 1] + 0.5) * 0.16; centers[:, 2] = (2 + -3) / 2
+        centers[:, 0] = (P[:, 2] + 0.5) * 0.16; centers[:, 1] = (P[:, 1] + 0.5) * 0.16; centers[:, 2] = (rng_pc[5] + rng_pc[2]) / 2
         gfeat = torch.cat([pf[pi], xyz[pi], xyz[pi] - centers[qi]], dim=1)
         h = m.shared_mlps(gfeat)
         exp = torch.zeros((ref["M"], 32), device=cuda)
@@ -216,21 +233,31 @@ def test_split_encode_large_and_dropped_rows(cuda, dataset, Fin, Fout):
     assert xyz.shape[0] == n and np.array_equal(feat.cpu().numpy().view(np.uint32), ref2[2][:n].view(np.uint32))
 
 
-def test_dynamic_pillar_feature_net_reader(cuda):
-    """The module mirror end to end: collated points in, the reader's (features, pillars, shape, B) out; both input forms agree."""
-    d = np.load(os.path.join(ROOT, "tests", "golden", "split_vod.npz"))
+@pytest.mark.parametrize("geom", ["vod", "tj4d"])
+def test_dynamic_pillar_feature_net_reader(cuda, geom):
+    """The module mirror end to end: collated points in, the reader's (features, pillars, shape, B) out; both input forms agree.
+    TJ4D: 18 -> 31 'split' columns, 31 + 6 -> 32 reader, non-square (496, 432) shape."""
+    gm = PATHB_GEOM[geom]
+    d = np.load(os.path.join(ROOT, "tests", "golden", f"split_{geom}.npz"))
+    nb = len(d["xyz_batch_cnt"])
     torch.manual_seed(0)
-    net = po.DynamicPillarFeatureNet(num_input_features=29, num_filters=[32], pillar_size=0.16, virtual=True,
-                                     pc_range=[0, -25.6, -3, 51.2, 25.6, 2], encoding_type="split", dataset="vod").to(cuda).eval()
-    assert "pfn_layers.shared_mlps.0.weight" in net.state_dict() and net.state_dict()["pfn_layers.shared_mlps.0.weight"].shape == (32, 35)
+    net = po.DynamicPillarFeatureNet(num_input_features=gm["Cf"], num_filters=[32], pillar_size=0.16, virtual=True,
+                                     pc_range=gm["pc_range"], encoding_type="split", dataset=geom).to(cuda).eval()
+    assert "pfn_layers.shared_mlps.0.weight" in net.state_dict()
+    assert net.state_dict()["pfn_layers.shared_mlps.0.weight"].shape == (32, gm["Cf"] + 6)
     pts = torch.from_numpy(d["points"]).to(cuda)
     with torch.no_grad():
-        a = net(dict(points=pts, batch_size=3))
-        frames = [pts[pts[:, 0] == i][:, 1:] for i in range(3)]
+        a = net(dict(points=pts, batch_size=nb))
+        frames = [pts[pts[:, 0] == i][:, 1:] for i in range(nb)]
         b = net(dict(points=frames))
-    fa, pa = (a.features, a.indices) if hasattr(a, "features") else (a[0], a[1])
+    fa, pa, sa = (a.features, a.indices, a.spatial_shape) if hasattr(a, "features") else (a[0], a[1], a[2])
     fb, pb_ = (b.features, b.indices) if hasattr(b, "features") else (b[0], b[1])
     assert torch.equal(fa, fb) and torch.equal(pa, pb_) and fa.shape[1] == 32 and pa.shape[1] == 3
+    assert tuple(sa) == (gm["Ny"], gm["Nx"])
+    assert int(pa[:, 1].max()) < sa[0] and int(pa[:, 2].max()) < sa[1] and int(pa[:, 0].max()) < nb
+    # the reader's pillar list against the numpy restatement of the reference's index generation on the fixture's own xyz
+    ref = pb.gen_indice_pairs_flat(d["xyz"], d["xyz_batch_cnt"], 0.16, gm["Ny"], gm["Nx"])
+    assert np.array_equal(pa.cpu().numpy(), ref["pillars"])
 
 
 @pytest.mark.parametrize("Cf,dataset", [(29, "vod"), (31, "tj4d"), (7, "vod")])

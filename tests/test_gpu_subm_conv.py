@@ -246,17 +246,20 @@ def test_encoder_conv2_against_oracle_and_cudnn(cuda):
     assert (one - ref).abs().max().item() <= TOL * max(1.0, ref.abs().max().item())
 
 
-def test_reader_to_conv1_conv2_to_dense_end_to_end(cuda):
+@pytest.mark.parametrize("geom", ["vod", "tj4d"])
+def test_reader_to_conv1_conv2_to_dense_end_to_end(cuda, geom):
     """Path B behind the reader: PillarMaxPooling (native) -> conv1 -> conv2 on the pillar list -> dense [B,64,H/2,W/2], against the
-    dense torch composition of the same modules (cuDNN fp32) fed with the reader's densified output."""
+    dense torch composition of the same modules (cuDNN fp32) fed with the reader's densified output.  TJ4D = the non-square
+    432 x 496 grid of hgsfusion_tj4d.yaml: spatial_shape must come out as (Ny, Nx) = (496, 432) (pillar_modules.py:82)."""
     import torch.nn.functional as F
-    from test_gpu_pillarnet import make_points
+    from test_gpu_pillarnet import PATHB_GEOM, make_points
+    gm = PATHB_GEOM[geom]
     rng = np.random.default_rng(31)
-    xyz, cnt = make_points(2, 4000, seed=3)
+    xyz, cnt = make_points(2, 4000, seed=3, H=gm["Ny"], W=gm["Nx"])
     N = xyz.shape[0]
-    feat = rng.normal(size=(N, 29)).astype(np.float32)
+    feat = rng.normal(size=(N, gm["Cf"])).astype(np.float32)
     torch.manual_seed(2)
-    reader = po.PillarMaxPooling([35, 32], 0.16, [0, -25.6, -3, 51.2, 25.6, 2]).to(cuda).eval()
+    reader = po.PillarMaxPooling([gm["Cf"] + 6, 32], 0.16, gm["pc_range"]).to(cuda).eval()
     c1, c2 = po.PillarEncoderConv1(32).to(cuda).eval(), po.PillarEncoderConv2(32, 64).to(cuda).eval()
     for mod in (reader, c1, c2):
         for m in mod.modules():
@@ -266,10 +269,12 @@ def test_reader_to_conv1_conv2_to_dense_end_to_end(cuda):
         out = reader(torch.from_numpy(xyz).to(cuda), torch.from_numpy(cnt).to(cuda), torch.from_numpy(feat).to(cuda))
         pf, pillars, (H, W), B = out if isinstance(out, tuple) else (out.features, out.indices, out.spatial_shape, out.batch_size)
         bev = reader.pillar_bev_indices
+        assert (H, W) == (gm["Ny"], gm["Nx"])
         assert bev is not None and tuple(bev.shape) == (B, H, W)
         x1 = c1(pf, pillars, bev)
         x2, p2, bev2 = c2(x1, pillars, bev)
         got = po.sparse_to_dense(x2, p2, (bev2.shape[1], bev2.shape[2]), B)
+        assert tuple(got.shape) == (B, 64, (H + 1) // 2, (W + 1) // 2)
         # dense composition
         old = torch.backends.cudnn.allow_tf32
         torch.backends.cudnn.allow_tf32 = False
