@@ -51,9 +51,9 @@ int64_t hgsf_pillar_capacity(const hgsf_geometry *g, int64_t n, int32_t B, int32
 
 int hgsf_workspace_size(const hgsf_geometry *g, int64_t n, int32_t B, int32_t F, size_t *bytes) {
     if (!geom_ok(g) || !bytes || n < 0 || B <= 0 || F < 3) return HGSF_ERR_INVALID_ARG;
-    const int64_t cells = (int64_t)g->grid[0] * g->grid[1] * g->grid[2];
-    if (cells * B > INT_MAX || n > INT_MAX) return HGSF_ERR_UNSUPPORTED;
-    *bytes = workspace_layout(n, B, cells, F).total;
+    const WorkspaceLayout w = workspace_layout(n, B, g->grid[0], g->grid[1], g->grid[2], F);
+    if (w.cells * B > INT_MAX || n > INT_MAX) return HGSF_ERR_UNSUPPORTED;
+    *bytes = w.total;
     return HGSF_OK;
 }
 
@@ -68,33 +68,43 @@ static int run_path(const hgsf_geometry *g, const hgsf_points *pt, const hgsf_pf
     if (P <= 0 || max_voxels < 0) return HGSF_ERR_INVALID_ARG;
     if (!out->voxel_coords || !out->voxel_num_points || !out->num_pillars) return HGSF_ERR_INVALID_ARG;
     if (P > 32) return HGSF_ERR_UNSUPPORTED;           // one warp orders a pillar: at most 32 slots
-    const int64_t cells = (int64_t)g->grid[0] * g->grid[1] * g->grid[2];
+    const WorkspaceLayout w = workspace_layout(pt->n, pt->batch_size, g->grid[0], g->grid[1], g->grid[2], pt->num_features);
+    const int64_t cells = w.cells;                     // table entries per frame (row pitch padded to 32)
     if (cells * pt->batch_size > INT_MAX || pt->n > INT_MAX) return HGSF_ERR_UNSUPPORTED;
     if (pt->batch_size > 32767 || g->grid[0] > 65535 || g->grid[1] > 65535 || g->grid[2] > 65535) return HGSF_ERR_UNSUPPORTED;
     if (out->pillar_capacity < hgsf_pillar_capacity(g, pt->n, pt->batch_size, max_voxels)) return HGSF_ERR_INVALID_ARG;
-    const WorkspaceLayout w = workspace_layout(pt->n, pt->batch_size, cells, pt->num_features);
     if (ws_bytes < w.total || (reinterpret_cast<uintptr_t>(ws) & 255)) return HGSF_ERR_WORKSPACE;
 
     PathParams p{};
     p.pts = pt->data; p.n = (int)pt->n; p.stride = pt->stride; p.xyz_col = pt->xyz_col; p.F = pt->num_features;
     p.batch_col = pt->batch_col; p.frame_offsets_in = pt->frame_offsets; p.B = pt->batch_size;
     for (int j = 0; j < 3; ++j) { p.rmin[j] = g->pc_range[j]; p.vsize[j] = g->voxel_size[j]; p.voff[j] = g->centre_off[j]; }
-    p.nx = g->grid[0]; p.ny = g->grid[1]; p.nz = g->grid[2]; p.cells = (int)cells;
+    p.nx = g->grid[0]; p.ny = g->grid[1]; p.nz = g->grid[2]; p.nxp = w.nxp; p.cells = (int)cells;
+    p.tiles_per_row = w.nxp / 32;
+    p.div_cells = make_fastdiv((uint32_t)cells); p.div_plane = make_fastdiv((uint32_t)(p.ny * p.nxp));
+    p.div_nxp = make_fastdiv((uint32_t)p.nxp); p.div_tpr = make_fastdiv((uint32_t)p.tiles_per_row);
+    p.div_ny = make_fastdiv((uint32_t)p.ny);
     p.P = P; p.max_voxels = max_voxels;
     uint8_t *base = static_cast<uint8_t *>(ws);
     p.ticket = reinterpret_cast<uint32_t *>(base + w.off_ticket);
-    p.scan_desc = reinterpret_cast<uint64_t *>(base + w.off_desc);
+    p.state = reinterpret_cast<uint64_t *>(base + w.off_state);
+    // "the table is clean" is only meaningful for the same table: tie the mark to its place and size
+    p.magic = 0x48475346c1ea9e5bull ^ ((uint64_t)w.cell_array_bytes * 0x9E3779B97F4A7C15ull) ^ (uint64_t)w.off_table;
+    p.scan_desc = reinterpret_cast<uint32_t *>(base + w.off_desc);
     p.frame_raw_base = reinterpret_cast<int32_t *>(base + w.off_raw_base);
     p.cell_tag = reinterpret_cast<uint32_t *>(base + w.off_table);
     p.cell_cnt = reinterpret_cast<uint32_t *>(base + w.off_table + w.cell_array_bytes);
     p.cell_start = reinterpret_cast<uint32_t *>(base + w.off_table + 2 * w.cell_array_bytes);
-    p.table_bytes = 3 * w.cell_array_bytes;
+    p.table_bytes = 2 * w.cell_array_bytes;
+    p.tile_rec = reinterpret_cast<uint4 *>(base + w.off_tile_rec);
+    p.frame_done = reinterpret_cast<uint32_t *>(base + w.off_frame_done);
     p.frame_offsets = pt->frame_offsets ? const_cast<int32_t *>(pt->frame_offsets)
                                         : reinterpret_cast<int32_t *>(base + w.off_frame_offsets);
     p.key = reinterpret_cast<int32_t *>(base + w.off_key);
     p.arrival = reinterpret_cast<uint32_t *>(base + w.off_arrival);
     p.sorted_rows = reinterpret_cast<float *>(base + w.off_sorted_rows);
-    p.prec = reinterpret_cast<int4 *>(base + w.off_prec);
+    p.pil = reinterpret_cast<int4 *>(base + w.off_pil);
+    p.featT = reinterpret_cast<float *>(base + w.off_featT);
     p.RW = w.RW;
     p.coords = out->voxel_coords; p.num = out->voxel_num_points; p.num_pillars = out->num_pillars;
     p.voxels = out->voxels;
@@ -113,8 +123,7 @@ static int run_path(const hgsf_geometry *g, const hgsf_points *pt, const hgsf_pf
         p.Cin = cin; p.C = pfn->out_channels;
         p.feats = out->pillar_features; p.canvas = out->spatial_features;
     }
-    return launch_pillar_path(p, pfn != nullptr, abs_xyz, dist, w.zero_bytes, base, static_cast<cudaStream_t>(stream),
-                              &g_last_launches);
+    return launch_pillar_path(p, pfn != nullptr, abs_xyz, dist, static_cast<cudaStream_t>(stream), &g_last_launches);
 }
 
 int hgsf_pillarize(const hgsf_geometry *g, const hgsf_points *pt, int32_t P, int32_t max_voxels, void *ws,

@@ -17,6 +17,6 @@ for mode in ("uniform", "clustered"):
     torch.cuda.synchronize()
     ws = path._ws
     base = (ws.data_ptr() + 255) // 256 * 256 - ws.data_ptr()
-    st = ws[base + 256 + 8 * 4000: base + 256 + 8 * 4008].view(torch.int64).cpu().numpy()
-    t0, t1, t2, t3, t4, t5, t6, t7 = [int(v) for v in st]
-    print(mode, f"ns: zero {t1-t0} count {t2-t1} pt-reduce {t7-t2} cell-reduce+sync {t3-t7} pt-apply {t6-t3} cell-apply+sync {t4-t6} fill {t5-t4} total {t5-t0}")
+    st = ws[base + 4 * 96: base + 4 * 96 + 8 * 6].view(torch.int64).cpu().numpy()      # k_front's stamps live at ticket[96..]
+    t0, t1, t2, t3, t4, t5 = [int(v) for v in st]
+    print(mode, f"ns: zero(skipped when clean) {t1-t0} count+sync {t2-t1} reduce+sync {t3-t2} apply+sync {t4-t3} fill {t5-t4} total {t5-t0}")

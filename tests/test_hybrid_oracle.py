@@ -47,11 +47,24 @@ def test_reference_quirks_are_kept():
                                      rng.normal(0, 1, (4, 16)).astype(np.float32), dataset="tj4d")
 
 
-def test_range_mask_compares_in_double():
-    # float32(25.6) > 25.6, float32(-25.6) < -25.6 and float32(51.2) > 51.2 as doubles: all three boundary points fall outside
-    # (common_utils.py:78-81 on the float64 array), where a float32 compare would keep them; one step inside is kept
-    real = np.zeros((4, 7), np.float32)
+def test_range_mask_limits_are_float32():
+    # The reference masks the float64 point array against DatasetTemplate.point_cloud_range = np.array(..., dtype=np.float32)
+    # (dataset.py:26, data_processor.py:83-85, common_utils.py:78-81): the limits are float32(25.6), float32(-25.6),
+    # float32(51.2), widened exactly, and the compare is inclusive -- points exactly on them are kept, one ulp beyond is dropped.
+    real = np.zeros((6, 7), np.float32)
     real[0, 1] = np.float32(25.6); real[1, 1] = np.float32(-25.6); real[2, 0] = np.float32(51.2)
     real[3, 0] = np.nextafter(np.float32(51.2), np.float32(0))
+    real[4, 0] = np.nextafter(np.float32(51.2), np.float32(100))          # outside
+    real[5, 1] = np.nextafter(np.float32(-25.6), np.float32(-100))        # outside
     p = hybrid_oracle.assemble_frame(real, None, None, use_virtual=False, pc_range=[0, -25.6, -3, 51.2, 25.6, 2])
-    assert len(p) == 1 and p[0, 0] == real[3, 0]
+    assert len(p) == 4 and np.array_equal(p, real[:4])
+    # the same through the reference's own statement
+    import ast
+    src = open("/root/reference/pcdet/utils/common_utils.py").read() if __import__("os").path.exists("/root/reference") else None
+    if src is not None:
+        tree = ast.parse(src)
+        fn = next(n for n in ast.walk(tree) if isinstance(n, ast.FunctionDef) and n.name == "mask_points_by_range")
+        ns = {"np": np}
+        exec(compile(ast.Module(body=[fn], type_ignores=[]), "common_utils.py", "exec"), ns)
+        m = ns["mask_points_by_range"](real.astype(np.float64), np.array([0, -25.6, -3, 51.2, 25.6, 2], dtype=np.float32))
+        assert m.tolist() == [True, True, True, True, False, False]
