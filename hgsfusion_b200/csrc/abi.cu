@@ -97,14 +97,12 @@ static int run_path(const hgsf_geometry *g, const hgsf_points *pt, const hgsf_pf
     p.cell_start = reinterpret_cast<uint32_t *>(base + w.off_table + 2 * w.cell_array_bytes);
     p.table_bytes = 2 * w.cell_array_bytes;
     p.tile_rec = reinterpret_cast<uint4 *>(base + w.off_tile_rec);
-    p.frame_done = reinterpret_cast<uint32_t *>(base + w.off_frame_done);
     p.frame_offsets = pt->frame_offsets ? const_cast<int32_t *>(pt->frame_offsets)
                                         : reinterpret_cast<int32_t *>(base + w.off_frame_offsets);
     p.key = reinterpret_cast<int32_t *>(base + w.off_key);
     p.arrival = reinterpret_cast<uint32_t *>(base + w.off_arrival);
     p.sorted_rows = reinterpret_cast<float *>(base + w.off_sorted_rows);
     p.pil = reinterpret_cast<int4 *>(base + w.off_pil);
-    p.featT = reinterpret_cast<float *>(base + w.off_featT);
     p.RW = w.RW;
     p.coords = out->voxel_coords; p.num = out->voxel_num_points; p.num_pillars = out->num_pillars;
     p.voxels = out->voxels;

@@ -192,7 +192,6 @@ __global__ void __launch_bounds__(FRONT_THREADS, 4) k_front(const PathParams p) 
     // ---- phase 0: zero the cell table, unless the previous call's consumer kernel left it clean ----
     const bool clean = (ld_volatile_u64(p.state) == p.magic);        // grid-uniform: nobody writes p.state before the first barrier
     if (cta == 0 && tid == 0) { p.ticket[0] = 0u; p.ticket[32] = 0u; p.ticket[64] = 0u; }
-    if (cta == 0) for (int b = tid; b < p.B; b += FRONT_THREADS) p.frame_done[b] = 0u;
     if (!clean) {
         uint4 *t4 = reinterpret_cast<uint4 *>(p.cell_tag);           // tag, cnt: two arrays back to back
         const long long n4 = (long long)(p.table_bytes >> 4);
@@ -522,33 +521,36 @@ __device__ __noinline__ int select_first32(const float *__restrict__ idx0, int s
 }
 
 // ---- k_pillars ------------------------------------------------------------------------------------
-// The consumer of k_front's tables: ONE persistent kernel whose warps play two roles.
-//
-//   PILLAR role (latency / FMA bound).  A warp takes a CHUNK of 32 consecutive pillars of one frame in CELL order (k_front's
-//   pillar list).  Lane j OWNS pillar j for the bookkeeping -- every lane is busy, unlike a tile-major walk where most cells
-//   are empty -- : voxel_coords / voxel_num_points, ordering by point index, first P kept, mean in torch's summation order.
-//   Because the CSR is in cell order too, the chunk's point rows are ONE contiguous span of sorted_rows: staged with a single
-//   cooperative cp.async copy, issued a chunk ahead from list entries loaded two chunks ahead.  The arithmetic is cut into
-//   UNITS of (pillar, 4 output channels): lane l always computes channels 4*(l&15)..+3, so its Linear weights (packed pairs, one
-//   FFMA2 per channel pair and input feature) and BatchNorm constants stay in REGISTERS for the whole kernel (CUDA-core FMA: a
-//   13x64 contraction is far below a tensor-core tile).  Single-point pillars are paired across the half-warps; a multi-point
-//   pillar is taken by both halves, which split its points and max-combine.  Results go to pillar_features[f] (f = first-seen
-//   id) and, channel major, into the chunk's 8 KB FEATURE BLOCK [64][32] (built in shared memory, written out coalesced).
-//
-//   CANVAS role (HBM-write bound).  A warp takes 8 consecutive canvas tiles (32 cells of one BEV row x 64 channels) and writes
-//   them with plain coalesced 16-byte stores, zeros included -- the canvas is written exactly once.  A tile's record {pillars
-//   before it, occupancy mask} says which cells hold a pillar and where its features sit in the feature blocks (L2 hits: the
-//   blocks were written moments ago).  ~190 instructions per tile, nothing to balance, a pure stream.
-//
-//   A frame's tiles may be written once all of its chunks are complete (a per-frame counter, release / acquire).  One warp in
-//   four prefers the canvas role; the others prefer pillars and switch when the chunks run out.  A canvas warp whose next frame
-//   is not complete yet does pillar chunks meanwhile, so nobody ever waits while unclaimed work exists (no deadlock: whoever
-//   claimed a chunk is running and will finish it).  The two roles overlap on every SM: the stores stream while the FMA chains
-//   of the other warps wait on their latencies.
+// The consumer of k_front's tables: one persistent kernel of autonomous warps.
+//   A warp takes a RUN of consecutive 32-cell tiles of the cell table (one global ticket, fetched a run ahead; the tiles'
+//   records {first CSR row, rows, pillars before the tile, occupancy mask} likewise) and cuts it into GROUPS of whole
+//   tiles holding at most 32 pillars.  Per group:
+//     * lane j OWNS pillar j (k_front's pillar list is in cell order, so the group's pillars are consecutive entries):
+//       voxel_coords / voxel_num_points, ordering by point index, first P kept, mean in torch's summation order.  The CSR is in
+//       cell order too: the group's point rows are ONE contiguous span of sorted_rows, staged with a single cooperative cp.async
+//       copy issued a group ahead;
+//     * the arithmetic is cut into UNITS of (pillar, 4 output channels): lane l always computes channels 4*(l&15)..+3, so its
+//       Linear weights (packed pairs, one FFMA2 per channel pair and input feature) and BatchNorm constants stay in REGISTERS for
+//       the whole kernel (CUDA-core FMA: a 13x64 contraction is far below a tensor-core tile).  Single-point pillars are paired
+//       across the half-warps; a multi-point pillar is taken by both halves, which split its points and max-combine.  Results go
+//       to pillar_features[f] (f = first-seen id) and, channel major, into the warp's feature block [64][32] in shared memory;
+//     * the warp then writes the group's canvas tiles itself (64 channels x 32 cells each, zeros included: the canvas is written
+//       exactly once): lane = (4 cells, 4 channel rows), values picked out of the feature block by the tile's occupancy mask,
+//       coalesced 16-byte streaming stores -- no second pass over the features, no hand-shake between warps.
+//   Runs are short (2 tiles, 1 in the last quarter of the table): the tiles in flight on the 1776 warps then form a compact window
+//   moving through the canvas, which the L2 -> DRAM write-back rewards (measured, VoD clustered, us per launch at 1 / 2 / 4 / 8 /
+//   16 tiles per run: 163 / 149 / 150 / 166 / 202), and the last runs handed out are short, so the warps finish together.
 constexpr int PW = 4;                 // warps per CTA
 constexpr int PT = PW * 32;
 constexpr int SMALL_CNT = 6;          // up to this many arrivals the owning lane ranks them itself
-constexpr int CT = 8;                 // canvas tiles per canvas ticket
+#ifndef HGSF_RUN_TILES
+#define HGSF_RUN_TILES 2
+#endif
+constexpr int CT = HGSF_RUN_TILES;    // tiles per run (= per global ticket), at most 32
+#ifndef HGSF_RUN_TILES_TAIL
+#define HGSF_RUN_TILES_TAIL 1
+#endif
+constexpr int CT_TAIL = HGSF_RUN_TILES_TAIL;   // ... for the last quarter of the table
 
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)
@@ -563,11 +565,16 @@ __device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t *p) {
     return v;
 }
 
-struct Chunk {
-    int b;        // frame, -1 = no chunk
-    int slot0;    // first pillar (cell order, frames concatenated)
-    int nvalid;   // pillars in the chunk (< 32 only for the last chunk of a frame)
-    int cid;      // global chunk id = index of its feature block
+struct Run {          // consecutive tiles of the cell table
+    int t0, nt;       // first tile, tiles (0 = none)
+    uint4 rec;        // lane i < nt: record of tile t0 + i
+};
+struct Group {        // whole tiles of one run holding at most 32 pillars
+    int t_a, nt;      // first tile, tiles (0 = none)
+    int slotA, npil;  // first pillar (cell order, frames concatenated), pillars
+    int rowA, nrows;  // first CSR row, rows
+    unsigned tmask;   // lane i < nt: occupancy mask of tile t_a + i ...
+    int tcol;         // ... and the block column of its first pillar
 };
 
 #ifndef HGSF_PILLARS_MINB
@@ -589,7 +596,6 @@ __global__ void __launch_bounds__(PT, HGSF_PILLARS_MINB) k_pillars(const PathPar
     float *stage_all = blk_all + (CANVAS ? PW * BLK : 0);                                   // [PW][2][SW * RWc]  (PFN)
     int *s_R = reinterpret_cast<int *>(stage_all + (PFN ? PW * 2 * SW * RWc : 0));          // [B+1] raw pillar base per frame
     int *s_K = s_R + (p.B + 1);                                                             // [B+1] kept (final) pillar base per frame
-    int *s_CB = s_K + (p.B + 1);                                                            // [B+1] chunk base per frame
     __shared__ float4 s_rec_all[PW][32][2];                        // work lists: singles from the front, multis from the back
     __shared__ unsigned char s_perm_all[PW][32][32];               // per pillar: arrival position of its rank-th point
     __shared__ int s_bperm_all[PW][32];                            // same for a pillar with > 32 arrivals
@@ -608,20 +614,17 @@ __global__ void __launch_bounds__(PT, HGSF_PILLARS_MINB) k_pillars(const PathPar
     if (CANVAS) for (int t = tid; t < PW * BLK; t += PT) blk_all[t] = 0.f;
     __syncthreads();
     if (tid == 0) {
-        int acc = 0, cb = 0;
+        int acc = 0;
         for (int b = 0; b < p.B; ++b) {
-            s_K[b] = acc; s_CB[b] = cb;
-            const int raw = s_R[b + 1] - s_R[b];
-            const int m = min(raw, p.max_voxels);
+            s_K[b] = acc;
+            const int m = min(s_R[b + 1] - s_R[b], p.max_voxels);
             if (blockIdx.x == 0) p.num_pillars[1 + b] = m;
             acc += m;
-            cb += (raw + 31) >> 5;
         }
-        s_K[p.B] = acc; s_CB[p.B] = cb;
+        s_K[p.B] = acc;
         if (blockIdx.x == 0) p.num_pillars[0] = acc;
     }
     __syncthreads();
-    const int n_chunks = s_CB[p.B];
 
     // this lane's 4 channels: Linear rows and BatchNorm constants, in registers for the whole kernel
     const int c0 = 4 * (lane & 15);
@@ -723,48 +726,77 @@ __global__ void __launch_bounds__(PT, HGSF_PILLARS_MINB) k_pillars(const PathPar
         tbase[3 * 32 + (((xs ^ 3) << 2) | xr)] = __int_as_float(v3);
     };
 
-    // ---- chunk hand-out: one global ticket per chunk of 32 pillars, fetched an iteration before it is decoded ----
+    // ---- run hand-out: one global ticket per run, fetched a run before it is used.  Guided sizes: the first three quarters
+    //      of the table go out in runs of CT tiles, the rest in runs of CT_TAIL.  [Measured and rejected: three tickets in flight
+    //      per warp (the same-address atomics queue three times as long: +6 %); the first half of the runs assigned round-robin
+    //      without tickets (the window of tiles in flight spreads: +16 %).] ----
+    const int n_tt = (int)(((long long)p.B * p.cells) >> 5);       // tiles of the cell table
+    const int n_big = (int)(((long long)n_tt * 3 / 4) / CT);       // runs of CT tiles
+    const int t_tail = n_big * CT;                                 // first tile of the short runs
+    const int n_runs = n_big + (n_tt - t_tail + CT_TAIL - 1) / CT_TAIL;
     unsigned tk_pending = 0u;            // lane 0: the ticket in flight
-    bool chunks_left = n_chunks > 0;     // warp-uniform: a ticket below n_chunks may still come
+    bool runs_left = n_runs > 0;         // warp-uniform: a ticket below n_runs may still come
     auto fetch_ticket = [&]() { if (lane == 0) tk_pending = atomicAdd(p.ticket, 1u); };
-    auto take_chunk = [&]() -> Chunk {
-        Chunk ck; ck.b = -1; ck.slot0 = 0; ck.nvalid = 0; ck.cid = 0;
-        if (!chunks_left) return ck;
+    auto take_run = [&]() -> Run {
+        Run r; r.t0 = 0; r.nt = 0; r.rec = make_uint4(0u, 0u, 0u, 0u);
+        if (!runs_left) return r;
         const int c = (int)__shfl_sync(FULL, tk_pending, 0);
-        if (c >= n_chunks) { chunks_left = false; return ck; }
+        if (c >= n_runs) { runs_left = false; return r; }
         fetch_ticket();
-        int lo = 0, hi = p.B;            // largest b with s_CB[b] <= c
-        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_CB[mid] <= c) lo = mid; else hi = mid; }
-        ck.b = lo; ck.cid = c;
-        ck.slot0 = s_R[lo] + ((c - s_CB[lo]) << 5);
-        ck.nvalid = min(32, s_R[lo + 1] - ck.slot0);
-        return ck;
+        if (c < n_big) { r.t0 = c * CT; r.nt = CT; }
+        else { r.t0 = t_tail + (c - n_big) * CT_TAIL; r.nt = min(CT_TAIL, n_tt - r.t0); }
+        if (lane < r.nt) r.rec = __ldg(p.tile_rec + r.t0 + lane);
+        return r;
     };
-    auto load_entry = [&](const Chunk &ck) -> int4 {
+    Run run_cur, run_nxt;
+    run_cur.t0 = run_cur.nt = 0; run_cur.rec = make_uint4(0u, 0u, 0u, 0u); run_nxt = run_cur;
+    int run_pos = 0;                     // next tile of run_cur that belongs to no group yet
+    // the next group: tiles of the current run from run_pos on, as many whole tiles as hold at most 32 pillars (a tile never
+    // holds more than 32, so at least one); moves on to the next run when this one is used up
+    auto next_group = [&]() -> Group {
+        Group g; g.t_a = 0; g.nt = 0; g.slotA = 0; g.npil = 0; g.rowA = 0; g.nrows = 0; g.tmask = 0u; g.tcol = 0;
+        if (run_pos >= run_cur.nt) {
+            run_cur = run_nxt; run_nxt = take_run(); run_pos = 0;
+            if (run_cur.nt == 0) return g;
+        }
+        const int a = run_pos;
+        const unsigned slot_after = run_cur.rec.z + (unsigned)__popc(run_cur.rec.w);     // pillars before the NEXT tile
+        const unsigned row_after = run_cur.rec.x + run_cur.rec.y;
+        const int slotA = (int)__shfl_sync(FULL, run_cur.rec.z, a);
+        const unsigned fits = __ballot_sync(FULL, lane >= a && lane < run_cur.nt && (int)slot_after - slotA <= 32);
+        const int nt = __popc(fits);                   // `fits` is a contiguous run of lanes starting at a
+        g.t_a = run_cur.t0 + a; g.nt = nt; g.slotA = slotA;
+        g.npil = (int)__shfl_sync(FULL, slot_after, a + nt - 1) - slotA;
+        g.rowA = (int)__shfl_sync(FULL, run_cur.rec.x, a);
+        g.nrows = (int)__shfl_sync(FULL, row_after, a + nt - 1) - g.rowA;
+        // lane i < nt keeps what the tile writer needs of tile a + i
+        const int srcl = min(a + lane, 31);
+        g.tmask = __shfl_sync(FULL, run_cur.rec.w, srcl);
+        g.tcol = (int)__shfl_sync(FULL, run_cur.rec.z, srcl) - slotA;
+        if (lane >= nt) { g.tmask = 0u; g.tcol = 0; }
+        run_pos = a + nt;
+        return g;
+    };
+    auto load_entry = [&](const Group &g) -> int4 {
         int4 e = make_int4(0, 0, 0, 0);
-        if (lane < ck.nvalid) e = __ldg(p.pil + ck.slot0 + lane);
+        if (lane < g.npil) e = __ldg(p.pil + g.slotA + lane);
         return e;
     };
-    // the chunk's rows are sorted_rows[first, last): one cooperative async copy of (at most SW of) them
-    auto issue_stage = [&](const Chunk &ck, const int4 e, float *stg) {
+    // the group's rows are sorted_rows[rowA, rowA + nrows): one cooperative async copy of (at most SW of) them
+    auto issue_stage = [&](const Group &g, float *stg) {
         if (PFN) {
-            int total = 0, first = 0;
-            if (ck.nvalid > 0) {
-                first = __shfl_sync(FULL, e.w, 0);
-                total = __shfl_sync(FULL, e.w + e.z, ck.nvalid - 1) - first;
-            }
-            const int pieces = min(total, SW) * NV;
-            const float *src = grows + (size_t)first * RWc;
+            const int pieces = min(g.nrows, SW) * NV;
+            const float *src = grows + (size_t)g.rowA * RWc;
             for (int c = lane; c < pieces; c += 32) cp_async16(stg + 4 * c, src + 4 * c);
             cp_async_commit();
         }
     };
 
-    // ---- one chunk of 32 pillars ----
-    auto process = [&](const Chunk &ck, const int4 e, const float *stg) {
-        const int b = ck.b;
-        const bool valid = lane < ck.nvalid;
+    // ---- the pillars of one group (all of one frame when there is a canvas; without one a group may straddle frames) ----
+    auto process = [&](const Group &g, const int4 e, const float *stg) {
+        const bool valid = lane < g.npil;
         const int key = e.x, cnt = e.z, start = e.w;
+        const int b = (int)fastdiv((uint32_t)key, p.div_cells);
         const int local = e.y - s_R[b];
         const bool kept = valid && (local < maxv);            // pillars beyond max_voxels were never created
         const int f = s_K[b] + local;                          // final pillar id (first-seen order, frames concatenated)
@@ -780,17 +812,13 @@ __global__ void __launch_bounds__(PT, HGSF_PILLARS_MINB) k_pillars(const PathPar
         // every pillar is visited exactly once: leave its table entry zero for the next call's k_front
         if (valid) { p.cell_cnt[key] = 0u; p.cell_tag[key] = 0u; }
         fcol[lane] = kept ? f : -1;
-        const int first = __shfl_sync(FULL, start, 0);
-        const int rel0 = start - first;
+        const int rel0 = start - g.rowA;
         const bool staged = PFN && kept && cnt <= 32 && rel0 + cnt <= SW;
         const int rel = staged ? rel0 : (-1 - start);         // where the pillar's rows are (see row_ptr)
         if (PFN) cp_async_wait<1>();     // this chunk's rows have landed (this lane's copies) ...
         __syncwarp();                    // ... and every other lane's
 #ifdef HGSF_EXPERIMENT
-        if (p.dbg & 1) {                 // timing only (WRONG results): no ordering / arithmetic, just the frame hand-shake
-            if (CANVAS) { __threadfence(); __syncwarp(); if (lane == 0) atomicAdd(p.frame_done + b, 1u); }
-            return;
-        }
+        if (p.dbg & 1) return;           // timing only (WRONG results): no ordering / arithmetic
 #endif
         // ---- order the pillar's points by input index ----
         if (kept && cnt > 1 && cnt <= SMALL_CNT) {
@@ -989,183 +1017,97 @@ __global__ void __launch_bounds__(PT, HGSF_PILLARS_MINB) k_pillars(const PathPar
                 }
             }
         }
-        // ---- the feature block goes out (coalesced 16-byte stores), then the frame's counter ----
-        if (CANVAS) {
-            __syncwarp();
-            float *dst = p.featT + (size_t)ck.cid * BLK;
-#pragma unroll
-            for (int i = 0; i < C / 4; ++i) {
-                const int row = 4 * i + (lane >> 3), q = lane & 7;
-                const float4 v = *reinterpret_cast<const float4 *>(blk + row * 32 + ((q ^ (row & 7)) << 2));
-                *reinterpret_cast<float4 *>(dst + row * 32 + 4 * q) = v;
-            }
-            __threadfence();             // every lane's block stores before the counter
-            __syncwarp();
-            if (lane == 0) atomicAdd(p.frame_done + b, 1u);
-        }
-        __syncwarp();   // rec / perm / fcol / blk are rewritten by the next chunk
+        __syncwarp();   // the feature block is complete; rec / perm / fcol are rewritten by the next group
     };
 
-    // ---- canvas role ----
+    // ---- the group's canvas tiles, out of the feature block.  lane -> cells 4*(lane&7)..+3 of the tile and channel rows
+    //      (lane>>3) + 4*q ----
     const int tiles_per_row = p.tiles_per_row;
-    const int n_tiles = CANVAS ? p.B * p.ny * tiles_per_row : 0;          // nz == 1 with a canvas (PointPillarScatter asserts it)
-    const int n_ctk = (n_tiles + CT - 1) / CT;
-    int ready_upto = 0;                  // frames below this one are known to be complete
-    auto frame_ready = [&](int b) -> bool {
-        while (ready_upto <= b) {
-            const uint32_t need = (uint32_t)(s_CB[ready_upto + 1] - s_CB[ready_upto]);
-            if (ld_acquire_u32(p.frame_done + ready_upto) < need) return false;
-            ++ready_upto;
-        }
-        return true;
-    };
-    // one tile: 64 channels x 32 cells.  lane -> cells 4*(lane&7)..+3 of the tile and channels (lane>>3) + 4*i.
-    // slot_before / mask = the tile's record: pillars (cell order, whole batch) before the tile, occupancy of its 32 cells
-    auto write_tile = [&](int b, int y, int xt, unsigned slot_before, unsigned mask) {
+    auto write_tiles = [&](const Group &g) {
         const int quad = lane & 7, cs = lane >> 3;
-        const int x = xt * 32 + 4 * quad;
-        if (p.canvas_vec) {
-            float *dst = p.canvas + (((size_t)b * C + cs) * p.ny + y) * p.nx + x;
-            const size_t plane4 = (size_t)4 * p.ny * p.nx;
-            if (mask == 0u) {
-                if (x < p.nx) {
-#pragma unroll
-                    for (int i = 0; i < C / 4; ++i) __stcs(reinterpret_cast<float4 *>(dst + i * plane4), make_float4(0.f, 0.f, 0.f, 0.f));
-                }
-                return;
-            }
-            // this lane's (up to 4) pillars: feature offset of column (chunk, j) = chunk*BLK + j, + channel*32
+        int r = (int)fastdiv((uint32_t)g.t_a, p.div_tpr), xt = g.t_a - r * tiles_per_row;
+        int b = (int)fastdiv((uint32_t)r, p.div_ny), y = r - b * p.ny;
+        const size_t plane4 = (size_t)4 * p.ny * p.nx;
+        for (int i = 0; i < g.nt; ++i) {
+            const unsigned mask = __shfl_sync(FULL, g.tmask, i);
+            const int col0 = __shfl_sync(FULL, g.tcol, i);
+            const int x = xt * 32 + 4 * quad;
             const unsigned bits = (mask >> (4 * quad)) & 0xFu;
-            int off[4];
-            {
-                int s = (int)slot_before - s_R[b] + __popc(mask & ((1u << (4 * quad)) - 1u));     // pillar index inside the frame (cell order)
-                const int cb = s_CB[b];
+            if (p.canvas_vec) {
+                float *dst = p.canvas + (((size_t)b * C + cs) * p.ny + y) * p.nx + x;
+                if (mask == 0u) {
+                    if (x < p.nx) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    off[k] = ((cb + (s >> 5)) * BLK) + (s & 31);
-                    s += (bits >> k) & 1u;
+                        for (int q = 0; q < C / 4; ++q) __stcs(reinterpret_cast<float4 *>(dst + q * plane4), make_float4(0.f, 0.f, 0.f, 0.f));
+                    }
+                } else {
+                    // block columns of this lane's (up to 4) pillars.  Channel row c = cs + 4q of column j sits at
+                    // blk[c*32 + ((((j>>2) ^ (c&7)) << 2) | (j&3))] and c&7 = cs + 4*(q&1): two base pointers per column (even / odd q),
+                    // then a compile-time offset q*128 per row.  Cell positions no quad of the tile occupies are skipped warp-wide.
+                    const int cc0 = col0 + __popc(mask & ((1u << (4 * quad)) - 1u));
+                    const float *rowbase = blk + cs * 32;
+                    float4 v[C / 4];
+#pragma unroll
+                    for (int q = 0; q < C / 4; ++q) v[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        if (mask & (0x11111111u << k)) {                     // warp-uniform
+                            if ((bits >> k) & 1u) {
+                                const int j = cc0 + __popc(bits & ((1u << k) - 1u));
+                                const float *pe = rowbase + ((((j >> 2) ^ cs) << 2) | (j & 3));
+                                const float *po = rowbase + ((((j >> 2) ^ (cs + 4)) << 2) | (j & 3));
+#pragma unroll
+                                for (int q = 0; q < C / 4; ++q) {
+                                    const float t = (q & 1) ? po[q * 128] : pe[q * 128];
+                                    if (k == 0) v[q].x = t; else if (k == 1) v[q].y = t; else if (k == 2) v[q].z = t; else v[q].w = t;
+                                }
+                            }
+                        }
+                    }
+                    if (x < p.nx) {
+#pragma unroll
+                        for (int q = 0; q < C / 4; ++q) __stcs(reinterpret_cast<float4 *>(dst + q * plane4), v[q]);
+                    }
+                }
+            } else {
+                // nx not a multiple of 4 (or a misaligned canvas): scalar stores, same mapping
+                int col[4];
+                {
+                    int cc = col0 + __popc(mask & ((1u << (4 * quad)) - 1u));
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) { col[k] = cc; cc += (bits >> k) & 1u; }
+                }
+                for (int q = 0; q < C / 4; ++q) {
+                    const int c = cs + 4 * q;
+                    float *dst = p.canvas + (((size_t)b * C + c) * p.ny + y) * p.nx;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (x + k < p.nx) dst[x + k] = ((bits >> k) & 1u) ? blk[swz128(c, col[k])] : 0.f;
                 }
             }
-            const float *src = p.featT + cs * 32;
-            // ALL of the tile's gathers are issued before the first store (one L2 round trip per tile); cell positions that no
-            // quad of the tile occupies are skipped warp-wide
-            float4 v[C / 4];
-#pragma unroll
-            for (int i = 0; i < C / 4; ++i) v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (mask & 0x11111111u) {
-                if (bits & 1u) {
-#pragma unroll
-                    for (int i = 0; i < C / 4; ++i) v[i].x = __ldcg(src + off[0] + i * 128);
-                }
-            }
-            if (mask & 0x22222222u) {
-                if (bits & 2u) {
-#pragma unroll
-                    for (int i = 0; i < C / 4; ++i) v[i].y = __ldcg(src + off[1] + i * 128);
-                }
-            }
-            if (mask & 0x44444444u) {
-                if (bits & 4u) {
-#pragma unroll
-                    for (int i = 0; i < C / 4; ++i) v[i].z = __ldcg(src + off[2] + i * 128);
-                }
-            }
-            if (mask & 0x88888888u) {
-                if (bits & 8u) {
-#pragma unroll
-                    for (int i = 0; i < C / 4; ++i) v[i].w = __ldcg(src + off[3] + i * 128);
-                }
-            }
-            if (x < p.nx) {
-#pragma unroll
-                for (int i = 0; i < C / 4; ++i) __stcs(reinterpret_cast<float4 *>(dst + i * plane4), v[i]);
-            }
-        } else {
-            // nx not a multiple of 4 (or a misaligned canvas): scalar stores, same mapping
-            const unsigned bits = (mask >> (4 * quad)) & 0xFu;
-            int off[4];
-            {
-                int s = (int)slot_before - s_R[b] + __popc(mask & ((1u << (4 * quad)) - 1u));
-                const int cb = s_CB[b];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    off[k] = ((cb + (s >> 5)) * BLK) + (s & 31);
-                    s += (bits >> k) & 1u;
-                }
-            }
-            const float *src = p.featT + cs * 32;
-            for (int i = 0; i < C / 4; ++i) {
-                float *dst = p.canvas + (((size_t)b * C + cs + 4 * i) * p.ny + y) * p.nx;
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    if (x + k < p.nx) dst[x + k] = ((bits >> k) & 1u) ? __ldcg(src + off[k] + i * 128) : 0.f;
-            }
+            if (++xt == tiles_per_row) { xt = 0; if (++y == p.ny) { y = 0; ++b; } }
         }
     };
 
-    // ---- the work loop ----
-#ifdef HGSF_EXPERIMENT
-    const int n_writers = (p.dbg >> 8) & 7 ? ((p.dbg >> 8) & 7) : 1;
-#else
-    const int n_writers = 1;
-#endif
-    bool writer = CANVAS && (warp < n_writers);   // prefers the canvas role while chunks are left
-    bool tiles_left = CANVAS && n_ctk > 0;        // a canvas ticket below n_ctk may still come
-    int t_base = 0, t_lo = 0, t_hi = 0;           // the canvas tiles this warp holds: [t_lo, t_hi) of the run starting at t_base
-    uint4 run_rec = make_uint4(0u, 0u, 0u, 0u);   // lane i: the record of tile t_base + i
-    unsigned ctk_pending = 0u;                    // lane 0: the canvas ticket in flight
-    bool ctk_fetched = false;
+    // ---- the work loop: the ticket and the records of the next run and the list entries + rows of the next group are in flight
+    //      while the current group is computed and written ----
     fetch_ticket();
-    Chunk ck_cur = take_chunk(), ck_nxt = take_chunk(), ck_nn;
-    int4 e_cur = load_entry(ck_cur), e_nxt = load_entry(ck_nxt), e_nn;
-    issue_stage(ck_cur, e_cur, stage);
-    int it = 0;
-    for (;;) {
-        if (CANVAS && (writer || ck_cur.b < 0)) {
-            // canvas role: take tiles while their frame is complete
-            if (t_lo == t_hi && tiles_left) {
-                if (!ctk_fetched) { if (lane == 0) ctk_pending = atomicAdd(p.ticket + 32, 1u); }
-                const int tk = (int)__shfl_sync(FULL, ctk_pending, 0);
-                ctk_fetched = false;
-                if (tk >= n_ctk) tiles_left = false;
-                else {
-                    t_base = t_lo = tk * CT; t_hi = min(t_lo + CT, n_tiles);
-                    run_rec = (lane < t_hi - t_base) ? __ldg(p.tile_rec + t_base + lane) : make_uint4(0u, 0u, 0u, 0u);
-                    if (lane == 0) ctk_pending = atomicAdd(p.ticket + 32, 1u);      // the next run's ticket, a run ahead
-                    ctk_fetched = true;
-                }
-            }
-            if (t_lo < t_hi) {
-                const int r0 = (int)fastdiv((uint32_t)t_lo, p.div_tpr);
-                const int fb = (int)fastdiv((uint32_t)r0, p.div_ny);
-                if (frame_ready(fb)) {
-                    // up to the end of the held run or of the frame (the next frame is checked on its own)
-                    const int fend = min(t_hi, (fb + 1) * p.ny * tiles_per_row);
-                    int y = r0 - fb * p.ny, xt = t_lo - r0 * tiles_per_row;
-                    for (; t_lo < fend; ++t_lo) {
-                        const unsigned sb = __shfl_sync(FULL, run_rec.z, t_lo - t_base), mk = __shfl_sync(FULL, run_rec.w, t_lo - t_base);
+    run_cur = take_run(); run_nxt = take_run();
+    Group g_cur = next_group(), g_nxt;
+    int4 e_cur = load_entry(g_cur), e_nxt;
+    issue_stage(g_cur, stage);
+    for (int it = 0; g_cur.nt > 0; ++it) {
+        g_nxt = next_group();
+        e_nxt = load_entry(g_nxt);
+        issue_stage(g_nxt, stage + (size_t)((it + 1) & 1) * SW * RWc);
+        if (g_cur.npil > 0) process(g_cur, e_cur, stage + (size_t)(it & 1) * SW * RWc);
 #ifdef HGSF_EXPERIMENT
-                        if (!(p.dbg & 2))
+        if (CANVAS && !(p.dbg & 2)) write_tiles(g_cur);
+#else
+        if (CANVAS) write_tiles(g_cur);
 #endif
-                        write_tile(fb, y, xt, sb, mk);
-                        if (++xt == tiles_per_row) { xt = 0; ++y; }
-                    }
-                    continue;
-                }
-            } else if (!tiles_left && ck_cur.b < 0) {
-                break;                                   // nothing left in either role
-            }
-            if (ck_cur.b < 0) { __nanosleep(200); continue; }   // chunks all claimed: whoever holds them will finish the frame
-        } else if (ck_cur.b < 0) {
-            break;                                       // no canvas: done when the chunks are
-        }
-        // pillar role: pipeline = list entries of the chunk after next, rows of the next chunk, then the current chunk
-        ck_nn = take_chunk();
-        e_nn = load_entry(ck_nn);
-        issue_stage(ck_nxt, e_nxt, stage + (size_t)((it + 1) & 1) * SW * RWc);
-        process(ck_cur, e_cur, stage + (size_t)(it & 1) * SW * RWc);
-        ck_cur = ck_nxt; ck_nxt = ck_nn; e_cur = e_nxt; e_nxt = e_nn;
-        ++it;
+        __syncwarp();   // the feature block is rewritten by the next group
+        g_cur = g_nxt; e_cur = e_nxt;
     }
     if (PFN) cp_async_wait<0>();
     mark_table_clean(p);
@@ -1236,13 +1178,12 @@ static int launch_pillars_t(const PathParams &p, cudaStream_t stream) {
     constexpr int SW = (RWc <= 8) ? 96 : 64;
     const bool canvas = PFN && p.canvas != nullptr;
     const size_t smem = (canvas ? sizeof(float) * PW * C * 32 : 0) + (PFN ? sizeof(float) * PW * 2 * SW * RWc : 0) +
-                        sizeof(int) * 3 * (size_t)(p.B + 1);
-    const long long n_tiles = canvas ? (long long)p.B * p.ny * p.tiles_per_row : 0;
-    const long long work_warps = ((long long)p.n + 31) / 32 + p.B + (n_tiles + CT - 1) / CT;     // upper bound on chunks + canvas tickets
+                        sizeof(int) * 2 * (size_t)(p.B + 1);
+    const long long n_runs = (((long long)p.B * p.cells >> 5) + CT_TAIL - 1) / CT_TAIL;    // upper bound
     const bool bn = p.bn_w != nullptr;
     auto go = [&](auto kern) -> int {
         int grid = 1;
-        const int st = launch_persistent(kern, PT, smem, (work_warps + PW - 1) / PW, stream, &grid);
+        const int st = launch_persistent(kern, PT, smem, (n_runs + PW - 1) / PW, stream, &grid);
         if (st != HGSF_OK) return st;
         kern<<<(unsigned)grid, PT, smem, stream>>>(p);
         return (int)cudaGetLastError();

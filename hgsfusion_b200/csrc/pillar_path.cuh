@@ -53,15 +53,12 @@ struct PathParams {
     size_t table_bytes;                // bytes of cell_tag + cell_cnt (the part that must be zero when k_front starts)
     uint4 *tile_rec;                   // [B*cells/32] per 32-cell tile: {CSR row of its first point, points in the tile,
                                        //   pillars (in cell order) before the tile, occupancy mask of its 32 cells}
-    uint32_t *frame_done;              // [B] pillar chunks of the frame whose feature blocks are complete (k_pillars)
     int32_t *frame_offsets;            // [B+1] (aliases frame_offsets_in when given)
     int32_t *key;                      // [n] cell key of each point, -1 = outside the grid
     uint32_t *arrival;                 // [n] unordered arrival rank of the point inside its cell
     float *sorted_rows;                // [n, RW] F features + point index of each point, grouped by cell (CSR in table order)
     int4 *pil;                         // [n] the pillars in CELL order (frames concatenated): {cell key, raw pillar id in first-seen
                                        //   order, arrivals, CSR start}
-    float *featT;                      // [chunks][C][32] pillar features of 32 consecutive cell-order pillars, channel major: what the
-                                       //   canvas writer gathers from (chunks are per frame: ceil(pillars of the frame / 32))
     int RW;
     int pslice, cslice;                // points / cells per k_front CTA (multiples of 32)
     int canvas_vec;                    // the canvas is written with 16-byte stores (nx % 4 == 0, aligned base)
@@ -76,8 +73,8 @@ struct PathParams {
 };
 
 struct WorkspaceLayout {
-    size_t off_ticket, off_state, off_desc, off_raw_base, off_frame_done, off_table, off_tile_rec;
-    size_t off_frame_offsets, off_key, off_arrival, off_sorted_rows, off_pil, off_featT;
+    size_t off_ticket, off_state, off_desc, off_raw_base, off_table, off_tile_rec;
+    size_t off_frame_offsets, off_key, off_arrival, off_sorted_rows, off_pil;
     size_t total, cell_array_bytes;
     int RW, nxp;
     int64_t cells;         // per frame, padded pitch
@@ -96,7 +93,6 @@ inline WorkspaceLayout workspace_layout(int64_t n, int B, int nx, int ny, int nz
     w.off_state = o;       o = align_up(o + 256, 256);
     w.off_desc = o;        o = align_up(o + sizeof(uint32_t) * 3 * MAX_FRONT_CTAS, 256);
     w.off_raw_base = o;    o = align_up(o + sizeof(int32_t) * (size_t)(B + 1), 256);
-    w.off_frame_done = o;  o = align_up(o + sizeof(uint32_t) * (size_t)(B + 1), 256);
     w.cell_array_bytes = align_up(sizeof(uint32_t) * ((size_t)B * (size_t)w.cells + 32), 256);
     w.off_table = o;       o = o + 3 * w.cell_array_bytes;
     w.off_tile_rec = o;    o = align_up(o + sizeof(uint4) * ((size_t)B * (size_t)w.cells / 32 + 1), 256);
@@ -105,8 +101,6 @@ inline WorkspaceLayout workspace_layout(int64_t n, int B, int nx, int ny, int nz
     w.off_arrival = o;     o = align_up(o + sizeof(uint32_t) * (size_t)n, 256);
     w.off_sorted_rows = o; o = align_up(o + sizeof(float) * (size_t)n * (size_t)w.RW, 256);
     w.off_pil = o;         o = align_up(o + sizeof(int4) * (size_t)n, 256);
-    // feature blocks: one 32-pillar block per chunk, at most ceil(n/32) + B chunks (every frame rounds up), C <= 64 channels
-    w.off_featT = o;       o = align_up(o + sizeof(float) * 64 * 32 * ((size_t)(n + 31) / 32 + (size_t)B), 256);
     w.total = o;
     return w;
 }

@@ -42,7 +42,7 @@ int main() {
     const size_t bytes = (size_t)B * C * ny * nx * 4;
     float4 *d; cudaMalloc(&d, bytes);
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-    for (int threads : {128, 256}) for (int per_sm : {4, 8, 16}) for (int pat = 0; pat < 4; ++pat) {
+    for (int threads : {128, 256}) for (int per_sm : {1, 2, 3, 4, 8, 16}) for (int pat = 0; pat < 4; ++pat) {
         const int grid = 148 * per_sm;
         for (int i = 0; i < 3; ++i) k_write<<<grid, threads>>>(d, B, C, ny, nx, pat);
         cudaEventRecord(e0);

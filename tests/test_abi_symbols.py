@@ -58,9 +58,8 @@ def test_capacity_and_workspace_queries():
     need = C.c_size_t(0)
     assert lib.hgsf_workspace_size(C.byref(g), 480000, 16, 7, C.byref(need)) == 0
     table = 16 * 320 * 320 * 12                       # tag, cnt, start per cell
-    # + tile records (16 B per 32 cells); per point: key, arrival, row, pillar-list entry; per potential pillar a 256-byte
-    # column of the channel-major feature blocks the canvas writer gathers from
-    assert table < need.value < table + 16 * 320 * 10 * 16 + 480000 * (4 + 4 + 32 + 16 + 256) + (1 << 20)
+    # + tile records (16 B per 32 cells); per point: key, arrival, row, pillar-list entry
+    assert table < need.value < table + 16 * 320 * 10 * 16 + 480000 * (4 + 4 + 32 + 16) + (1 << 20)
     assert lib.hgsf_workspace_size(C.byref(g), 480000, 0, 7, C.byref(need)) == _lib.ERR_INVALID_ARG
     assert lib.hgsf_workspace_size(C.byref(g), 480000, 16, 7, None) == _lib.ERR_INVALID_ARG
     # B * cells must fit int32 keys
