@@ -97,6 +97,7 @@ static int run_path(const hgsf_geometry *g, const hgsf_points *pt, const hgsf_pf
     p.cell_start = reinterpret_cast<uint32_t *>(base + w.off_table + 2 * w.cell_array_bytes);
     p.table_bytes = 2 * w.cell_array_bytes;
     p.tile_rec = reinterpret_cast<uint4 *>(base + w.off_tile_rec);
+    p.heavy_list = reinterpret_cast<uint32_t *>(base + w.off_heavy);
     p.frame_offsets = pt->frame_offsets ? const_cast<int32_t *>(pt->frame_offsets)
                                         : reinterpret_cast<int32_t *>(base + w.off_frame_offsets);
     p.key = reinterpret_cast<int32_t *>(base + w.off_key);

@@ -24,6 +24,7 @@
 #include "contract_ops.cuh"
 
 #include <algorithm>
+#include <climits>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -125,7 +126,7 @@ constexpr int FRONT_THREADS = 256;
 constexpr int FRONT_WARPS = FRONT_THREADS / 32;
 constexpr int PPT = 4;                                  // points per thread and block
 constexpr int PBLOCK = FRONT_THREADS * PPT;             // 1024 points per block; thread t holds points base + u*256 + t
-constexpr int KC = 4;                                   // cell blocks (1024 cells, one uint4 per thread) kept in registers
+constexpr int KC = 1;                                   // cell blocks (1024 cells, one uint4 per thread) kept in registers
 static_assert(PBLOCK == SCAN_TILE, "block size");
 
 // block-wide sum of a 64-bit value; every thread gets the total
@@ -191,7 +192,7 @@ __global__ void __launch_bounds__(FRONT_THREADS, 4) k_front(const PathParams p) 
 
     // ---- phase 0: zero the cell table, unless the previous call's consumer kernel left it clean ----
     const bool clean = (ld_volatile_u64(p.state) == p.magic);        // grid-uniform: nobody writes p.state before the first barrier
-    if (cta == 0 && tid == 0) { p.ticket[0] = 0u; p.ticket[32] = 0u; p.ticket[64] = 0u; }
+    if (cta == 0 && tid == 0) { p.ticket[0] = 0u; p.ticket[32] = 0u; p.ticket[64] = 0u; }      // run ticket, heavy-tile count, finished CTAs
     if (!clean) {
         uint4 *t4 = reinterpret_cast<uint4 *>(p.cell_tag);           // tag, cnt: two arrays back to back
         const long long n4 = (long long)(p.table_bytes >> 4);
@@ -386,13 +387,22 @@ __global__ void __launch_bounds__(FRONT_THREADS, 4) k_front(const PathParams p) 
             for (int d = 1; d < 8; d <<= 1) { tsum += __shfl_xor_sync(FULL, tsum, d); tmask |= __shfl_xor_sync(FULL, tmask, d); }
             if (c0 < chi) {
                 *reinterpret_cast<uint4 *>(p.cell_start + c0) = make_uint4(run, run + v.x, run + v.x + v.y, run + v.x + v.y + v.z);
-                if ((lane & 7) == 0) p.tile_rec[c0 >> 5] = make_uint4(run, tsum, orn, tmask);
+                if ((lane & 7) == 0) {
+                    p.tile_rec[c0 >> 5] = make_uint4(run, tsum, orn, tmask);
+                    // a tile with many points takes one warp a long time: listed, so that the consumer starts on those first
+                    if (tsum > (uint32_t)p.heavy_pts) {
+                        p.heavy_list[atomicAdd(p.ticket + 32, 1u)] = (uint32_t)(c0 >> 5);
+                    }
+                }
             }
             crun += (uint32_t)blk_total; orun += (uint32_t)(blk_total >> 32);
         }
     }
     grid.sync();
     stamp(4);
+#ifdef HGSF_PDL_TRIGGER
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");      // k_pillars may be scheduled from here on
+#endif
 
     // ---- phase 4: fill.  Per point: table entries of its cell -> destination row; then the row is copied ----
     for (int base = lo; base < hi; base += PBLOCK) {
@@ -568,6 +578,7 @@ __device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t *p) {
 struct Run {          // consecutive tiles of the cell table
     int t0, nt;       // first tile, tiles (0 = none)
     uint4 rec;        // lane i < nt: record of tile t0 + i
+    bool heavy;       // a run out of k_front's list of heavy tiles (one tile)
 };
 struct Group {        // whole tiles of one run holding at most 32 pillars
     int t_a, nt;      // first tile, tiles (0 = none)
@@ -575,6 +586,7 @@ struct Group {        // whole tiles of one run holding at most 32 pillars
     int rowA, nrows;  // first CSR row, rows
     unsigned tmask;   // lane i < nt: occupancy mask of tile t_a + i ...
     int tcol;         // ... and the block column of its first pillar
+    bool skip;        // a listed heavy tile met inside the moving window: already taken care of, neither computed nor written
 };
 
 #ifndef HGSF_PILLARS_MINB
@@ -610,8 +622,10 @@ __global__ void __launch_bounds__(PT, HGSF_PILLARS_MINB) k_pillars(const PathPar
     int *fcol = s_fcol_all[warp];
 
     // ---- one-time setup (the only CTA barriers) ----
-    for (int b = tid; b <= p.B; b += PT) s_R[b] = p.frame_raw_base[b];
     if (CANVAS) for (int t = tid; t < PW * BLK; t += PT) blk_all[t] = 0.f;
+    // launched as a programmatic dependent of k_front: everything below reads what that grid wrote
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    for (int b = tid; b <= p.B; b += PT) s_R[b] = p.frame_raw_base[b];
     __syncthreads();
     if (tid == 0) {
         int acc = 0;
@@ -730,31 +744,39 @@ __global__ void __launch_bounds__(PT, HGSF_PILLARS_MINB) k_pillars(const PathPar
     //      of the table go out in runs of CT tiles, the rest in runs of CT_TAIL.  [Measured and rejected: three tickets in flight
     //      per warp (the same-address atomics queue three times as long: +6 %); the first half of the runs assigned round-robin
     //      without tickets (the window of tiles in flight spreads: +16 %).] ----
+    //      Before all of that come the HEAVY tiles k_front listed (more than p.heavy_pts points), one tile per run: a single warp
+    //      needs up to half the kernel's duration for the densest tile of a clustered scene, so it has to start at once; the moving
+    //      window later steps over them.
     const int n_tt = (int)(((long long)p.B * p.cells) >> 5);       // tiles of the cell table
+    const int n_heavy = (int)p.ticket[32];                          // the list holds one entry per tile at most: it cannot overflow
     const int n_big = (int)(((long long)n_tt * 3 / 4) / CT);       // runs of CT tiles
     const int t_tail = n_big * CT;                                 // first tile of the short runs
-    const int n_runs = n_big + (n_tt - t_tail + CT_TAIL - 1) / CT_TAIL;
+    const int n_runs = n_heavy + n_big + (n_tt - t_tail + CT_TAIL - 1) / CT_TAIL;
     unsigned tk_pending = 0u;            // lane 0: the ticket in flight
     bool runs_left = n_runs > 0;         // warp-uniform: a ticket below n_runs may still come
     auto fetch_ticket = [&]() { if (lane == 0) tk_pending = atomicAdd(p.ticket, 1u); };
     auto take_run = [&]() -> Run {
-        Run r; r.t0 = 0; r.nt = 0; r.rec = make_uint4(0u, 0u, 0u, 0u);
+        Run r; r.t0 = 0; r.nt = 0; r.rec = make_uint4(0u, 0u, 0u, 0u); r.heavy = false;
         if (!runs_left) return r;
-        const int c = (int)__shfl_sync(FULL, tk_pending, 0);
+        int c = (int)__shfl_sync(FULL, tk_pending, 0);
         if (c >= n_runs) { runs_left = false; return r; }
         fetch_ticket();
-        if (c < n_big) { r.t0 = c * CT; r.nt = CT; }
-        else { r.t0 = t_tail + (c - n_big) * CT_TAIL; r.nt = min(CT_TAIL, n_tt - r.t0); }
+        if (c < n_heavy) { r.t0 = (int)__ldg(p.heavy_list + c); r.nt = 1; r.heavy = true; }
+        else {
+            c -= n_heavy;
+            if (c < n_big) { r.t0 = c * CT; r.nt = CT; }
+            else { r.t0 = t_tail + (c - n_big) * CT_TAIL; r.nt = min(CT_TAIL, n_tt - r.t0); }
+        }
         if (lane < r.nt) r.rec = __ldg(p.tile_rec + r.t0 + lane);
         return r;
     };
     Run run_cur, run_nxt;
-    run_cur.t0 = run_cur.nt = 0; run_cur.rec = make_uint4(0u, 0u, 0u, 0u); run_nxt = run_cur;
+    run_cur.t0 = run_cur.nt = 0; run_cur.rec = make_uint4(0u, 0u, 0u, 0u); run_cur.heavy = false; run_nxt = run_cur;
     int run_pos = 0;                     // next tile of run_cur that belongs to no group yet
     // the next group: tiles of the current run from run_pos on, as many whole tiles as hold at most 32 pillars (a tile never
     // holds more than 32, so at least one); moves on to the next run when this one is used up
     auto next_group = [&]() -> Group {
-        Group g; g.t_a = 0; g.nt = 0; g.slotA = 0; g.npil = 0; g.rowA = 0; g.nrows = 0; g.tmask = 0u; g.tcol = 0;
+        Group g; g.t_a = 0; g.nt = 0; g.slotA = 0; g.npil = 0; g.rowA = 0; g.nrows = 0; g.tmask = 0u; g.tcol = 0; g.skip = false;
         if (run_pos >= run_cur.nt) {
             run_cur = run_nxt; run_nxt = take_run(); run_pos = 0;
             if (run_cur.nt == 0) return g;
@@ -763,12 +785,22 @@ __global__ void __launch_bounds__(PT, HGSF_PILLARS_MINB) k_pillars(const PathPar
         const unsigned slot_after = run_cur.rec.z + (unsigned)__popc(run_cur.rec.w);     // pillars before the NEXT tile
         const unsigned row_after = run_cur.rec.x + run_cur.rec.y;
         const int slotA = (int)__shfl_sync(FULL, run_cur.rec.z, a);
-        const unsigned fits = __ballot_sync(FULL, lane >= a && lane < run_cur.nt && (int)slot_after - slotA <= 32);
-        const int nt = __popc(fits);                   // `fits` is a contiguous run of lanes starting at a
+        // listed heavy tiles of a window run are stepped over (a group of their own that is neither computed nor written)
+        unsigned hv = 0u;
+        if (!run_cur.heavy && n_heavy > 0)
+            hv = __ballot_sync(FULL, lane < run_cur.nt && run_cur.rec.y > (unsigned)p.heavy_pts) & (0xFFFFFFFFu << a);
+        unsigned fits = __ballot_sync(FULL, lane >= a && lane < run_cur.nt && (int)slot_after - slotA <= 32);
+        int nt;
+        g.skip = false;
+        if (hv & (1u << a)) { nt = 1; g.skip = true; }
+        else {
+            if (hv) fits &= (1u << (__ffs(hv) - 1)) - 1u;  // up to the first heavy tile
+            nt = __popc(fits);                             // `fits` is a contiguous run of lanes starting at a
+        }
         g.t_a = run_cur.t0 + a; g.nt = nt; g.slotA = slotA;
-        g.npil = (int)__shfl_sync(FULL, slot_after, a + nt - 1) - slotA;
+        g.npil = g.skip ? 0 : (int)__shfl_sync(FULL, slot_after, a + nt - 1) - slotA;
         g.rowA = (int)__shfl_sync(FULL, run_cur.rec.x, a);
-        g.nrows = (int)__shfl_sync(FULL, row_after, a + nt - 1) - g.rowA;
+        g.nrows = g.skip ? 0 : (int)__shfl_sync(FULL, row_after, a + nt - 1) - g.rowA;
         // lane i < nt keeps what the tile writer needs of tile a + i
         const int srcl = min(a + lane, 31);
         g.tmask = __shfl_sync(FULL, run_cur.rec.w, srcl);
@@ -881,7 +913,9 @@ __global__ void __launch_bounds__(PT, HGSF_PILLARS_MINB) k_pillars(const PathPar
                 const int slot = (n_keep == 1) ? __popc(sbal & lt) : 31 - __popc(mbal & lt);   // singles from the front, multis from the back
                 // position of the single evaluated point: 0, or the rank-0 arrival when P == 1 truncated a larger pillar
                 const int pos0 = (cnt == 1) ? 0 : (int)perm[lane][0];
-                rec[slot][0] = make_float4(mx, my, mz, __int_as_float(n_keep | (lane << 8) | (pos0 << 16)));
+                // bit 24: the pillar was truncated to its first P points, so the unit lanes must go through the rank table; an
+                // untruncated pillar is evaluated in arrival order (the max does not care), one dependent shared-memory load less
+                rec[slot][0] = make_float4(mx, my, mz, __int_as_float(n_keep | (lane << 8) | (pos0 << 16) | ((cnt > Pmax) ? (1 << 24) : 0)));
                 rec[slot][1] = make_float4(cx, cy, cz, __int_as_float(rel));
             }
             // the feature block: columns of pillars that were never created (beyond max_voxels) read as zero on the canvas
@@ -910,8 +944,8 @@ __global__ void __launch_bounds__(PT, HGSF_PILLARS_MINB) k_pillars(const PathPar
                     if (1 < Pmax) { a0 = __float_as_int(pv.x); a1 = __float_as_int(pv.y); a2 = __float_as_int(pv.z); a3 = __float_as_int(pv.w); }
                     int b0 = a0, b1 = a1, b2 = a2, b3 = a3;
                     float rowA[RWc], rowB[RWc];
-                    load_row(stg, __float_as_int(rA1.w), metaA >> 16, rowA);
-                    load_row(stg, __float_as_int(rB1.w), metaB >> 16, rowB);
+                    load_row(stg, __float_as_int(rA1.w), (metaA >> 16) & 0xFF, rowA);
+                    load_row(stg, __float_as_int(rB1.w), (metaB >> 16) & 0xFF, rowB);
                     eval_row(rowA, rA0.x, rA0.y, rA0.z, rA1.x, rA1.y, rA1.z, a0, a1, a2, a3);
                     eval_row(rowB, rB0.x, rB0.y, rB0.z, rB1.x, rB1.y, rB1.z, b0, b1, b2, b3);
                     if (p.feats) {
@@ -931,6 +965,7 @@ __global__ void __launch_bounds__(PT, HGSF_PILLARS_MINB) k_pillars(const PathPar
                 const float4 r0 = rec[31 - j][0], r1 = rec[31 - j][1];
                 const int meta = __float_as_int(r0.w);
                 const int nk = meta & 0xFF, col = (meta >> 8) & 0xFF;
+                const bool trunc = (meta >> 24) & 1;
                 const int relp = __float_as_int(r1.w);
                 int v0 = 0, v1 = 0, v2 = 0, v3 = 0;
                 if (nk < Pmax) { v0 = __float_as_int(pv.x); v1 = __float_as_int(pv.y); v2 = __float_as_int(pv.z); v3 = __float_as_int(pv.w); }
@@ -939,8 +974,8 @@ __global__ void __launch_bounds__(PT, HGSF_PILLARS_MINB) k_pillars(const PathPar
                 for (int s2 = half; s2 < nk; s2 += 4) {
                     const int s3 = (s2 + 2 < nk) ? s2 + 2 : s2;        // the last odd one is evaluated twice: max is idempotent
                     float rowA[RWc], rowB[RWc];
-                    load_row(stg, relp, perm[col][s2], rowA);
-                    load_row(stg, relp, perm[col][s3], rowB);
+                    load_row(stg, relp, trunc ? (int)perm[col][s2] : s2, rowA);
+                    load_row(stg, relp, trunc ? (int)perm[col][s3] : s3, rowB);
                     eval_row(rowA, r0.x, r0.y, r0.z, r1.x, r1.y, r1.z, v0, v1, v2, v3);
                     eval_row(rowB, r0.x, r0.y, r0.z, r1.x, r1.y, r1.z, u0, u1, u2, u3);
                 }
@@ -1102,9 +1137,9 @@ __global__ void __launch_bounds__(PT, HGSF_PILLARS_MINB) k_pillars(const PathPar
         issue_stage(g_nxt, stage + (size_t)((it + 1) & 1) * SW * RWc);
         if (g_cur.npil > 0) process(g_cur, e_cur, stage + (size_t)(it & 1) * SW * RWc);
 #ifdef HGSF_EXPERIMENT
-        if (CANVAS && !(p.dbg & 2)) write_tiles(g_cur);
+        if (CANVAS && !g_cur.skip && !(p.dbg & 2)) write_tiles(g_cur);
 #else
-        if (CANVAS) write_tiles(g_cur);
+        if (CANVAS && !g_cur.skip) write_tiles(g_cur);
 #endif
         __syncwarp();   // the feature block is rewritten by the next group
         g_cur = g_nxt; e_cur = e_nxt;
@@ -1185,8 +1220,20 @@ static int launch_pillars_t(const PathParams &p, cudaStream_t stream) {
         int grid = 1;
         const int st = launch_persistent(kern, PT, smem, (n_runs + PW - 1) / PW, stream, &grid);
         if (st != HGSF_OK) return st;
-        kern<<<(unsigned)grid, PT, smem, stream>>>(p);
-        return (int)cudaGetLastError();
+        // programmatic dependent launch behind k_front (same stream): this kernel's launch latency overlaps k_front's last
+        // phase; griddepcontrol.wait at the top of the kernel orders every dependent read after k_front's completion
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(PT); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+#ifdef HGSF_NO_PDL
+        cfg.numAttrs = 0;
+#else
+        cfg.numAttrs = 1;
+#endif
+        return (int)cudaLaunchKernelEx(&cfg, kern, p);
     };
     if constexpr (PFN) {
         if (canvas) return bn ? go(k_pillars<F, ABS, DIST, true, true, true>) : go(k_pillars<F, ABS, DIST, false, true, true>);
@@ -1246,6 +1293,13 @@ int launch_pillar_path(const PathParams &p_in, bool with_pfn, bool abs_xyz, bool
     { static const int dbg = getenv("HGSF_DBG") ? atoi(getenv("HGSF_DBG")) : 0; p.dbg = dbg; }
 #endif
     int nl = 0;
+    {
+        // heavy tile = more than 6 times the average tile's points, at least 48 (HGSF_HEAVY_PTS overrides; huge = none)
+        const long long n_tt = ((long long)p.B * p.cells) >> 5;
+        const long long avg6 = n_tt > 0 ? 6 * (long long)p.n / n_tt : 0;
+        p.heavy_pts = (int)std::min<long long>(std::max<long long>(48, avg6), INT_MAX);
+        if (const char *hp = getenv("HGSF_HEAVY_PTS")) p.heavy_pts = atoi(hp);
+    }
     p.canvas_vec = (p.canvas != nullptr) && (p.nx % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.canvas) & 15) == 0) &&
                    !(getenv("HGSF_CANVAS_STORE") && getenv("HGSF_CANVAS_STORE")[0] == 's');       // 's': force scalar stores (tests)
     {

@@ -43,8 +43,8 @@ struct PathParams {
     // ---- limits ----
     int P, max_voxels;
     // ---- workspace ----
-    uint32_t *ticket;                  // [128]: word 0 = k_pfn's chunk ticket, word 32 = k_emit's chunk ticket, word 64 = CTAs of the
-                                       // consumer kernel that have finished (each on its own 128-byte line); reset by k_front
+    uint32_t *ticket;                  // [128]: word 0 = k_pillars' run ticket, word 32 = heavy tiles listed by k_front, word 64 = CTAs of
+                                       // k_pillars that have finished (each on its own 128-byte line); reset by k_front
     uint64_t *state;                   // == magic: the cell table is known to be all zero (the consumer kernel cleaned up after itself)
     uint64_t magic;                    // geometry / layout dependent
     uint32_t *scan_desc;               // [3 * 2048] per-CTA slice totals of k_front's scans (first points; points, occupied cells)
@@ -53,6 +53,8 @@ struct PathParams {
     size_t table_bytes;                // bytes of cell_tag + cell_cnt (the part that must be zero when k_front starts)
     uint4 *tile_rec;                   // [B*cells/32] per 32-cell tile: {CSR row of its first point, points in the tile,
                                        //   pillars (in cell order) before the tile, occupancy mask of its 32 cells}
+    uint32_t *heavy_list;              // [B*cells/32] tiles with more than heavy_pts points (ticket[32] of them), in no particular order
+    int heavy_pts;
     int32_t *frame_offsets;            // [B+1] (aliases frame_offsets_in when given)
     int32_t *key;                      // [n] cell key of each point, -1 = outside the grid
     uint32_t *arrival;                 // [n] unordered arrival rank of the point inside its cell
@@ -73,7 +75,7 @@ struct PathParams {
 };
 
 struct WorkspaceLayout {
-    size_t off_ticket, off_state, off_desc, off_raw_base, off_table, off_tile_rec;
+    size_t off_ticket, off_state, off_desc, off_raw_base, off_table, off_tile_rec, off_heavy;
     size_t off_frame_offsets, off_key, off_arrival, off_sorted_rows, off_pil;
     size_t total, cell_array_bytes;
     int RW, nxp;
@@ -96,6 +98,7 @@ inline WorkspaceLayout workspace_layout(int64_t n, int B, int nx, int ny, int nz
     w.cell_array_bytes = align_up(sizeof(uint32_t) * ((size_t)B * (size_t)w.cells + 32), 256);
     w.off_table = o;       o = o + 3 * w.cell_array_bytes;
     w.off_tile_rec = o;    o = align_up(o + sizeof(uint4) * ((size_t)B * (size_t)w.cells / 32 + 1), 256);
+    w.off_heavy = o;       o = align_up(o + sizeof(uint32_t) * ((size_t)B * (size_t)w.cells / 32 + 1), 256);
     w.off_frame_offsets = o; o = align_up(o + sizeof(int32_t) * (size_t)(B + 1), 256);
     w.off_key = o;         o = align_up(o + sizeof(int32_t) * (size_t)n, 256);
     w.off_arrival = o;     o = align_up(o + sizeof(uint32_t) * (size_t)n, 256);
