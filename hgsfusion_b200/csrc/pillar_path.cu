@@ -743,7 +743,9 @@ __global__ void __launch_bounds__(PT, HGSF_PILLARS_MINB) k_pillars(const PathPar
     // ---- run hand-out: one global ticket per run, fetched a run before it is used.  Guided sizes: the first three quarters
     //      of the table go out in runs of CT tiles, the rest in runs of CT_TAIL.  [Measured and rejected: three tickets in flight
     //      per warp (the same-address atomics queue three times as long: +6 %); the first half of the runs assigned round-robin
-    //      without tickets (the window of tiles in flight spreads: +16 %).] ----
+    //      without tickets (the window of tiles in flight spreads: +16 %); 4 / 8 / 16 interleaved ticket counters (counter j
+    //      hands out runs j, j + NQ, ...: the counters drift apart and the write window loses its order: +17 %, even on an almost
+    //      empty scene, where the kernel is a pure zero-fill).] ----
     //      Before all of that come the HEAVY tiles k_front listed (more than p.heavy_pts points), one tile per run: a single warp
     //      needs up to half the kernel's duration for the densest tile of a clustered scene, so it has to start at once; the moving
     //      window later steps over them.
