@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get("HGSF_LIB") or os.path.join(_HERE, "libhgsfusion_b200.
 OK, ERR_INVALID_ARG, ERR_UNSUPPORTED, ERR_WORKSPACE, ERR_DRIVER = 0, -1, -2, -3, -4
 
 EXPORTS = ["hgsf_abi_version", "hgsf_status_string", "hgsf_pillar_capacity", "hgsf_workspace_size",
-           "hgsf_pillarize", "hgsf_points_to_bev", "hgsf_pillar_vfe", "hgsf_scatter_workspace_size",
+           "hgsf_pillarize", "hgsf_points_to_bev", "hgsf_pillar_vfe", "hgsf_pillar_vfe_stacked", "hgsf_scatter_workspace_size",
            "hgsf_pointpillar_scatter", "hgsf_last_launch_count", "hgsf_emit_timing_begin", "hgsf_emit_timing_collect",
            "hgsf_pillarnet_workspace_size", "hgsf_pillarnet_indices", "hgsf_gather_feature", "hgsf_gather_feature_grad",
            "hgsf_scatter_max", "hgsf_scatter_max_grad", "hgsf_split_encode", "hgsf_pillarnet_reader",
@@ -93,6 +93,8 @@ def load():
     lib.hgsf_points_to_bev.argtypes = path_args + [C.POINTER(Pfn)] + tail
     lib.hgsf_pillar_vfe.argtypes = [C.POINTER(Geometry), C.POINTER(Pfn), C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
+    lib.hgsf_pillar_vfe_stacked.argtypes = [C.POINTER(Geometry), C.POINTER(Pfn), C.POINTER(Pfn), C.c_void_p, C.c_void_p, C.c_void_p,
+                                            C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
     lib.hgsf_scatter_workspace_size.argtypes = [C.POINTER(Geometry), C.c_int32, C.POINTER(C.c_size_t)]
     lib.hgsf_pointpillar_scatter.argtypes = [C.POINTER(Geometry), C.c_void_p, C.c_void_p, C.c_int32, C.c_int64,
                                              C.c_int32, C.c_int32, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]

@@ -67,7 +67,7 @@ static int run_path(const hgsf_geometry *g, const hgsf_points *pt, const hgsf_pf
     if (!pt->frame_offsets && (pt->batch_col < 0 || pt->batch_col >= pt->stride)) return HGSF_ERR_INVALID_ARG;
     if (P <= 0 || max_voxels < 0) return HGSF_ERR_INVALID_ARG;
     if (!out->voxel_coords || !out->voxel_num_points || !out->num_pillars) return HGSF_ERR_INVALID_ARG;
-    if (P > 32) return HGSF_ERR_UNSUPPORTED;           // one warp orders a pillar: at most 32 slots
+    if (P > 128) return HGSF_ERR_UNSUPPORTED;          // the rank list of a pillar with more than 32 points is held in shared memory
     const WorkspaceLayout w = workspace_layout(pt->n, pt->batch_size, g->grid[0], g->grid[1], g->grid[2], pt->num_features);
     const int64_t cells = w.cells;                     // table entries per frame (row pitch padded to 32)
     if (cells * pt->batch_size > INT_MAX || pt->n > INT_MAX) return HGSF_ERR_UNSUPPORTED;
@@ -156,6 +156,33 @@ int hgsf_pillar_vfe(const hgsf_geometry *g, const hgsf_pfn *pfn, const float *vo
     q.pfn = PfnArgs{pfn->weight, pfn->bias, pfn->bn_weight, pfn->bn_bias, pfn->bn_mean, pfn->bn_var, pfn->bn_eps};
     q.out = pillar_features;
     const int st = launch_vfe(q, abs_xyz, dist, static_cast<cudaStream_t>(stream));
+    if (st == HGSF_OK) g_last_launches = M > 0 ? 1 : 0;
+    return st;
+}
+
+int hgsf_pillar_vfe_stacked(const hgsf_geometry *g, const hgsf_pfn *pfn0, const hgsf_pfn *pfn1, const float *voxels,
+                            const void *coords, const void *num, int32_t coords_are_float, int32_t num_are_float, int64_t M,
+                            int32_t P, int32_t F, float *pillar_features, hgsf_stream_t stream) {
+    g_last_launches = 0;
+    if (!geom_ok(g) || !pfn0 || !pfn1 || M < 0 || P <= 0 || F < 3) return HGSF_ERR_INVALID_ARG;
+    if (M > 0 && (!voxels || !coords || !num || !pillar_features)) return HGSF_ERR_INVALID_ARG;
+    for (const hgsf_pfn *pf : {pfn0, pfn1}) {
+        if (!pf->weight) return HGSF_ERR_INVALID_ARG;
+        const bool bn = pf->bn_weight != nullptr;
+        if (bn && !(pf->bn_bias && pf->bn_mean && pf->bn_var)) return HGSF_ERR_INVALID_ARG;
+        if (!bn && !pf->bias) return HGSF_ERR_INVALID_ARG;
+    }
+    const bool abs_xyz = pfn0->use_absolute_xyz != 0, dist = pfn0->with_distance != 0;
+    if ((abs_xyz ? F : F - 3) + 6 + (dist ? 1 : 0) != pfn0->in_channels) return HGSF_ERR_INVALID_ARG;
+    if (pfn1->in_channels != 2 * pfn0->out_channels) return HGSF_ERR_INVALID_ARG;
+    VfeParams q{};
+    q.voxels = voxels; q.coords = coords; q.num = num; q.coords_float = coords_are_float; q.num_float = num_are_float;
+    q.M = M; q.P = P; q.F = F; q.C = pfn0->out_channels; q.C1 = pfn1->out_channels;
+    for (int j = 0; j < 3; ++j) { q.vsize[j] = g->voxel_size[j]; q.voff[j] = g->centre_off[j]; }
+    q.pfn = PfnArgs{pfn0->weight, pfn0->bias, pfn0->bn_weight, pfn0->bn_bias, pfn0->bn_mean, pfn0->bn_var, pfn0->bn_eps};
+    q.pfn1 = PfnArgs{pfn1->weight, pfn1->bias, pfn1->bn_weight, pfn1->bn_bias, pfn1->bn_mean, pfn1->bn_var, pfn1->bn_eps};
+    q.out = pillar_features;
+    const int st = launch_vfe_stacked(q, abs_xyz, dist, static_cast<cudaStream_t>(stream));
     if (st == HGSF_OK) g_last_launches = M > 0 ? 1 : 0;
     return st;
 }

@@ -15,6 +15,10 @@ struct VfeParams {
     float vsize[3], voff[3];
     PfnArgs pfn;
     float *out;               // [M, C]
+    // stacked PFN (NUM_FILTERS with two entries, pillar_vfe.py:63-74): `pfn` is then the first layer (C = its out_channels =
+    // NUM_FILTERS[0] / 2) and pfn1 the last one, in_channels 2*C -> C1
+    PfnArgs pfn1;
+    int C1;
 };
 
 struct ScatterParams {
@@ -30,6 +34,7 @@ struct ScatterParams {
 };
 
 int launch_vfe(const VfeParams &q, bool abs_xyz, bool dist, cudaStream_t stream);
+int launch_vfe_stacked(const VfeParams &q, bool abs_xyz, bool dist, cudaStream_t stream);
 int launch_scatter(const ScatterParams &q, cudaStream_t stream, int *launches);
 
 // shared host helpers (pillar_path.cu)

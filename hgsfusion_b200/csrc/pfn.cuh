@@ -54,6 +54,30 @@ struct PfnLane {
         for (int j = 0; j < CPL; ++j) vmax[j] = has_padding ? padv[j] : 0.f;
     }
 
+    // one point, NOT folded into a maximum: y[j] = relu(BN(Linear(decorated row))) of this lane's channels (the input of the next
+    // layer of a stacked PFN, pillar_vfe.py:47-49)
+    template <int RW>
+    __device__ __forceinline__ void value(const float (&row)[RW], float mx, float my, float mz,
+                                          float cx, float cy, float cz, float (&yout)[CPL]) const {
+        float feat[CIN];
+        int kf = 0;
+#pragma unroll
+        for (int q = ABS ? 0 : 3; q < F; ++q) feat[kf++] = row[q];
+        feat[kf++] = __fsub_rn(row[0], mx); feat[kf++] = __fsub_rn(row[1], my); feat[kf++] = __fsub_rn(row[2], mz);
+        feat[kf++] = __fsub_rn(row[0], cx); feat[kf++] = __fsub_rn(row[1], cy); feat[kf++] = __fsub_rn(row[2], cz);
+        if (DIST) feat[kf++] = __fsqrt_rn(fmaf(row[2], row[2], fmaf(row[1], row[1], __fmul_rn(row[0], row[0]))));
+#pragma unroll
+        for (int j = 0; j < CPL; ++j) {
+            float acc = 0.f;
+#pragma unroll
+            for (int q = 0; q < CIN; ++q) acc = fmaf(feat[q], w[j][q], acc);
+            float y;
+            if (has_bn) y = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(acc, bn_m[j]), bn_i[j]), bn_g[j]), bn_b[j]);
+            else        y = __fadd_rn(acc, bn_b[j]);
+            yout[j] = (y > 0.f || y != y) ? y : 0.f;
+        }
+    }
+
     // one point: row[0..F) raw features (x, y, z first), pillar mean and centre
     template <int RW>
     __device__ __forceinline__ void point(const float (&row)[RW], float mx, float my, float mz,

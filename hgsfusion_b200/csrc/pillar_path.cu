@@ -507,13 +507,16 @@ __device__ __forceinline__ void warp_bitonic(uint32_t &key, int &val, int lane, 
     }
 }
 
-// cnt > 32 arrivals in a cell: positions of the 32 smallest point indices, ascending, one per lane
-__device__ __noinline__ int select_first32(const float *__restrict__ idx0, int stride, int cnt, int lane) {
+// cnt > 32 arrivals in a cell: positions of the 32 smallest point indices above `lo` (all of them when !have_lo), ascending, one per
+// lane; `key_out` = the lane's point index (0xFFFFFFFF when fewer than lane+1 are left).  Called once per 32 slots of the pillar.
+__device__ __noinline__ int select_next32(const float *__restrict__ idx0, int stride, int cnt, int lane, bool have_lo, uint32_t lo,
+                                          uint32_t &key_out) {
     uint32_t best = 0xFFFFFFFFu;
     int bestv = 0;
     for (int base = 0; base < cnt; base += 32) {
         const int j = base + lane;
         uint32_t k = (j < cnt) ? __float_as_uint(__ldg(idx0 + (size_t)j * stride)) : 0xFFFFFFFFu;
+        if (have_lo && k <= lo) k = 0xFFFFFFFFu;          // taken by an earlier round
         int v = j;
         if (base > 0) {
             const uint32_t worst = __shfl_sync(FULL, best, 31);
@@ -527,6 +530,7 @@ __device__ __noinline__ int select_first32(const float *__restrict__ idx0, int s
         if (rk < best) { best = rk; bestv = rv; }
         warp_bitonic(best, bestv, lane, 32);
     }
+    key_out = best;
     return bestv;
 }
 
@@ -553,6 +557,7 @@ __device__ __noinline__ int select_first32(const float *__restrict__ idx0, int s
 constexpr int PW = 4;                 // warps per CTA
 constexpr int PT = PW * 32;
 constexpr int SMALL_CNT = 6;          // up to this many arrivals the owning lane ranks them itself
+constexpr int MAX_P = 128;            // largest max_points_per_voxel (the rank list of a > 32-point pillar lives in shared memory)
 #ifndef HGSF_RUN_TILES
 #define HGSF_RUN_TILES 2
 #endif
@@ -610,7 +615,7 @@ __global__ void __launch_bounds__(PT, HGSF_PILLARS_MINB) k_pillars(const PathPar
     int *s_K = s_R + (p.B + 1);                                                             // [B+1] kept (final) pillar base per frame
     __shared__ float4 s_rec_all[PW][32][2];                        // work lists: singles from the front, multis from the back
     __shared__ unsigned char s_perm_all[PW][32][32];               // per pillar: arrival position of its rank-th point
-    __shared__ int s_bperm_all[PW][32];                            // same for a pillar with > 32 arrivals
+    __shared__ int s_bperm_all[PW][MAX_P];                         // same for a pillar with > 32 arrivals: its first min(cnt, P) points
     __shared__ int s_fcol_all[PW][32];                             // final pillar id of the chunk's pillar j (-1: never created)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1001,7 +1006,15 @@ __global__ void __launch_bounds__(PT, HGSF_PILLARS_MINB) k_pillars(const PathPar
             const float cx_o = __shfl_sync(FULL, cx, o), cy_o = __shfl_sync(FULL, cy, o), cz_o = __shfl_sync(FULL, cz, o);
             const int nk = min(cnt_o, Pmax);
             const float *grow_o = grows + (size_t)start_o * RW;
-            bperm[lane] = select_first32(grow_o + Fr, RW, cnt_o, lane);
+            {
+                // the pillar's first nk points by index, 32 per round (P <= 32: one round)
+                uint32_t lo = 0u, key = 0u;
+                for (int r0 = 0; r0 < nk; r0 += 32) {
+                    const int pos = select_next32(grow_o + Fr, RW, cnt_o, lane, r0 > 0, lo, key);
+                    if (r0 + lane < MAX_P) bperm[r0 + lane] = pos;
+                    lo = __shfl_sync(FULL, key, 31);
+                }
+            }
             __syncwarp();
             if (p.voxels) {
                 float *vo = p.voxels + (size_t)f_o * Pmax * Fr;

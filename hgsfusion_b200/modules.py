@@ -136,10 +136,12 @@ class _VFEBase(nn.Module):
             num_point_features += 1
         self.num_filters = list(self.model_cfg.NUM_FILTERS)
         assert len(self.num_filters) > 0
-        if len(self.num_filters) != 1:
-            raise NotImplementedError("hgsfusion_b200 implements the single-layer PFN every HGSFusion/PointPillars "
-                                      "config uses (NUM_FILTERS: [64]); stacked PFN layers are not built yet")
-        self.pfn_layers = nn.ModuleList([_PFNLayerParams(num_point_features, self.num_filters[0], self.use_norm, True)])
+        if len(self.num_filters) > 2:
+            raise NotImplementedError("PFN stacks of more than two layers (NUM_FILTERS with three entries) are not built")
+        # the reference's loop (pillar_vfe.py:63-74): every layer but the last halves its out_channels and concatenates the max
+        widths = [num_point_features] + self.num_filters
+        self.pfn_layers = nn.ModuleList([_PFNLayerParams(widths[i], widths[i + 1], self.use_norm, last_layer=(i >= len(widths) - 2))
+                                         for i in range(len(widths) - 1)])
         self.voxel_size = [float(v) for v in voxel_size]
         self.point_cloud_range = point_cloud_range
         self.voxel_x, self.voxel_y, self.voxel_z = self.voxel_size
@@ -155,6 +157,26 @@ class _VFEBase(nn.Module):
     def _pfn(self) -> PfnWeights:
         return self.pfn_layers[0].weights(self.use_absolute_xyz, self.with_distance)
 
+    @property
+    def stacked(self) -> bool:
+        return len(self.pfn_layers) == 2
+
+    @property
+    def fused_ok(self) -> bool:
+        """The one-pass points -> canvas kernel covers the single-layer 64-channel PFN (every shipped config); other widths
+        and the stacked PFN run as pillarize -> PFN -> scatter, three native launches on the same kernels' siblings."""
+        return (not self.stacked) and self.num_filters[-1] == 64
+
+    def _pfn_eval(self, path, voxels, coords, num):
+        """Eval-mode PFN stack on the contract tensors (one native launch)."""
+        if self.stacked:
+            if self.training or (torch.is_grad_enabled() and any(p.requires_grad for p in self.pfn_layers.parameters())):
+                raise NotImplementedError("training through a stacked (two-layer) PFN is not built: use eval() / no_grad()")
+            return path.pillar_vfe_stacked(voxels, coords, num, self.pfn_layers[0].weights(self.use_absolute_xyz, self.with_distance),
+                                           self.pfn_layers[1].weights(True, False))
+        return _pfn_forward(path, self.pfn_layers[0], voxels, coords, num, self.use_absolute_xyz, self.with_distance,
+                            self.training)
+
 
 class PillarVFE(_VFEBase):
     """batch_dict contract mode: voxels, voxel_num_points, voxel_coords in; pillar_features out."""
@@ -166,8 +188,7 @@ class PillarVFE(_VFEBase):
 
     def forward(self, batch_dict, **kwargs):
         voxels, num, coords = batch_dict['voxels'], batch_dict['voxel_num_points'], batch_dict['voxel_coords']
-        features = _pfn_forward(self.path, self.pfn_layers[0], voxels, coords, num, self.use_absolute_xyz,
-                                self.with_distance, self.training)
+        features = self._pfn_eval(self.path, voxels, coords, num)
         batch_dict['pillar_features'] = features.view(-1, 1, features.shape[-1]).squeeze()   # pillar_vfe.py:121
         return batch_dict
 
@@ -299,8 +320,7 @@ class FusedPillarVFE(_VFEBase):
         path = self._path()
         out = path.pillarize(points, batch_size, xyz_col=1, batch_col=0, want_voxels=True).trim()
         out.pop('num_pillars')
-        feats = _pfn_forward(path, self.pfn_layers[0], out['voxels'], out['voxel_coords'], out['voxel_num_points'],
-                             self.use_absolute_xyz, self.with_distance, self.training)
+        feats = self._pfn_eval(path, out['voxels'], out['voxel_coords'], out['voxel_num_points'])
         out['pillar_features'] = feats
         if torch.is_grad_enabled() and feats.requires_grad:
             out['spatial_features'] = _ScatterFunction.apply(path, feats, out['voxel_coords'], batch_size)
@@ -314,7 +334,9 @@ class FusedPillarVFE(_VFEBase):
         points = batch_dict['points']
         batch_size = int(batch_dict['batch_size'])
         layer = self.pfn_layers[0]
-        if (self.training and layer.use_norm) or (torch.is_grad_enabled() and any(p.requires_grad for p in layer.parameters())):
+        if (not self.fused_ok or (self.training and layer.use_norm) or
+                (torch.is_grad_enabled() and any(p.requires_grad for p in layer.parameters()))):
+            # train mode / gradients, or a PFN outside the fused kernel set (stacked, or not 64 channels): the composed native path
             batch_dict.update(self._forward_train(points, batch_size))
             return batch_dict
         res = self._path().points_to_bev(points, batch_size, self._pfn(), xyz_col=1, batch_col=0,

@@ -211,6 +211,21 @@ class PillarPath:
         self.last_launches = int(self.lib.hgsf_last_launch_count())
         return out
 
+    def pillar_vfe_stacked(self, voxels, voxel_coords, voxel_num_points, pfn0: PfnWeights, pfn1: PfnWeights) -> torch.Tensor:
+        """The same for a two-layer (stacked) PFN: pfn0 = Linear(Cin -> H) (+BN), pfn1 = Linear(2H -> C1) (+BN); eval mode."""
+        vox = _f32c(voxels, "voxels")
+        M, P, F = (int(v) for v in vox.shape)
+        co, cf = _coords(voxel_coords, "voxel_coords")
+        nu, nf = _coords(voxel_num_points, "voxel_num_points")
+        p0, p1 = pfn0.to_struct(), pfn1.to_struct()
+        out = torch.empty((M, int(pfn1.weight.shape[0])), dtype=torch.float32, device=vox.device)
+        with torch.cuda.device(vox.device):
+            st = self.lib.hgsf_pillar_vfe_stacked(C.byref(self.geom), C.byref(p0), C.byref(p1), _ptr(vox), _ptr(co), _ptr(nu), cf, nf,
+                                                  M, P, F, _ptr(out), _stream(vox.device))
+        _lib.check(st, "hgsf_pillar_vfe_stacked")
+        self.last_launches = int(self.lib.hgsf_last_launch_count())
+        return out
+
     # -- training (include/hgsfusion_b200.h "Training through the path") ---------------------------------------
     def _contract_args(self, voxels, voxel_coords, voxel_num_points):
         vox = _f32c(voxels, "voxels")

@@ -136,6 +136,16 @@ HGSF_API int hgsf_pillar_vfe(const hgsf_geometry *geom, const hgsf_pfn *pfn,
                     int64_t num_pillars, int32_t max_points_per_voxel, int32_t num_features,
                     float *pillar_features, hgsf_stream_t stream);
 
+/* The same for a STACKED PFN of two layers (model_cfg NUM_FILTERS = [2H, C1]; PillarVFE.__init__ pillar_vfe.py:63-74 builds
+ * PFNLayer(Cin, 2H, last_layer=False) -> Linear(Cin, H) and PFNLayer(2H, C1, last_layer=True); PFNLayer.forward :29-49 concatenates
+ * each slot's features with the pillar's max).  pfn0->out_channels = H in {32, 64}, pfn1->in_channels = 2H,
+ * pfn1->out_channels = C1 in {32, 64, 128}; use_absolute_xyz / with_distance are read from pfn0.  Eval mode. */
+HGSF_API int hgsf_pillar_vfe_stacked(const hgsf_geometry *geom, const hgsf_pfn *pfn0, const hgsf_pfn *pfn1,
+                            const float *voxels, const void *voxel_coords, const void *voxel_num_points,
+                            int32_t coords_are_float, int32_t num_are_float,
+                            int64_t num_pillars, int32_t max_points_per_voxel, int32_t num_features,
+                            float *pillar_features, hgsf_stream_t stream);
+
 /* Bytes of workspace hgsf_pointpillar_scatter needs. */
 HGSF_API int hgsf_scatter_workspace_size(const hgsf_geometry *geom, int32_t batch_size, size_t *bytes);
 

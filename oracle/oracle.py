@@ -233,3 +233,58 @@ def points_to_bev(points, frame_offsets, geom: Geometry, pfn: PfnParams, P: int,
                                 _p(voxels), _p(coords), _p(num), _p(feat), _p(canvas), _p(fp))
     return dict(voxels=voxels[:M] if want_voxels else None, voxel_coords=coords[:M], voxel_num_points=num[:M],
                 pillar_features=feat[:M], spatial_features=canvas, frame_pillars=fp[:B], num_pillars=int(M))
+
+
+# ---- stacked PFN (numpy restatement; test infrastructure) -------------------------------------------------------------------
+def _fma_rows(x, w):
+    """x [..., K] fp32, w [C, K] fp32 -> [..., C]: acc = fmaf(x[k], w[c][k], acc) for k ascending, as the kernels evaluate nn.Linear
+    (pillar_vfe.py:37).  The product of two fp32 values is exact in float64; the sum is rounded to float64 and then to fp32 (a
+    double rounding that differs from a true fma in rare last-bit cases: the stacked comparison carries a 1e-5 tolerance anyway)."""
+    acc = np.zeros(x.shape[:-1] + (w.shape[0],), dtype=np.float32)
+    for k in range(x.shape[-1]):
+        acc = (acc.astype(np.float64) + x[..., k:k + 1].astype(np.float64) * w[:, k].astype(np.float64)).astype(np.float32)
+    return acc
+
+
+def _bn_relu(x, p: PfnParams):
+    if p.gamma is None:
+        y = x + _f32(p.bias)
+    else:
+        inv = (np.float32(1.0) / np.sqrt(_f32(p.running_var) + np.float32(p.eps))).astype(np.float32)
+        y = ((x - _f32(p.running_mean)) * inv) * _f32(p.gamma) + _f32(p.beta)      # four roundings, as BatchNorm1d eval does (:39)
+    return np.maximum(y, np.float32(0)).astype(np.float32)
+
+
+def pillar_vfe_layers(voxels, coords_bzyx, num_points, geom: Geometry, layers, use_absolute_xyz=True, with_distance=False):
+    """PillarVFE.forward (pillar_vfe.py:94-123) with a STACK of PFN layers (`layers`: list of PfnParams; every layer but the last
+    concatenates each slot's features with the pillar's max, PFNLayer.forward :29-49).  Plain numpy, float32 throughout."""
+    vox = _f32(voxels)
+    M, P, F = vox.shape
+    num = _f32(num_points)
+    co = _f32(coords_bzyx)
+    xo, yo, zo = (np.float32(v) for v in geom.centre_offsets())
+    vs = geom.vsize_f32
+    # torch CPU sum(dim=1): four interleaved partial sums over the leading 4*floor(P/4) slots, the tail into partial 0
+    P4 = (P // 4) * 4
+    acc = [np.zeros((M, 3), np.float32) for _ in range(4)]
+    for s in range(P):
+        q = (s % 4) if s < P4 else 0
+        acc[q] = acc[q] + vox[:, s, :3]
+    mean = (((acc[0] + acc[1]) + acc[2]) + acc[3]) / num[:, None]
+    f_cluster = vox[:, :, :3] - mean[:, None, :]
+    centre = np.stack([co[:, 3] * vs[0] + xo, co[:, 2] * vs[1] + yo, co[:, 1] * vs[2] + zo], axis=1).astype(np.float32)
+    f_center = vox[:, :, :3] - centre[:, None, :]
+    feats = [vox if use_absolute_xyz else vox[:, :, 3:], f_cluster, f_center]
+    if with_distance:
+        x, y, z = vox[:, :, 0], vox[:, :, 1], vox[:, :, 2]
+        feats.append(np.sqrt((z.astype(np.float64) * z + (y.astype(np.float64) * y + (x * x).astype(np.float32)).astype(np.float32))
+                             .astype(np.float32))[:, :, None].astype(np.float32))
+    x = np.concatenate(feats, axis=2).astype(np.float32)
+    mask = (num.astype(np.int32)[:, None] > np.arange(P)[None, :]).astype(np.float32)
+    x = x * mask[:, :, None]
+    for li, p in enumerate(layers):
+        h = _bn_relu(_fma_rows(x, _f32(p.weight)), p)
+        hmax = h.max(axis=1, keepdims=True)
+        if li == len(layers) - 1:
+            return hmax[:, 0, :]
+        x = np.concatenate([h, np.repeat(hmax, P, axis=1)], axis=2)

@@ -261,3 +261,29 @@ def test_pfn_requested_without_feature_or_canvas_outputs(cuda):
     # canvas only (no pillar_features rows)
     res = path.points_to_bev(dpts, 2, device_pfn(w, cuda), want_features=False, want_canvas=True)
     assert bits_equal(res.trim()["spatial_features"].cpu().numpy(), ref["spatial_features"])
+
+
+@pytest.mark.parametrize("P", [33, 42, 100, 128])
+def test_more_than_32_points_per_pillar(cuda, P):
+    """MAX_POINTS_PER_VOXEL above 32 (KITTI PointPillars uses 32, the VoD radar configs up to 100): pillars with 1 .. several
+    hundred arrivals, so that untruncated (cnt <= P), truncated (cnt > P) and multi-round (cnt > 32) pillars all occur; P = 42 also
+    exercises the tail of torch's 4-way interleaved slot sum (slots beyond 4*floor(P/4))."""
+    cfg = synthetic.CONFIGS["vod"]
+    rng = np.random.default_rng(P)
+    frames = []
+    for b in range(2):
+        f = synthetic.make_frame(5000, cfg["pc_range"], 7, 40 + b, "clustered")
+        # three very dense spots: up to a few hundred points per 0.16 m cell
+        for k in range(3):
+            c = rng.uniform([5, -20], [45, 20])
+            f[k * 900:(k + 1) * 900, :2] = (c + rng.normal(0, 0.12, size=(900, 2))).astype(np.float32)
+        frames.append(f)
+    pts, offs = synthetic.batch_points(frames)
+    ref, got = both(pts, offs, cfg["pc_range"], cfg["voxel_size"], P, 40000, 7, cuda)
+    n = ref["voxel_num_points"]
+    assert n.max() == P and (n > 32).any() and ((n > 1) & (n < 32)).any()
+    # pillarize alone (no PFN: the generic-F kernel) with the padded voxels tensor
+    path = PillarPath(np.asarray(cfg["pc_range"], dtype=np.float32), cfg["voxel_size"], P, 40000, 7)
+    r = path.pillarize(torch.from_numpy(pts).to(cuda), 2).trim()
+    assert bits_equal(r["voxels"].cpu().numpy(), ref["voxels"])
+    assert np.array_equal(r["voxel_num_points"].cpu().numpy(), n)

@@ -55,8 +55,14 @@ def test_pillar_vfe_module_has_the_reference_parameter_names():
 
 
 def test_module_guards():
-    with pytest.raises(NotImplementedError):
-        modules.PillarVFE(model_cfg=cfg_ns(NUM_FILTERS=[32, 64]), num_point_features=7, voxel_size=[0.16, 0.16, 5],
+    # a stacked PFN builds the reference's parameter tree (pillar_vfe.py:18-19,63-74): the non-last layer halves its width
+    st = modules.PillarVFE(model_cfg=cfg_ns(NUM_FILTERS=[64, 128]), num_point_features=7, voxel_size=[0.16, 0.16, 5],
+                           point_cloud_range=np.array([0, -25.6, -3, 51.2, 25.6, 2], dtype=np.float32))
+    sd = st.state_dict()
+    assert sd["pfn_layers.0.linear.weight"].shape == (32, 13) and sd["pfn_layers.1.linear.weight"].shape == (128, 64)
+    assert st.stacked and not st.fused_ok and st.get_output_feature_dim() == 128
+    with pytest.raises(NotImplementedError):                      # three layers: not built
+        modules.PillarVFE(model_cfg=cfg_ns(NUM_FILTERS=[64, 64, 64]), num_point_features=7, voxel_size=[0.16, 0.16, 5],
                           point_cloud_range=np.array([0, -25.6, -3, 51.2, 25.6, 2], dtype=np.float32))
     m = modules.FusedPillarVFE(model_cfg=cfg_ns(MAX_POINTS_PER_VOXEL=32, MAX_NUMBER_OF_VOXELS={'train': 16000, 'test': 40000}),
                                num_point_features=7, voxel_size=[0.16, 0.16, 5],
