@@ -34,7 +34,10 @@ class Geometry(C.Structure):
 class Points(C.Structure):
     _fields_ = [("data", C.c_void_p), ("n", C.c_int64), ("stride", C.c_int32), ("xyz_col", C.c_int32),
                 ("num_features", C.c_int32), ("batch_col", C.c_int32), ("frame_offsets", C.c_void_p),
-                ("batch_size", C.c_int32)]
+                ("batch_size", C.c_int32), ("flags", C.c_int32)]
+
+
+POINTS_SPCONV1_BREAK, POINTS_FLIP_X, POINTS_FLIP_Y = 1, 2, 4
 
 
 class Pfn(C.Structure):

@@ -92,6 +92,8 @@ static int run_path(const hgsf_geometry *g, const hgsf_points *pt, const hgsf_pf
     p.magic = 0x48475346c1ea9e5bull ^ ((uint64_t)w.cell_array_bytes * 0x9E3779B97F4A7C15ull) ^ (uint64_t)w.off_table;
     p.scan_desc = reinterpret_cast<uint32_t *>(base + w.off_desc);
     p.frame_raw_base = reinterpret_cast<int32_t *>(base + w.off_raw_base);
+    p.cutoff = reinterpret_cast<int32_t *>(base + w.off_cutoff);
+    p.flags = pt->flags;
     p.cell_tag = reinterpret_cast<uint32_t *>(base + w.off_table);
     p.cell_cnt = reinterpret_cast<uint32_t *>(base + w.off_table + w.cell_array_bytes);
     p.cell_start = reinterpret_cast<uint32_t *>(base + w.off_table + 2 * w.cell_array_bytes);

@@ -73,7 +73,10 @@ __device__ __forceinline__ int point_key(const PathParams &p, int i) {
     int key = -1;
     if (i < p.n) {
         const float *row = p.pts + (size_t)i * p.stride;
-        const float x = __ldg(row + p.xyz_col), y = __ldg(row + p.xyz_col + 1), z = __ldg(row + p.xyz_col + 2);
+        float x = __ldg(row + p.xyz_col), y = __ldg(row + p.xyz_col + 1);
+        const float z = __ldg(row + p.xyz_col + 2);
+        if (p.flags & HGSF_POINTS_FLIP_X) x = -x;        // DataProcessor.double_flip (data_processor.py:116-130): exact sign flips
+        if (p.flags & HGSF_POINTS_FLIP_Y) y = -y;
         int b;
         if (p.frame_offsets_in) {
             b = find_frame(p.frame_offsets_in, p.B, i);
@@ -193,6 +196,7 @@ __global__ void __launch_bounds__(FRONT_THREADS, 4) k_front(const PathParams p) 
     // ---- phase 0: zero the cell table, unless the previous call's consumer kernel left it clean ----
     const bool clean = (ld_volatile_u64(p.state) == p.magic);        // grid-uniform: nobody writes p.state before the first barrier
     if (cta == 0 && tid == 0) { p.ticket[0] = 0u; p.ticket[32] = 0u; p.ticket[64] = 0u; }      // run ticket, heavy-tile count, finished CTAs
+    if ((p.flags & HGSF_POINTS_SPCONV1_BREAK) && cta == 0) for (int b = tid; b < p.B; b += FRONT_THREADS) p.cutoff[b] = INT_MAX;
     if (!clean) {
         uint4 *t4 = reinterpret_cast<uint4 *>(p.cell_tag);           // tag, cnt: two arrays back to back
         const long long n4 = (long long)(p.table_bytes >> 4);
@@ -448,6 +452,8 @@ __global__ void __launch_bounds__(FRONT_THREADS, 4) k_front(const PathParams p) 
                     const int b = (int)fastdiv((uint32_t)key[u], p.div_cells);
                     const int local = (int)(tag[u] - 1u) - p.frame_raw_base[b];
                     on[u] = local < p.max_voxels;             // pillar beyond max_voxels: never created
+                    // spconv 1.x: the first point of the first refused pillar is where the voxelization loop stopped
+                    if ((p.flags & HGSF_POINTS_SPCONV1_BREAK) && first[u] && local == p.max_voxels) p.cutoff[b] = idx[u];
                 }
             }
         }
@@ -463,6 +469,10 @@ __global__ void __launch_bounds__(FRONT_THREADS, 4) k_front(const PathParams p) 
                 v[u].y = (k + 1 < p.F) ? __ldg(src + k + 1) : (k + 1 == p.F ? fi : 0.f);
                 v[u].z = (k + 2 < p.F) ? __ldg(src + k + 2) : (k + 2 == p.F ? fi : 0.f);
                 v[u].w = (k + 3 < p.F) ? __ldg(src + k + 3) : (k + 3 == p.F ? fi : 0.f);
+                if (k == 0) {
+                    if (p.flags & HGSF_POINTS_FLIP_X) v[u].x = -v[u].x;
+                    if (p.flags & HGSF_POINTS_FLIP_Y) v[u].y = -v[u].y;
+                }
             }
 #pragma unroll
             for (int u = 0; u < PPT; ++u) {
@@ -839,7 +849,17 @@ __global__ void __launch_bounds__(PT, HGSF_PILLARS_MINB) k_pillars(const PathPar
         const int local = e.y - s_R[b];
         const bool kept = valid && (local < maxv);            // pillars beyond max_voxels were never created
         const int f = s_K[b] + local;                          // final pillar id (first-seen order, frames concatenated)
-        const int n_keep = min(cnt, Pmax);
+        // spconv 1.x overflow: points from the frame's cut-off index on were never seen by the voxelizer
+        const int cut = ((p.flags & HGSF_POINTS_SPCONV1_BREAK) && kept) ? p.cutoff[b] : INT_MAX;
+        int cnt_eff = cnt;
+        if (__any_sync(FULL, cut != INT_MAX)) {
+            if (cut != INT_MAX && cnt <= 32) {
+                cnt_eff = 0;
+                for (int s2 = 0; s2 < cnt; ++s2)
+                    cnt_eff += (__float_as_uint(__ldg(grows + (size_t)(start + s2) * RW + Fr)) < (uint32_t)cut) ? 1 : 0;
+            }
+        }
+        const int n_keep = min(cnt_eff, Pmax);                 // (a pillar with more than 32 arrivals counts its own, below)
         // the pillar's cell: key = b*cells + (z*ny + y)*nxp + x
         const uint32_t rem = (uint32_t)(key - b * p.cells);
         const uint32_t pz = fastdiv(rem, p.div_plane), rem2 = rem - pz * (uint32_t)(p.ny * p.nxp);
@@ -922,7 +942,7 @@ __global__ void __launch_bounds__(PT, HGSF_PILLARS_MINB) k_pillars(const PathPar
                 const int pos0 = (cnt == 1) ? 0 : (int)perm[lane][0];
                 // bit 24: the pillar was truncated to its first P points, so the unit lanes must go through the rank table; an
                 // untruncated pillar is evaluated in arrival order (the max does not care), one dependent shared-memory load less
-                rec[slot][0] = make_float4(mx, my, mz, __int_as_float(n_keep | (lane << 8) | (pos0 << 16) | ((cnt > Pmax) ? (1 << 24) : 0)));
+                rec[slot][0] = make_float4(mx, my, mz, __int_as_float(n_keep | (lane << 8) | (pos0 << 16) | ((cnt > n_keep) ? (1 << 24) : 0)));
                 rec[slot][1] = make_float4(cx, cy, cz, __int_as_float(rel));
             }
             // the feature block: columns of pillars that were never created (beyond max_voxels) read as zero on the canvas
@@ -1004,8 +1024,18 @@ __global__ void __launch_bounds__(PT, HGSF_PILLARS_MINB) k_pillars(const PathPar
             hm &= hm - 1;
             const int cnt_o = __shfl_sync(FULL, cnt, o), start_o = __shfl_sync(FULL, start, o), f_o = __shfl_sync(FULL, f, o);
             const float cx_o = __shfl_sync(FULL, cx, o), cy_o = __shfl_sync(FULL, cy, o), cz_o = __shfl_sync(FULL, cz, o);
-            const int nk = min(cnt_o, Pmax);
             const float *grow_o = grows + (size_t)start_o * RW;
+            int cnt_e = cnt_o;
+            const int cut_o = __shfl_sync(FULL, cut, o);
+            if (cut_o != INT_MAX) {
+                cnt_e = 0;
+                for (int j0 = 0; j0 < cnt_o; j0 += 32) {
+                    const int j = j0 + lane;
+                    cnt_e += __popc(__ballot_sync(FULL, j < cnt_o && __float_as_uint(__ldg(grow_o + (size_t)j * RW + Fr)) < (uint32_t)cut_o));
+                }
+            }
+            const int nk = min(cnt_e, Pmax);
+            if (lane == 0) p.num[f_o] = nk;
             {
                 // the pillar's first nk points by index, 32 per round (P <= 32: one round)
                 uint32_t lo = 0u, key = 0u;
@@ -1057,7 +1087,7 @@ __global__ void __launch_bounds__(PT, HGSF_PILLARS_MINB) k_pillars(const PathPar
                 const int o = __ffs(todo) - 1;
                 todo &= todo - 1;
                 const int cnt_o = __shfl_sync(FULL, cnt, o), rel_o = __shfl_sync(FULL, rel, o), f_o = __shfl_sync(FULL, f, o);
-                const int nk = min(cnt_o, Pmax);
+                const int nk = __shfl_sync(FULL, n_keep, o);
                 float *vo = p.voxels + (size_t)f_o * Pmax * Fr;
                 for (int t = lane; t < Pmax * Fr; t += 32) {
                     const int s2 = t / Fr, kk = t - s2 * Fr;

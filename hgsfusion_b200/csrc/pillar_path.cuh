@@ -64,6 +64,8 @@ struct PathParams {
     int RW;
     int pslice, cslice;                // points / cells per k_front CTA (multiples of 32)
     int canvas_vec;                    // the canvas is written with 16-byte stores (nx % 4 == 0, aligned base)
+    int flags;                         // hgsf_points.flags (HGSF_POINTS_*)
+    int32_t *cutoff;                   // [B] HGSF_POINTS_SPCONV1_BREAK: index of the frame's first dropped point (INT_MAX: none)
     int dbg;                           // experiment switches (HGSF_DBG), 0 in normal use
     // ---- PFN ----
     const float *W, *bias, *bn_w, *bn_b, *bn_m, *bn_v;
@@ -75,7 +77,7 @@ struct PathParams {
 };
 
 struct WorkspaceLayout {
-    size_t off_ticket, off_state, off_desc, off_raw_base, off_table, off_tile_rec, off_heavy;
+    size_t off_ticket, off_state, off_desc, off_raw_base, off_cutoff, off_table, off_tile_rec, off_heavy;
     size_t off_frame_offsets, off_key, off_arrival, off_sorted_rows, off_pil;
     size_t total, cell_array_bytes;
     int RW, nxp;
@@ -95,6 +97,7 @@ inline WorkspaceLayout workspace_layout(int64_t n, int B, int nx, int ny, int nz
     w.off_state = o;       o = align_up(o + 256, 256);
     w.off_desc = o;        o = align_up(o + sizeof(uint32_t) * 3 * MAX_FRONT_CTAS, 256);
     w.off_raw_base = o;    o = align_up(o + sizeof(int32_t) * (size_t)(B + 1), 256);
+    w.off_cutoff = o;      o = align_up(o + sizeof(int32_t) * (size_t)(B + 1), 256);
     w.cell_array_bytes = align_up(sizeof(uint32_t) * ((size_t)B * (size_t)w.cells + 32), 256);
     w.off_table = o;       o = o + 3 * w.cell_array_bytes;
     w.off_tile_rec = o;    o = align_up(o + sizeof(uint4) * ((size_t)B * (size_t)w.cells / 32 + 1), 256);

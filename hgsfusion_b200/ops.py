@@ -100,7 +100,13 @@ class PillarPath:
     four kernels on the current stream and returns without synchronising."""
 
     def __init__(self, point_cloud_range, voxel_size, max_points_per_voxel: int, max_voxels: int,
-                 num_point_features: int, grid_size=None):
+                 num_point_features: int, grid_size=None, spconv_version: int = 2):
+        """spconv_version: whose overflow semantics to reproduce when a frame holds more than max_voxels pillars -- 2
+        (Point2VoxelCPU3d: later NEW pillars are refused) or 1 (VoxelGenerator: the loop stops there, dropping every later
+        point).  VoxelGeneratorWrapper picks whichever spconv is installed (data_processor.py:16-26)."""
+        if spconv_version not in (1, 2):
+            raise ValueError("spconv_version must be 1 or 2")
+        self.flags = _lib.POINTS_SPCONV1_BREAK if spconv_version == 1 else 0
         self.lib = _lib.load()
         self.geom = make_geometry(point_cloud_range, voxel_size, grid_size)
         self.nx, self.ny, self.nz = (int(v) for v in self.geom.grid)
@@ -123,7 +129,7 @@ class PillarPath:
             self._ws = torch.empty(need.value + 256, dtype=torch.uint8, device=device)
         return self._ws
 
-    def _points_struct(self, points, batch_size, xyz_col, batch_col, frame_offsets):
+    def _points_struct(self, points, batch_size, xyz_col, batch_col, frame_offsets, flip=(False, False)):
         pts = _f32c(points, "points")
         if pts.dim() != 2:
             raise ValueError("points must be [n, stride]")
@@ -140,11 +146,12 @@ class PillarPath:
             s.frame_offsets = fo.data_ptr()
             keep.append(fo)
         s.batch_size = int(batch_size)
+        s.flags = self.flags | (_lib.POINTS_FLIP_X if flip[0] else 0) | (_lib.POINTS_FLIP_Y if flip[1] else 0)
         return s, keep
 
     def _run(self, points, batch_size, pfn, xyz_col, batch_col, frame_offsets, want_voxels, want_features,
-             want_canvas, out: PillarResult | None):
-        ps, keep = self._points_struct(points, batch_size, xyz_col, batch_col, frame_offsets)
+             want_canvas, out: PillarResult | None, flip=(False, False)):
+        ps, keep = self._points_struct(points, batch_size, xyz_col, batch_col, frame_offsets, flip)
         dev = points.device
         cap = max(self.capacity(ps.n, batch_size), 1)
         ws = self._workspace(ps.n, batch_size, dev)
@@ -184,9 +191,16 @@ class PillarPath:
 
     # -- public ----------------------------------------------------------------------------------
     def pillarize(self, points, batch_size, xyz_col=1, batch_col=0, frame_offsets=None, want_voxels=True,
-                  out: PillarResult | None = None) -> PillarResult:
-        """points [n, stride] -> voxels, voxel_coords, voxel_num_points (transform_points_to_voxels + collate)."""
-        return self._run(points, batch_size, None, xyz_col, batch_col, frame_offsets, want_voxels, False, False, out)
+                  out: PillarResult | None = None, flip=(False, False)) -> PillarResult:
+        """points [n, stride] -> voxels, voxel_coords, voxel_num_points (transform_points_to_voxels + collate).
+        flip = (flip_x, flip_y): voxelize the mirrored cloud (DataProcessor.double_flip) without copying the points."""
+        return self._run(points, batch_size, None, xyz_col, batch_col, frame_offsets, want_voxels, False, False, out, flip)
+
+    def pillarize_double_flip(self, points, batch_size, xyz_col=1, batch_col=0, frame_offsets=None):
+        """DOUBLE_FLIP test-time augmentation (data_processor.py:161-178): the cloud and its y-, x- and xy-mirrored copies,
+        voxelized one after the other -> four PillarResults in the reference's order [original, yflip, xflip, xyflip]."""
+        return [self.pillarize(points, batch_size, xyz_col, batch_col, frame_offsets, True, None, flip)
+                for flip in ((False, False), (False, True), (True, False), (True, True))]
 
     def points_to_bev(self, points, batch_size, pfn: PfnWeights, xyz_col=1, batch_col=0, frame_offsets=None,
                       want_voxels=False, want_features=True, want_canvas=True,

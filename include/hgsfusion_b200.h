@@ -63,7 +63,17 @@ typedef struct hgsf_points {
     int32_t        batch_col;     /* -1 if absent */
     const int32_t *frame_offsets; /* device int32[batch_size+1] or NULL */
     int32_t        batch_size;    /* B */
+    int32_t        flags;         /* HGSF_POINTS_* below, 0 = the default path */
 } hgsf_points;
+
+/* hgsf_points.flags */
+#define HGSF_POINTS_SPCONV1_BREAK 1   /* spconv 1.x overflow semantics (VoxelGenerator.generate, which VoxelGeneratorWrapper prefers
+                                       * when it imports: data_processor.py:16-26,47-52): the voxelization loop STOPS at the first
+                                       * point that would open pillar number max_voxels + 1, dropping every later point of the frame;
+                                       * default = spconv 2.x (Point2VoxelCPU3d): only new pillars are refused                       */
+#define HGSF_POINTS_FLIP_X        2   /* voxelize (-x, y, z, ...): DataProcessor.double_flip's x flip (data_processor.py:116-130,
+                                       * 161-178); the stored features carry the flipped sign, as the reference's copies do          */
+#define HGSF_POINTS_FLIP_Y        4   /* likewise (x, -y, z, ...)                                                                     */
 
 /* The single (last) PFN layer of PillarVFE (pillar_vfe.py:8-49,63-74), eval mode.
  * weight = pfn_layers.0.linear.weight [C, Cin]; USE_NORM=True: BatchNorm1d(eps=1e-3) running stats;

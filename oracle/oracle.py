@@ -43,6 +43,7 @@ def lib():
     if _LIB is None:
         _LIB = C.CDLL(build())
         _LIB.orc_voxelize.restype = C.c_int32
+        _LIB.orc_voxelize_mode.restype = C.c_int32
         _LIB.orc_voxelize_batch.restype = C.c_int64
         _LIB.orc_points_to_bev.restype = C.c_int64
         _LIB.orc_mask_points_by_range.restype = C.c_int64
@@ -98,8 +99,9 @@ def mask_points_by_range(points, pc_range, xcol=0):
 
 
 def voxelize(points, geom: Geometry, P: int, max_voxels: int, F: int | None = None, xcol: int = 0,
-             return_point_pillar: bool = False):
-    """One frame.  points [n, stride] fp32.  Returns voxels [M,P,F], coords [M,3] int32 (z,y,x), num [M] int32."""
+             return_point_pillar: bool = False, spconv1_break: bool = False):
+    """One frame.  points [n, stride] fp32.  Returns voxels [M,P,F], coords [M,3] int32 (z,y,x), num [M] int32.
+    spconv1_break: spconv 1.x overflow semantics (the loop stops at the first point that would open pillar max_voxels + 1)."""
     pts = _f32(points)
     n, stride = pts.shape
     F = stride - xcol if F is None else F
@@ -110,15 +112,15 @@ def voxelize(points, geom: Geometry, P: int, max_voxels: int, F: int | None = No
     coords = np.zeros((cap, 3), dtype=np.int32)
     num = np.zeros(cap, dtype=np.int32)
     pp = np.zeros(max(n, 1), dtype=np.int32) if return_point_pillar else None
-    m = lib().orc_voxelize(_p(pts), C.c_int64(n), C.c_int(stride), C.c_int(xcol), C.c_int(F),
-                           _p(geom.pc_range), _p(geom.vsize_f32), _p(grid), C.c_int(P), C.c_int(max_voxels),
-                           _p(lookup), _p(voxels), _p(coords), _p(num), _p(pp))
+    m = lib().orc_voxelize_mode(_p(pts), C.c_int64(n), C.c_int(stride), C.c_int(xcol), C.c_int(F),
+                                _p(geom.pc_range), _p(geom.vsize_f32), _p(grid), C.c_int(P), C.c_int(max_voxels),
+                                _p(lookup), _p(voxels), _p(coords), _p(num), _p(pp), C.c_int(int(spconv1_break)))
     assert (lookup == -1).all()
     out = (voxels[:m].copy(), coords[:m].copy(), num[:m].copy())
     return out + (pp[:n],) if return_point_pillar else out
 
 
-def voxelize_py(points, geom: Geometry, P: int, max_voxels: int, F: int | None = None, xcol: int = 0):
+def voxelize_py(points, geom: Geometry, P: int, max_voxels: int, F: int | None = None, xcol: int = 0, spconv1_break: bool = False):
     """Independent pure-Python twin of `voxelize` (slow; small cases only)."""
     pts = _f32(points)
     n, stride = pts.shape
@@ -142,6 +144,8 @@ def voxelize_py(points, geom: Geometry, P: int, max_voxels: int, F: int | None =
         v = table.get(key, -1)
         if v == -1:
             if len(coords) >= max_voxels:
+                if spconv1_break:
+                    break
                 continue
             v = len(coords)
             table[key] = v

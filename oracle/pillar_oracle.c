@@ -111,13 +111,30 @@ ORC_API void orc_grid_size(const float *range6, const double *vsize3, int32_t *g
 /*   point_pillar (optional, may be NULL) [n] int32: pillar id the point was    */
 /*            stored in, -1 if dropped (out of range, overflow or truncated)    */
 /* returns the number of pillars.                                              */
+/* overflow_break = 0: spconv 2.x (Point2VoxelCPU3d): a point that would open pillar number max_voxels + 1 is skipped      */
+/*                      (`continue`), later points still fill the pillars that exist.                                    */
+/* overflow_break = 1: spconv 1.x (VoxelGenerator / points_to_voxel, which data_processor.py:16-26 prefers when it       */
+/*                      imports): the loop `break`s at that point -- every later point of the frame is dropped.          */
+ORC_API int32_t orc_voxelize_mode(const float *points, int64_t n, int stride, int xcol, int F,
+                                  const float *range6, const float *vsize3, const int32_t *grid3,
+                                  int P, int max_voxels, int32_t *lookup,
+                                  float *voxels, int32_t *coords, int32_t *num, int32_t *point_pillar, int overflow_break);
 ORC_API int32_t orc_voxelize(const float *points, int64_t n, int stride, int xcol, int F,
                              const float *range6, const float *vsize3, const int32_t *grid3,
                              int P, int max_voxels, int32_t *lookup,
                              float *voxels, int32_t *coords, int32_t *num, int32_t *point_pillar)
 {
+    return orc_voxelize_mode(points, n, stride, xcol, F, range6, vsize3, grid3, P, max_voxels, lookup, voxels, coords, num,
+                             point_pillar, 0);
+}
+ORC_API int32_t orc_voxelize_mode(const float *points, int64_t n, int stride, int xcol, int F,
+                                  const float *range6, const float *vsize3, const int32_t *grid3,
+                                  int P, int max_voxels, int32_t *lookup,
+                                  float *voxels, int32_t *coords, int32_t *num, int32_t *point_pillar, int overflow_break)
+{
     const int nx = grid3[0], ny = grid3[1];
     int32_t voxel_num = 0;
+    int stop = 0;
     for (int64_t i = 0; i < n; ++i) {
         const float *pt = points + i * stride + xcol;
         int c[3];
@@ -131,10 +148,14 @@ ORC_API int32_t orc_voxelize(const float *points, int64_t n, int stride, int xco
         }
         if (point_pillar) point_pillar[i] = -1;
         if (!ok) continue;
+        if (stop) continue;                          /* spconv 1.x broke out of the loop earlier */
         const int64_t cell = ((int64_t)c[2] * ny + c[1]) * nx + c[0];
         int32_t v = lookup[cell];
         if (v == -1) {
-            if (voxel_num >= max_voxels) continue;   /* later NEW pillars are dropped */
+            if (voxel_num >= max_voxels) {           /* later NEW pillars are dropped ... */
+                if (overflow_break) stop = 1;        /* ... and with spconv 1.x everything after this point */
+                continue;
+            }
             v = voxel_num++;
             lookup[cell] = v;
             coords[3 * v + 0] = c[2];

@@ -110,3 +110,19 @@ def test_batch_matches_per_frame_and_is_thread_invariant():
         assert np.array_equal(a["voxels"][m0:m0 + m], v) and np.array_equal(a["voxel_num_points"][m0:m0 + m], n)
         m0 += m
     assert m0 == a["num_pillars"]
+
+
+def test_spconv1_break_hand_case():
+    """max_voxels = 2 on a 1 m grid: points land in cells A, B, A, C (refused: third pillar), A, B.
+    spconv 2.x (`continue`): pillars A (3 points: #0, #2, #4) and B (2 points: #1, #5).
+    spconv 1.x (`break` at point #3): pillars A (2 points: #0, #2) and B (1 point: #1) -- points #4 and #5 are never looked at."""
+    geom = oracle.Geometry([0, 0, 0, 4, 4, 1], [1.0, 1.0, 1.0])
+    pts = np.array([[0.5, 0.5, 0.5, 10], [1.5, 0.5, 0.5, 11], [0.6, 0.4, 0.5, 12], [2.5, 0.5, 0.5, 13], [0.7, 0.3, 0.5, 14],
+                    [1.6, 0.4, 0.5, 15]], dtype=np.float32)
+    for twin in (oracle.voxelize, oracle.voxelize_py):
+        v, c, n = twin(pts, geom, 4, 2, F=4, xcol=0)
+        assert c.tolist() == [[0, 0, 0], [0, 0, 1]] and n.tolist() == [3, 2]
+        assert v[0, :3, 3].tolist() == [10, 12, 14] and v[1, :2, 3].tolist() == [11, 15]
+        v, c, n = twin(pts, geom, 4, 2, F=4, xcol=0, spconv1_break=True)
+        assert c.tolist() == [[0, 0, 0], [0, 0, 1]] and n.tolist() == [2, 1]
+        assert v[0, :, 3].tolist() == [10, 12, 0, 0] and v[1, :, 3].tolist() == [11, 0, 0, 0]
