@@ -760,7 +760,9 @@ __global__ void __launch_bounds__(PT, HGSF_PILLARS_MINB) k_pillars(const PathPar
     //      per warp (the same-address atomics queue three times as long: +6 %); the first half of the runs assigned round-robin
     //      without tickets (the window of tiles in flight spreads: +16 %); 4 / 8 / 16 interleaved ticket counters (counter j
     //      hands out runs j, j + NQ, ...: the counters drift apart and the write window loses its order: +17 %, even on an almost
-    //      empty scene, where the kernel is a pure zero-fill).] ----
+    //      empty scene, where the kernel is a pure zero-fill); one tile per group with a tile-layout buffer and one TMA tensor store
+    //      per tile instead of the gather + 16 coalesced stores below (same time on VoD, +10 % on TJ4D and on sparse scenes: twice
+    //      as many groups, and the group's fixed cost is what the sparse tiles pay).] ----
     //      Before all of that come the HEAVY tiles k_front listed (more than p.heavy_pts points), one tile per run: a single warp
     //      needs up to half the kernel's duration for the densest tile of a clustered scene, so it has to start at once; the moving
     //      window later steps over them.
