@@ -30,8 +30,13 @@
 // 64 -> 64 (the weights take 147 KB of the SM's shared memory, one CTA per SM): 8-pillar x 4-channel thread tiles over 128-pillar
 // tiles, 256 threads, 2 stages: 0.278 ms for the 143 k pillars of conv2's active set = 38.0 TFLOP/s, 51 % of the peak (4 x 4 over 64
 // pillars 27.4; 3 stages 30.5; 16 x 4 35.6; 8 x 8 with 128 threads 32.2 -- too few warps).
+// 128 and 256 channels (conv3 / conv4, pcnres18.py:227-245): 9 x Cin x Cout weights no longer fit shared memory (590 KB / 2.4 MB), so
+// the output channels are cut into SLICES whose weights do (147 KB each: 64 of 64 -> 128, 32 of 128 -> {128, 256}, 16 of 256 -> 256);
+// blockIdx.y = slice, every slice gathers the input rows again (L2 hits: these layers run on the stride-4 / stride-8 active sets,
+// at most a few ten thousand pillars).  Same arithmetic (fp32 FMA in (tap, ci) order), same fused epilogue.
 #include "subm_conv.cuh"
 
+#include <algorithm>
 #include <cstdlib>
 
 #ifndef SUBM_UNROLL
@@ -123,15 +128,24 @@ __global__ void __launch_bounds__(SubmCfg<CIN, COUT, PT, NCO, TM, NBUF>::THREADS
     const long long M = q.m_dev ? min((long long)max(q.m_dev[0], 0), q.M) : q.M;
     const long long n_tiles = (M + TM - 1) / TM;
     if ((long long)blockIdx.x >= n_tiles) return;
+    // COUT is the width of this CTA's slice of the q.Cout output channels: channels co0 .. co0 + COUT - 1
+    const int CT = q.Cout, co0 = (int)blockIdx.y * COUT;
 
-    // the weights, once per CTA, into [tap][ci][co]
+    // the slice's weights, once per CTA, into [tap][ci][co]
     if (q.layout == 1) {
-        for (int i = tid; i < 9 * CIN * COUT / 4; i += THREADS)
-            reinterpret_cast<float4 *>(Ws)[i] = __ldg(reinterpret_cast<const float4 *>(q.W) + i);
+        if (CT == COUT) {
+            for (int i = tid; i < 9 * CIN * COUT / 4; i += THREADS)
+                reinterpret_cast<float4 *>(Ws)[i] = __ldg(reinterpret_cast<const float4 *>(q.W) + i);
+        } else {
+            for (int i = tid; i < 9 * CIN * COUT / 4; i += THREADS) {      // rows of COUT floats out of rows of CT
+                const int r = i / (COUT / 4), c = i - r * (COUT / 4);
+                reinterpret_cast<float4 *>(Ws)[i] = __ldg(reinterpret_cast<const float4 *>(q.W + (size_t)r * CT + co0) + c);
+            }
+        }
     } else {
         for (int i = tid; i < 9 * CIN * COUT; i += THREADS) {      // source order [co][tap][ci]: coalesced reads
             const int ci = i % CIN, k = (i / CIN) % 9, co = i / (9 * CIN);
-            Ws[(k * CIN + ci) * COUT + co] = __ldg(q.W + i);
+            Ws[(k * CIN + ci) * COUT + co] = __ldg(q.W + (size_t)co0 * 9 * CIN + i);
         }
     }
 
@@ -139,7 +153,7 @@ __global__ void __launch_bounds__(SubmCfg<CIN, COUT, PT, NCO, TM, NBUF>::THREADS
     float bnm[NCO], bni[NCO], bnw[NCO], bnb[NCO], bia[NCO];
 #pragma unroll
     for (int c = 0; c < NCO; ++c) {
-        const int co = tx * NCO + c;
+        const int co = co0 + tx * NCO + c;
         bia[c] = q.bias ? q.bias[co] : 0.f;
         if (q.bn_w) {
             bnm[c] = q.bn_m[co];
@@ -238,7 +252,7 @@ __global__ void __launch_bounds__(SubmCfg<CIN, COUT, PT, NCO, TM, NBUF>::THREADS
                 if (q.bn_w) t = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(t, bnm[c]), bni[c]), bnw[c]), bnb[c]);
                 v[c] = t;
             }
-            const size_t o = (size_t)row * COUT + tx * NCO;
+            const size_t o = (size_t)row * CT + co0 + tx * NCO;
             if (q.residual) {
 #pragma unroll
                 for (int c = 0; c < NCO; ++c) v[c] = __fadd_rn(v[c], q.residual[o + c]);
@@ -256,10 +270,12 @@ __global__ void __launch_bounds__(SubmCfg<CIN, COUT, PT, NCO, TM, NBUF>::THREADS
     }
 }
 
+// COUT = slice width (== q.Cout for the layers whose weights fit shared memory whole)
 template <int CIN, int COUT, int PT, int NCO, int TM, int NBUF>
 int launch_conv_t(const SubmConvParams &q, cudaStream_t stream) {
     using S = SubmCfg<CIN, COUT, PT, NCO, TM, NBUF>;
     auto kern = k_subm_conv<CIN, COUT, PT, NCO, TM, NBUF>;
+    const int slices = q.Cout / COUT;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::total);
     if (e != cudaSuccess) return (int)e;
     int dev = 0, sms = 0, per_sm = 0;
@@ -268,8 +284,9 @@ int launch_conv_t(const SubmConvParams &q, cudaStream_t stream) {
     if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, S::THREADS, S::total)) != cudaSuccess) return (int)e;
     if (per_sm < 1) return HGSF_ERR_UNSUPPORTED;
     const long long tiles = (q.M + TM - 1) / TM;
-    const long long grid = tiles < (long long)sms * per_sm ? tiles : (long long)sms * per_sm;
-    kern<<<(unsigned)grid, S::THREADS, S::total, stream>>>(q);
+    long long grid = tiles < (long long)sms * per_sm ? tiles : (long long)sms * per_sm;
+    if (slices > 1) grid = std::max<long long>(1, std::min<long long>(tiles, ((long long)sms * per_sm + slices - 1) / slices));
+    kern<<<dim3((unsigned)grid, (unsigned)slices), S::THREADS, S::total, stream>>>(q);
     return (int)cudaGetLastError();
 }
 
@@ -325,6 +342,10 @@ int launch_subm_conv(const SubmConvParams &q, cudaStream_t stream) {
         return launch_conv_t<64, 64, 8, 4, 128, 2>(q, stream);
     }
     if (q.Cin == 32 && q.Cout == 64) return launch_conv_t<32, 64, 4, 4, 64, 3>(q, stream);
+    // conv3 / conv4: output channels in slices whose weights fit shared memory (see the header)
+    if (q.Cin == 64 && q.Cout == 128) return launch_conv_t<64, 64, 8, 4, 128, 2>(q, stream);
+    if (q.Cin == 128 && (q.Cout == 128 || q.Cout == 256)) return launch_conv_t<128, 32, 4, 4, 64, 2>(q, stream);
+    if (q.Cin == 256 && q.Cout == 256) return launch_conv_t<256, 16, 2, 2, 32, 2>(q, stream);
     return HGSF_ERR_UNSUPPORTED;
 }
 

@@ -543,3 +543,43 @@ class PillarEncoderConv2(nn.Module):
         x = getattr(self, "3")(x, nbr)
         x = getattr(self, "4")(x, nbr)
         return x, r["pillars"], r["pillar_bev_indices"]
+
+
+class PillarEncoderConv3(PillarEncoderConv2):
+    """`SpMiddlePillarEncoder18.conv3` (pcnres18.py:227-235): SparseConv2d(64, 128, 3, 2, padding 1) + BatchNorm1d + ReLU + two
+    Sparse2DBasicBlock(128, 128) (indice key "res3"); same structure and sub-module names as conv2."""
+
+    def __init__(self, inplanes=64, planes=128):
+        super().__init__(inplanes, planes)
+
+
+class PillarEncoderConv4(PillarEncoderConv2):
+    """`SpMiddlePillarEncoder18.conv4` (pcnres18.py:237-245): 128 -> 256, stride 2, + two Sparse2DBasicBlock(256, 256) ("res4")."""
+
+    def __init__(self, inplanes=128, planes=256):
+        super().__init__(inplanes, planes)
+
+
+class SpMiddlePillarEncoder18(nn.Module):
+    """The whole sparse encoder behind the reader (pcnres18.py:200-285) on pillar lists: conv1 .. conv4 with the reference's
+    attribute names, so that a reference checkpoint's `conv1.*` .. `conv4.*` keys load.  forward(pillar_features, pillars,
+    pillar_bev_indices) -> [(features, pillars [M,3] (b,y,x), pillar_bev_indices [B,H,W])] for x_conv1 .. x_conv4 filtered by
+    `out_indices` as the reference does (:278-281); `sparse_to_dense` turns an entry into the [B,C,H,W] tensor `.dense()` gives."""
+
+    def __init__(self, in_planes=32, out_indices=(1, 2, 3)):
+        super().__init__()
+        self.out_indices = list(out_indices)
+        self.conv1 = PillarEncoderConv1(in_planes)
+        self.conv2 = PillarEncoderConv2(in_planes, 64)
+        self.conv3 = PillarEncoderConv3(64, 128)
+        self.conv4 = PillarEncoderConv4(128, 256)
+        self.backbone_channels = {'x_conv1': 32, 'x_conv2': 64, 'x_conv3': 128, 'x_conv4': 256}
+        self.backbone_strides = {'x_conv1': 1, 'x_conv2': 2, 'x_conv3': 4, 'x_conv4': 8}
+
+    def forward(self, pillar_features, pillars, pillar_bev_indices):
+        x1 = (self.conv1(pillar_features, pillars, pillar_bev_indices), pillars, pillar_bev_indices)
+        x2 = self.conv2(*x1)
+        x3 = self.conv3(*x2)
+        x4 = self.conv4(*x3)
+        outs = [x1, x2, x3, x4]
+        return [outs[i] for i in self.out_indices]

@@ -44,7 +44,7 @@ def test_neighbors_bit_exact(cuda, B, H, W, M_per):
     assert np.array_equal(got.cpu().numpy(), pb.subm_neighbors(bev, pillars))
 
 
-@pytest.mark.parametrize("Cin,Cout", [(32, 32), (64, 64), (32, 64)])
+@pytest.mark.parametrize("Cin,Cout", [(32, 32), (64, 64), (32, 64), (64, 128), (128, 128), (128, 256), (256, 256)])
 @pytest.mark.parametrize("layout", ["KRSC", "RSCK"])
 @pytest.mark.parametrize("opts", [dict(), dict(bias=True), dict(bias=True, bn=True, relu=True), dict(bias=True, bn=True, res=True, relu=True)])
 def test_conv_matches_oracle(cuda, Cin, Cout, layout, opts):
@@ -300,3 +300,62 @@ def test_reader_to_conv1_conv2_to_dense_end_to_end(cuda, geom):
             torch.backends.cudnn.allow_tf32 = old
     assert got.shape == x.shape
     assert (got - x).abs().max().item() <= 5e-5 * max(1.0, x.abs().max().item())      # eleven fp32 layers deep
+
+
+def test_whole_sparse_encoder_conv1_to_conv4_against_dense_cudnn(cuda):
+    """SpMiddlePillarEncoder18 (pcnres18.py:200-285) on pillar lists, all four stages (32 -> 32, 64, 128, 256 channels at strides
+    1 / 2 / 4 / 8), against the dense torch composition of the same modules (cuDNN fp32, masked to the active sets) on the same
+    GPU; the module tree carries the reference's parameter names (conv1.0.conv0.0.weight ... conv4.4.conv2.1.running_var)."""
+    import torch.nn.functional as F
+    rng = np.random.default_rng(77)
+    B, H, W = 2, 96, 80
+    pillars_np, bev_np = _random_pillars(rng, B, H, W, 900)
+    pillars, bev = torch.from_numpy(pillars_np).to(cuda), torch.from_numpy(bev_np).to(cuda)
+    M = pillars.shape[0]
+    feats = torch.from_numpy(np.abs(rng.normal(size=(M, 32))).astype(np.float32)).to(cuda)
+    torch.manual_seed(5)
+    enc = po.SpMiddlePillarEncoder18(32, out_indices=(0, 1, 2, 3)).to(cuda).eval()
+    for m in enc.modules():
+        if isinstance(m, torch.nn.BatchNorm1d):
+            m.load_state_dict(_bn(rng, m.num_features, cuda).state_dict())
+    keys = set(enc.state_dict().keys())
+    assert {"conv1.0.conv0.0.weight", "conv2.0.weight", "conv3.0.weight", "conv3.3.conv1.0.bias", "conv4.4.conv2.1.running_var"} <= keys
+    assert enc.state_dict()["conv4.0.weight"].shape == (256, 3, 3, 128) and "conv3.0.bias" not in keys
+    with torch.no_grad():
+        outs = enc(feats, pillars, bev)
+        assert [o[0].shape[1] for o in outs] == [32, 64, 128, 256]
+        old = torch.backends.cudnn.allow_tf32
+        torch.backends.cudnn.allow_tf32 = False
+        try:
+            idx = pillars.long()
+            mask = torch.zeros((B, 1, H, W), device=cuda); mask[idx[:, 0], 0, idx[:, 1], idx[:, 2]] = 1
+
+            def cb(seq, x, res, msk, stride=1):
+                conv, bn = seq
+                y = F.conv2d(x, conv.weight.permute(0, 3, 1, 2).contiguous(), conv.bias, stride=stride, padding=1)
+                y = F.batch_norm(y, bn.running_mean, bn.running_var, bn.weight, bn.bias, False, 0.0, bn.eps)
+                if res is not None: y = y + res
+                return torch.relu(y) * msk
+            x = po.sparse_to_dense(feats, pillars, (H, W), B)
+            b0, b1 = getattr(enc.conv1, "0"), getattr(enc.conv1, "1")
+            i = cb(b0.conv0, x, None, mask); x = cb(b0.conv2, cb(b0.conv1, i, None, mask), i, mask)
+            x = cb(b1.conv2, cb(b1.conv1, x, None, mask), x, mask)
+            dense = [x]
+            for stage in (enc.conv2, enc.conv3, enc.conv4):
+                mask = (F.max_pool2d(mask, 3, 2, 1) > 0).float()
+                x = cb((getattr(stage, "0"), getattr(stage, "1")), x, None, mask, stride=2)
+                for name in ("3", "4"):
+                    blk = getattr(stage, name)
+                    x = cb(blk.conv2, cb(blk.conv1, x, None, mask), x, mask)
+                dense.append(x)
+        finally:
+            torch.backends.cudnn.allow_tf32 = old
+        for (f, pl, bv), ref in zip(outs, dense):
+            got = po.sparse_to_dense(f, pl, (bv.shape[1], bv.shape[2]), B)
+            assert got.shape == ref.shape
+            assert (got - ref).abs().max().item() <= 1e-4 * max(1.0, ref.abs().max().item())      # up to 21 fp32 layers deep, K up to 2304
+            assert int((mask_of(got) != mask_of(ref)).sum()) == 0
+
+
+def mask_of(t):
+    return (t != 0).any(dim=1)
