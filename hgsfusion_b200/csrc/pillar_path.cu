@@ -567,7 +567,10 @@ __device__ __noinline__ int select_next32(const float *__restrict__ idx0, int st
 constexpr int PW = 4;                 // warps per CTA
 constexpr int PT = PW * 32;
 constexpr int SMALL_CNT = 6;          // up to this many arrivals the owning lane ranks them itself
-constexpr int MAX_P = 128;            // largest max_points_per_voxel (the rank list of a > 32-point pillar lives in shared memory)
+#ifndef HGSF_MAX_P
+#define HGSF_MAX_P 128
+#endif
+constexpr int MAX_P = HGSF_MAX_P;     // largest max_points_per_voxel (the rank list of a > 32-point pillar lives in shared memory)
 #ifndef HGSF_RUN_TILES
 #define HGSF_RUN_TILES 2
 #endif
@@ -608,7 +611,8 @@ struct Group {        // whole tiles of one run holding at most 32 pillars
 #define HGSF_PILLARS_MINB 3
 #endif
 // CANVAS: also write spatial_features (p.canvas_vec: with 16-byte stores -- nx % 4 == 0 and an aligned canvas -- else scalar ones)
-template <int F, bool ABS, bool DIST, bool BN, bool PFN, bool CANVAS>
+// GEN: the general build (spconv 1.x cut-off, more than 32 points per pillar); the shipped configs run the lean one
+template <int F, bool ABS, bool DIST, bool BN, bool PFN, bool CANVAS, bool GEN>
 __global__ void __launch_bounds__(PT, HGSF_PILLARS_MINB) k_pillars(const PathParams p) {
     constexpr int C = 64;
     constexpr int CIN = PFN ? ((ABS ? F : F - 3) + 6 + (DIST ? 1 : 0)) : 1;
@@ -625,7 +629,7 @@ __global__ void __launch_bounds__(PT, HGSF_PILLARS_MINB) k_pillars(const PathPar
     int *s_K = s_R + (p.B + 1);                                                             // [B+1] kept (final) pillar base per frame
     __shared__ float4 s_rec_all[PW][32][2];                        // work lists: singles from the front, multis from the back
     __shared__ unsigned char s_perm_all[PW][32][32];               // per pillar: arrival position of its rank-th point
-    __shared__ int s_bperm_all[PW][MAX_P];                         // same for a pillar with > 32 arrivals: its first min(cnt, P) points
+    __shared__ int s_bperm_all[PW][GEN ? MAX_P : 32];                         // same for a pillar with > 32 arrivals: its first min(cnt, P) points
     __shared__ int s_fcol_all[PW][32];                             // final pillar id of the chunk's pillar j (-1: never created)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -852,9 +856,9 @@ __global__ void __launch_bounds__(PT, HGSF_PILLARS_MINB) k_pillars(const PathPar
         const bool kept = valid && (local < maxv);            // pillars beyond max_voxels were never created
         const int f = s_K[b] + local;                          // final pillar id (first-seen order, frames concatenated)
         // spconv 1.x overflow: points from the frame's cut-off index on were never seen by the voxelizer
-        const int cut = ((p.flags & HGSF_POINTS_SPCONV1_BREAK) && kept) ? p.cutoff[b] : INT_MAX;
+        const int cut = (GEN && (p.flags & HGSF_POINTS_SPCONV1_BREAK) && kept) ? p.cutoff[b] : INT_MAX;
         int cnt_eff = cnt;
-        if (__any_sync(FULL, cut != INT_MAX)) {
+        if (GEN && __any_sync(FULL, cut != INT_MAX)) {
             if (cut != INT_MAX && cnt <= 32) {
                 cnt_eff = 0;
                 for (int s2 = 0; s2 < cnt; ++s2)
@@ -1028,8 +1032,8 @@ __global__ void __launch_bounds__(PT, HGSF_PILLARS_MINB) k_pillars(const PathPar
             const float cx_o = __shfl_sync(FULL, cx, o), cy_o = __shfl_sync(FULL, cy, o), cz_o = __shfl_sync(FULL, cz, o);
             const float *grow_o = grows + (size_t)start_o * RW;
             int cnt_e = cnt_o;
-            const int cut_o = __shfl_sync(FULL, cut, o);
-            if (cut_o != INT_MAX) {
+            const int cut_o = GEN ? __shfl_sync(FULL, cut, o) : INT_MAX;
+            if (GEN && cut_o != INT_MAX) {
                 cnt_e = 0;
                 for (int j0 = 0; j0 < cnt_o; j0 += 32) {
                     const int j = j0 + lane;
@@ -1037,14 +1041,18 @@ __global__ void __launch_bounds__(PT, HGSF_PILLARS_MINB) k_pillars(const PathPar
                 }
             }
             const int nk = min(cnt_e, Pmax);
-            if (lane == 0) p.num[f_o] = nk;
+            if (GEN && lane == 0) p.num[f_o] = nk;
             {
-                // the pillar's first nk points by index, 32 per round (P <= 32: one round)
+                // the pillar's first nk points by index, 32 per round (the lean build has P <= 32: one round)
                 uint32_t lo = 0u, key = 0u;
-                for (int r0 = 0; r0 < nk; r0 += 32) {
-                    const int pos = select_next32(grow_o + Fr, RW, cnt_o, lane, r0 > 0, lo, key);
-                    if (r0 + lane < MAX_P) bperm[r0 + lane] = pos;
-                    lo = __shfl_sync(FULL, key, 31);
+                if (GEN) {
+                    for (int r0 = 0; r0 < nk; r0 += 32) {
+                        const int pos = select_next32(grow_o + Fr, RW, cnt_o, lane, r0 > 0, lo, key);
+                        if (r0 + lane < MAX_P) bperm[r0 + lane] = pos;
+                        lo = __shfl_sync(FULL, key, 31);
+                    }
+                } else {
+                    bperm[lane] = select_next32(grow_o + Fr, RW, cnt_o, lane, false, lo, key);
                 }
             }
             __syncwarp();
@@ -1282,11 +1290,16 @@ static int launch_pillars_t(const PathParams &p, cudaStream_t stream) {
 #endif
         return (int)cudaLaunchKernelEx(&cfg, kern, p);
     };
+    const bool gen = (p.flags & HGSF_POINTS_SPCONV1_BREAK) || p.P > 32;
     if constexpr (PFN) {
-        if (canvas) return bn ? go(k_pillars<F, ABS, DIST, true, true, true>) : go(k_pillars<F, ABS, DIST, false, true, true>);
-        return bn ? go(k_pillars<F, ABS, DIST, true, true, false>) : go(k_pillars<F, ABS, DIST, false, true, false>);
+        if (canvas) {
+            if (gen) return bn ? go(k_pillars<F, ABS, DIST, true, true, true, true>) : go(k_pillars<F, ABS, DIST, false, true, true, true>);
+            return bn ? go(k_pillars<F, ABS, DIST, true, true, true, false>) : go(k_pillars<F, ABS, DIST, false, true, true, false>);
+        }
+        // without a canvas (features only): the general build serves both
+        return bn ? go(k_pillars<F, ABS, DIST, true, true, false, true>) : go(k_pillars<F, ABS, DIST, false, true, false, true>);
     }
-    return go(k_pillars<F, ABS, DIST, true, false, false>);
+    return go(k_pillars<F, ABS, DIST, true, false, false, true>);
 }
 
 static int launch_pillars(const PathParams &p, bool with_pfn, bool abs_xyz, bool dist, cudaStream_t s) {
