@@ -607,6 +607,9 @@ struct Group {        // whole tiles of one run holding at most 32 pillars
     bool skip;        // a listed heavy tile met inside the moving window: already taken care of, neither computed nor written
 };
 
+#ifndef HGSF_STAGE_ROWS
+#define HGSF_STAGE_ROWS 96
+#endif
 #ifndef HGSF_PILLARS_MINB
 #define HGSF_PILLARS_MINB 3
 #endif
@@ -618,7 +621,7 @@ __global__ void __launch_bounds__(PT, HGSF_PILLARS_MINB) k_pillars(const PathPar
     constexpr int CIN = PFN ? ((ABS ? F : F - 3) + 6 + (DIST ? 1 : 0)) : 1;
     constexpr int RWc = (F + 1 + 3) / 4 * 4;   // F features + the point index, padded to float4
     constexpr int NV = RWc / 4;
-    constexpr int SW = (RWc <= 8) ? 96 : 64;   // staged point rows per chunk (the rest is read through L1)
+    constexpr int SW = (RWc <= 8) ? HGSF_STAGE_ROWS : HGSF_STAGE_ROWS * 2 / 3;   // staged point rows per group (the rest is read through L1)
     constexpr int BLK = C * 32;
     const int Fr = PFN ? F : p.F, RW = PFN ? RWc : p.RW;      // without the PFN the kernel is generic in F (rows read from global)
 
@@ -1265,7 +1268,7 @@ template <int F, bool ABS, bool DIST, bool PFN>
 static int launch_pillars_t(const PathParams &p, cudaStream_t stream) {
     constexpr int C = 64;
     constexpr int RWc = (F + 1 + 3) / 4 * 4;
-    constexpr int SW = (RWc <= 8) ? 96 : 64;
+    constexpr int SW = (RWc <= 8) ? HGSF_STAGE_ROWS : HGSF_STAGE_ROWS * 2 / 3;
     const bool canvas = PFN && p.canvas != nullptr;
     const size_t smem = (canvas ? sizeof(float) * PW * C * 32 : 0) + (PFN ? sizeof(float) * PW * 2 * SW * RWc : 0) +
                         sizeof(int) * 2 * (size_t)(p.B + 1);
