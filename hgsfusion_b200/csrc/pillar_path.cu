@@ -1206,6 +1206,599 @@ __global__ void __launch_bounds__(PT, HGSF_PILLARS_MINB) k_pillars(const PathPar
     mark_table_clean(p);
 }
 
+// ---- k_emit -------------------------------------------------------------------------------------
+// The fused kernel (used whenever the canvas is requested): order + decorate + PFN + max AND the canvas tile, one pass.
+// Every WARP is an autonomous worker walking its own sequence of canvas tiles (a tile = 32 cells of one BEV row x 64
+// channels = 64 rows of 128 B); no CTA barrier in the loop.  Because k_front laid the CSR out in cell order, the point
+// rows of a tile are ONE contiguous span of sorted_rows: they are staged with a single cooperative cp.async copy issued
+// a tile ahead, from table entries loaded two tiles ahead -- no dependent gathers anywhere.
+//   lane l OWNS cell l of the tile for the bookkeeping (ordering by point index, first P kept, mean in torch's
+//   summation order, voxel_coords / voxel_num_points);
+//   the arithmetic is cut into UNITS of (pillar, 4 output channels): lane l always computes channels 4*(l&15)..+3, so
+//   its Linear weight float4s and BatchNorm constants stay in REGISTERS for the whole kernel (CUDA-core FMA: a 13x64
+//   contraction is far below a tensor-core tile).  Single-point pillars are paired across the half-warps; a
+//   multi-point pillar is taken by both halves, which split its points and max-combine.
+//   A finished tile leaves in ONE TMA tensor store (128-byte swizzle so the column writes spread over banks); an
+//   empty tile is four stores of a shared 2 KB zero tile.  The canvas is written exactly once, zeros included.
+constexpr int EMIT_WARPS = 4;
+constexpr int EMIT_THREADS = EMIT_WARPS * 32;
+constexpr int STAGE_W = 64;           // staged point rows per tile (a typical tile holds ~10; the rest is read from L2)
+
+#ifndef HGSF_EMIT_MINB
+#define HGSF_EMIT_MINB 3
+#endif
+template <int F, bool ABS, bool DIST, bool BN, int CHUNK>
+__global__ void __launch_bounds__(EMIT_THREADS, HGSF_EMIT_MINB)
+k_emit(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap zmap, const PathParams p) {
+    constexpr int C = 64;
+    constexpr int CIN = (ABS ? F : F - 3) + 6 + (DIST ? 1 : 0);
+    constexpr int RWc = (F + 1 + 3) / 4 * 4;   // F features + the point index, padded to float4
+    constexpr int NV = RWc / 4;
+    constexpr int TILE = C * 32;
+    constexpr int ZC = C / 4;
+    constexpr bool TMA = true;
+    constexpr int STORE = 0;
+    constexpr int NT = EMIT_THREADS;
+
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // the TMA swizzle works on absolute shared-memory address bits: the tiles must start on a 1024-byte boundary
+    // (static shared memory in front of the dynamic part can shift it; the launcher reserves the slack)
+    uint8_t *smem_al = smem_raw + ((1024u - ((uint32_t)__cvta_generic_to_shared(smem_raw) & 1023u)) & 1023u);
+    float *tiles = reinterpret_cast<float *>(smem_al);                     // [EMIT_WARPS][TILE]
+    float *zerobuf = tiles + EMIT_WARPS * TILE;                            // [ZC*32]
+    float *stage_all = zerobuf + ZC * 32;                                  // [EMIT_WARPS][2][STAGE_W * RWc]
+    int *s_R = reinterpret_cast<int *>(stage_all + EMIT_WARPS * 2 * STAGE_W * RWc);   // [B+1] raw pillar base per frame
+    int *s_K = s_R + (p.B + 1);                                            // [B+1] kept (final) pillar base per frame
+    __shared__ float4 s_rec_all[EMIT_WARPS][32][2];                        // work lists: singles from the front, multis from the back
+    __shared__ unsigned char s_perm_all[EMIT_WARPS][32][32];               // per cell: arrival position of its rank-th point
+    __shared__ int s_bperm_all[EMIT_WARPS][32];                            // same for a pillar with > 32 arrivals
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float *tile = tiles + warp * TILE;
+    float *stage = stage_all + (size_t)warp * 2 * STAGE_W * RWc;
+    float4(*rec)[2] = s_rec_all[warp];
+    unsigned char(*perm)[32] = s_perm_all[warp];
+    int *bperm = s_bperm_all[warp];
+
+    // ---- one-time setup (the only CTA barriers) ----
+    for (int t = tid; t < ZC * 32; t += NT) zerobuf[t] = 0.f;
+    for (int t = tid; t < EMIT_WARPS * TILE; t += NT) tiles[t] = 0.f;
+    // launched as a programmatic dependent of k_front: nothing k_front wrote may be read before this returns
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    for (int b = tid; b <= p.B; b += NT) s_R[b] = p.frame_raw_base[b];
+    __syncthreads();
+    if (tid == 0) {
+        int acc = 0;
+        for (int b = 0; b < p.B; ++b) {
+            s_K[b] = acc;
+            const int m = min(s_R[b + 1] - s_R[b], p.max_voxels);
+            if (blockIdx.x == 0) p.num_pillars[1 + b] = m;
+            acc += m;
+        }
+        s_K[p.B] = acc;
+        if (blockIdx.x == 0) p.num_pillars[0] = acc;
+    }
+    if (TMA) fence_proxy_async_smem();
+    __syncthreads();
+
+    // this lane's 4 channels: Linear rows and BatchNorm constants, in registers for the whole kernel
+    const int c0 = 4 * (lane & 15);
+    const int half = lane >> 4;
+    uint64_t w01[CIN], w23[CIN];           // channel pairs (c0, c0+1), (c0+2, c0+3): one FFMA2 each per input feature
+    float4 mu = make_float4(0.f, 0.f, 0.f, 0.f), iv = mu, ga = mu, be = mu, pv = mu;
+    {
+#pragma unroll
+        for (int k = 0; k < CIN; ++k) {
+            w01[k] = pack_f2(__ldg(p.W + (c0 + 0) * CIN + k), __ldg(p.W + (c0 + 1) * CIN + k));
+            w23[k] = pack_f2(__ldg(p.W + (c0 + 2) * CIN + k), __ldg(p.W + (c0 + 3) * CIN + k));
+        }
+        float bnv[5][4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int c = c0 + j;
+            float y;
+            if (BN) {
+                bnv[0][j] = __ldg(p.bn_m + c);
+                bnv[1][j] = __frcp_rn(__fsqrt_rn(__fadd_rn(__ldg(p.bn_v + c), p.eps)));
+                bnv[2][j] = __ldg(p.bn_w + c);
+                bnv[3][j] = __ldg(p.bn_b + c);
+                // a zero (padded) row still goes through BN + ReLU and joins the max (pillar_vfe.py:37-42)
+                y = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(0.f, bnv[0][j]), bnv[1][j]), bnv[2][j]), bnv[3][j]);
+            } else {
+                bnv[0][j] = bnv[1][j] = bnv[2][j] = 0.f;
+                bnv[3][j] = __ldg(p.bias + c);
+                y = __fadd_rn(0.f, bnv[3][j]);
+            }
+            bnv[4][j] = (y > 0.f || y != y) ? y : 0.f;
+        }
+        mu = make_float4(bnv[0][0], bnv[0][1], bnv[0][2], bnv[0][3]); iv = make_float4(bnv[1][0], bnv[1][1], bnv[1][2], bnv[1][3]);
+        ga = make_float4(bnv[2][0], bnv[2][1], bnv[2][2], bnv[2][3]); be = make_float4(bnv[3][0], bnv[3][1], bnv[3][2], bnv[3][3]);
+        pv = make_float4(bnv[4][0], bnv[4][1], bnv[4][2], bnv[4][3]);
+    }
+    const uint64_t mu01 = pack_f2(mu.x, mu.y), mu23 = pack_f2(mu.z, mu.w), iv01 = pack_f2(iv.x, iv.y), iv23 = pack_f2(iv.z, iv.w),
+                   ga01 = pack_f2(ga.x, ga.y), ga23 = pack_f2(ga.z, ga.w);
+
+    const int P4 = (p.P >> 2) << 2;
+    const int maxv = p.max_voxels, Pmax = p.P;
+    const float vsx = p.vsize[0], vsy = p.vsize[1], vox = p.voff[0], voy = p.voff[1];
+    const float cz = __fadd_rn(__fmul_rn(0.f, p.vsize[2]), p.voff[2]);     // z index 0: fl(fl(0*vz)+z_off)
+    const float *__restrict__ grows = p.sorted_rows;
+    const unsigned lt = (1u << lane) - 1u;
+    const uint64_t stream_policy = l2_policy_evict_first();   // canvas: written once, never re-read here
+#ifdef HGSF_EXPERIMENT
+    const uint64_t feats_policy = (p.dbg & 8) ? l2_policy_evict_last() : ((p.dbg & 16) ? l2_policy_evict_normal() : stream_policy);
+#else
+    const uint64_t feats_policy = stream_policy;
+#endif
+
+    // one point through decorate + Linear + BN, folded into the running max (integer max on the float bits: exact for
+    // the non-negative post-ReLU values, drops negatives and -0 = the ReLU, lets a NaN 0x7fffffff win as torch.max does)
+    auto eval_row = [&](const float (&row)[RWc], float mx, float my, float mz, float cx, float cy,
+                        int &v0, int &v1, int &v2, int &v3) {
+        float feat[CIN];
+        {
+            int kf = 0;
+#pragma unroll
+            for (int q = ABS ? 0 : 3; q < F; ++q) feat[kf++] = row[q];
+            feat[kf++] = __fsub_rn(row[0], mx); feat[kf++] = __fsub_rn(row[1], my); feat[kf++] = __fsub_rn(row[2], mz);
+            feat[kf++] = __fsub_rn(row[0], cx); feat[kf++] = __fsub_rn(row[1], cy); feat[kf++] = __fsub_rn(row[2], cz);
+            // torch.norm(xyz, 2, 2) on the CPU: sqrt(fma(z,z, fma(y,y, x*x)))  (pillar_vfe.py:110-112)
+            if (DIST) feat[kf++] = __fsqrt_rn(fmaf(row[2], row[2], fmaf(row[1], row[1], __fmul_rn(row[0], row[0]))));
+        }
+        uint64_t a01 = 0ull, a23 = 0ull;       // (+0, +0)
+#pragma unroll
+        for (int kk = 0; kk < CIN; ++kk) {     // Linear: sequential FMA in k order (pillar_vfe.py:37), two channels per FFMA2
+            const uint64_t ff = pack_f2(feat[kk], feat[kk]);
+            a01 = fma2_rn(ff, w01[kk], a01);
+            a23 = fma2_rn(ff, w23[kk], a23);
+        }
+        float y0, y1, y2, y3;
+        if (BN) {                              // BN eval: (((x-mean)*invstd)*gamma)+beta, 4 roundings (:39); the last add scalar (common.cuh)
+            unpack_f2(mul2_rn(mul2_rn(sub2_rn(a01, mu01), iv01), ga01), y0, y1);
+            unpack_f2(mul2_rn(mul2_rn(sub2_rn(a23, mu23), iv23), ga23), y2, y3);
+            y0 = __fadd_rn(y0, be.x); y1 = __fadd_rn(y1, be.y); y2 = __fadd_rn(y2, be.z); y3 = __fadd_rn(y3, be.w);
+        } else {
+            unpack_f2(a01, y0, y1); unpack_f2(a23, y2, y3);
+            y0 = __fadd_rn(y0, be.x); y1 = __fadd_rn(y1, be.y); y2 = __fadd_rn(y2, be.z); y3 = __fadd_rn(y3, be.w);
+        }
+        v0 = max(v0, __float_as_int(y0)); v1 = max(v1, __float_as_int(y1));
+        v2 = max(v2, __float_as_int(y2)); v3 = max(v3, __float_as_int(y3));
+    };
+    // a point row: from the staging buffer (rel >= 0: row index in it) or from global memory (rel < 0: -1 - CSR row),
+    // read through ONE generic pointer so that the two sources do not become two divergent code paths
+    auto load_row = [&](const float *stg, int rel, int pos, float (&row)[RWc]) {
+        const float *base = (rel >= 0) ? stg + (size_t)rel * RWc : grows + (size_t)(-1 - rel) * RWc;
+        const float4 *r4 = reinterpret_cast<const float4 *>(base + (size_t)pos * RWc);
+#pragma unroll
+        for (int v = 0; v < NV; ++v) { const float4 t4 = r4[v]; row[4 * v] = t4.x; row[4 * v + 1] = t4.y; row[4 * v + 2] = t4.z; row[4 * v + 3] = t4.w; }
+    };
+    // channel c0+i of cell `cell` sits at tile[(c0+i)*32 + (((cell>>2) ^ ((c0+i)&7)) << 2 | (cell&3))] (128-byte swizzle);
+    // with c0 = 4*(lane&15): (c0+i)&7 = ((lane&1)<<2) ^ i, so the lane-constant part is folded once
+    float *const tbase = tile + c0 * 32;
+    const int swb = (lane & 1) << 2;
+    auto put_tile = [&](int cell, int v0, int v1, int v2, int v3) {
+        const int xs = (cell >> 2) ^ swb, xr = cell & 3;
+        tbase[0 * 32 + (((xs ^ 0) << 2) | xr)] = __int_as_float(v0);
+        tbase[1 * 32 + (((xs ^ 1) << 2) | xr)] = __int_as_float(v1);
+        tbase[2 * 32 + (((xs ^ 2) << 2) | xr)] = __int_as_float(v2);
+        tbase[3 * 32 + (((xs ^ 3) << 2) | xr)] = __int_as_float(v3);
+    };
+
+    // Tiles are handed out DYNAMICALLY, one global ticket per CHUNK consecutive tiles, fetched a chunk ahead: a dense tile costs
+    // ten times a sparse one, and a static assignment leaves the unlucky warps running alone at the end.  Short chunks also keep
+    // x-adjacent tiles -- adjacent 128-byte pieces of the same canvas rows -- in flight at the same time on different warps,
+    // which the DRAM write stream rewards.  The first tickets are k_front's list of HEAVY tiles (more than p.heavy_pts points:
+    // one warp is busy with such a tile for a long time, so they start first and the many light tiles fill in around them);
+    // the moving window then steps over the listed tiles.
+    const int n_tiles = (int)(((long long)p.B * p.cells) >> 5);
+    const int n_heavy = (int)p.ticket[32];
+    const unsigned heavy_pts = (unsigned)p.heavy_pts;
+    constexpr int chunk = CHUNK;
+    const int n_tickets = n_heavy + (n_tiles + chunk - 1) / chunk;
+    // the ticket stays in lane 0's register until the chunk is actually started: broadcasting it right away would
+    // stall the whole warp on the atomic's round trip
+    auto fetch_raw = [&]() -> int {
+        int v = 0;
+        if (lane == 0) v = (int)atomicAdd(p.ticket, 1u);
+        return v;
+    };
+    struct Slot { int t; bool listed; };             // t == n_tiles: past the end
+    Slot seq; seq.t = 0; seq.listed = false;
+    int seq_left = 0, next_raw = 0;
+    auto start_chunk = [&](int c) {
+        if (c < n_heavy) { seq.t = (int)__ldg(p.heavy_list + c); seq_left = 1; seq.listed = true; }
+        else if (c < n_tickets) { seq.t = (c - n_heavy) * chunk; seq_left = min(chunk, n_tiles - seq.t); seq.listed = false; }
+        else { seq.t = n_tiles; seq_left = 0; seq.listed = false; }
+    };
+    start_chunk(__shfl_sync(FULL, fetch_raw(), 0));
+    if (seq.t < n_tiles) next_raw = fetch_raw();
+    auto next_tile = [&]() -> Slot {
+        if (seq.t >= n_tiles) return seq;
+        if (seq_left > 1) { --seq_left; ++seq.t; }
+        else {
+            start_chunk(__shfl_sync(FULL, next_raw, 0));
+            if (seq.t < n_tiles) next_raw = fetch_raw();
+        }
+        return seq;
+    };
+    Slot cur = seq;
+    Slot nxt = next_tile();
+    Slot nxt2 = next_tile();
+    // k_front's record of a tile: {first CSR row, rows, pillars before it, occupancy mask}
+    auto load_rec = [&](const Slot &s) -> uint4 {
+        return (s.t < n_tiles) ? __ldg(p.tile_rec + s.t) : make_uint4(0u, 0u, 0u, 0u);
+    };
+    // a listed tile met inside the window was handed out at the start: neither computed nor written here
+    auto skipped = [&](const Slot &s, const uint4 &r) -> bool { return !s.listed && r.y > heavy_pts; };
+    // lane l: table entry of cell 32*t + l (the table rows are padded to whole tiles); empty cells are not read
+    auto load_entry = [&](const Slot &s, const uint4 &r) -> uint4 {
+        uint4 e = make_uint4(0, 0, 0, 0);
+        if (((r.w >> lane) & 1u) && !skipped(s, r)) {
+            const size_t c = (size_t)s.t * 32 + lane;
+            e.x = __ldg(p.cell_tag + c); e.y = __ldg(p.cell_cnt + c); e.z = __ldg(p.cell_start + c);
+        }
+        return e;
+    };
+    // the tile's rows are sorted_rows[row0, row0 + total): one cooperative async copy of (at most STAGE_W of) them
+    auto issue_stage = [&](const Slot &s, const uint4 &r, float *stg) {
+        const int chunks = skipped(s, r) ? 0 : min((int)r.y, STAGE_W) * NV;
+        const float *src = grows + (size_t)r.x * RWc;
+        for (int c = lane; c < chunks; c += 32) cp_async16(stg + 4 * c, src + 4 * c);
+        cp_async_commit();
+    };
+
+    uint4 r_cur = load_rec(cur);
+    uint4 r_nxt = load_rec(nxt);
+    uint4 e_cur = load_entry(cur, r_cur);
+    issue_stage(cur, r_cur, stage);
+    unsigned dirty = 0;                  // cells of the tile buffer that hold non-zero columns
+    bool store_pending = false;          // a TMA store from the tile buffer may still be reading it
+
+    for (int it = 0; cur.t < n_tiles; ++it) {
+        const float *stg = stage + (size_t)(it & 1) * STAGE_W * RWc;
+        // ---- pipeline: record of the tile after next, entries and rows of the next tile ----
+        const uint4 r_nn = load_rec(nxt2);
+        const uint4 e_nxt = load_entry(nxt, r_nxt);
+        issue_stage(nxt, r_nxt, stage + (size_t)((it + 1) & 1) * STAGE_W * RWc);
+
+        // tile t = (frame b, BEV row y, 32 cells from x0)
+        const uint32_t row_id = fastdiv((uint32_t)cur.t, p.div_tpr);
+        const int b = (int)fastdiv(row_id, p.div_ny);
+        const int y = (int)row_id - b * p.ny, x0 = (cur.t - (int)row_id * p.tiles_per_row) * 32;
+        const bool skip = skipped(cur, r_cur);
+        if (e_cur.y) {                   // the entry has been read: leave the table clean for the next call's k_front
+            const size_t c = (size_t)cur.t * 32 + lane;
+            p.cell_tag[c] = 0u; p.cell_cnt[c] = 0u;
+        }
+        const int m = (int)(e_cur.x - 1u), cnt = (int)e_cur.y, start = (int)e_cur.z;
+        const int local = m - s_R[b];
+        const bool occ = (e_cur.x != 0u) && (local < maxv);     // pillars beyond max_voxels were never created
+        const unsigned bal_occ = __ballot_sync(FULL, occ);
+        if (skip) {
+        } else if (bal_occ == 0u) {
+            // empty tile: four stores of the shared zero tile
+            if (TMA) {
+                // issued by lane 1: bulk async-groups are per thread, so lane 0's wait for its tile store to have read the
+                // tile buffer (below) does not also wait for the zero stores of the empty tiles that came after it
+                if (lane == 1) {
+#pragma unroll
+                    for (int q4 = 0; q4 < 4; ++q4) tma_store_3d_hint(&zmap, zerobuf, x0, y, b * C + q4 * ZC, stream_policy);
+                    tma_commit();
+                }
+            } else if (STORE == 1) {
+                const int xc = x0 + 4 * (lane & 7);      // lane l: 16-byte chunk (l & 7) of channel rows (l >> 3) + 4*i
+                if (xc < p.nx) {
+                    float *dst = p.canvas + (((size_t)b * C + (lane >> 3)) * p.ny + y) * p.nx + xc;
+                    const size_t plane4 = (size_t)4 * p.ny * p.nx;
+#pragma unroll
+                    for (int i = 0; i < C / 4; ++i) __stcs(reinterpret_cast<float4 *>(dst + i * plane4), make_float4(0.f, 0.f, 0.f, 0.f));
+                }
+            } else if (x0 + lane < p.nx) {
+                for (int ch = 0; ch < C; ++ch) p.canvas[(((size_t)b * C + ch) * p.ny + y) * p.nx + x0 + lane] = 0.f;
+            }
+        } else {
+            const int row0 = (int)r_cur.x;
+            const int rel0 = start - row0;
+            const bool staged = occ && cnt <= 32 && rel0 + cnt <= STAGE_W;
+            const int rel = staged ? rel0 : (-1 - start);         // where the pillar's rows are (see load_row)
+            const int n_keep = min(cnt, Pmax);
+            const int f = s_K[b] + local;                          // final pillar id (first-seen order, frames concatenated)
+            if (occ) {
+                p.num[f] = n_keep;
+                *reinterpret_cast<int4 *>(p.coords + 4 * (size_t)f) = make_int4(b, 0, y, x0 + lane);
+            }
+            cp_async_wait<1>();          // this tile's rows have landed (this lane's copies) ...
+            __syncwarp();                // ... and every other lane's
+            // ---- order the pillar's points by input index; mean of the kept points (torch CPU sum order) ----
+            const bool live = occ && cnt <= 32;
+            float mx = 0.f, my = 0.f, mz = 0.f;
+            // the common tile has only 1- and 2-point pillars: a warp-uniform short cut for it (one compare instead of the
+            // 6-way ranking, no summation loop, and x/2 as the exact x*0.5 instead of the IEEE division routine)
+            const unsigned multi_bal = __ballot_sync(FULL, occ && cnt > 1);
+            const unsigned pair_bal = __ballot_sync(FULL, occ && cnt == 2 && staged);
+            const bool pairs_only = (multi_bal == pair_bal) && Pmax >= 2;
+#ifdef HGSF_EXPERIMENT
+            // ablation (WRONG results, timing only): as if the rows arrived ordered and the mean were precomputed
+            if (p.dbg & 32) {
+                if (live) {
+                    if (!(p.dbg & 64)) for (int j = 0; j < n_keep; ++j) perm[lane][j] = (unsigned char)j;
+                    const float4 a = *reinterpret_cast<const float4 *>((rel >= 0) ? stg + (size_t)rel * RWc : grows + (size_t)(-1 - rel) * RWc);
+                    mx = a.x; my = a.y; mz = a.z;
+                }
+                __syncwarp();
+            } else
+#endif
+            if (pairs_only) {
+                if (occ && cnt == 2) {
+                    const float *r0p = stg + (size_t)rel * RWc, *r1p = r0p + RWc;
+                    const int first = (__float_as_uint(r1p[F]) < __float_as_uint(r0p[F])) ? 1 : 0;
+                    perm[lane][0] = (unsigned char)first; perm[lane][1] = (unsigned char)(first ^ 1);
+                    const float4 a = *reinterpret_cast<const float4 *>(first ? r1p : r0p);
+                    const float4 c = *reinterpret_cast<const float4 *>(first ? r0p : r1p);
+                    SlotSum sum;
+                    sum.add(0, P4, a.x, a.y, a.z);
+                    sum.add(1, P4, c.x, c.y, c.z);
+                    mx = __fmul_rn(sum.sx(), 0.5f); my = __fmul_rn(sum.sy(), 0.5f); mz = __fmul_rn(sum.sz(), 0.5f);
+                } else if (occ) {
+                    float row[RWc];
+                    load_row(stg, rel, 0, row);
+                    mx = row[0]; my = row[1]; mz = row[2];       // mean of one point is the point (x/1 is exact)
+                }
+                __syncwarp();
+            } else {
+            if (occ && cnt > 1 && cnt <= SMALL_CNT) {
+                uint32_t idx[SMALL_CNT];
+#pragma unroll
+                for (int j = 0; j < SMALL_CNT; ++j) {
+                    idx[j] = 0xFFFFFFFFu;
+                    if (j < cnt) idx[j] = staged ? __float_as_uint(stg[(size_t)(rel + j) * RWc + F])
+                                                 : __float_as_uint(__ldg(grows + (size_t)(start + j) * RWc + F));
+                }
+#pragma unroll
+                for (int j = 0; j < SMALL_CNT; ++j) {
+                    int rank = 0;
+#pragma unroll
+                    for (int q = 0; q < SMALL_CNT; ++q) rank += (idx[q] < idx[j]) ? 1 : 0;
+                    if (j < cnt) perm[lane][rank] = (unsigned char)j;
+                }
+            }
+            unsigned coop = __ballot_sync(FULL, occ && cnt > SMALL_CNT && cnt <= 32);   // the warp ranks these one at a time
+            while (coop) {
+                const int o = __ffs(coop) - 1;
+                coop &= coop - 1;
+                const int cnt_o = __shfl_sync(FULL, cnt, o), rel_o = __shfl_sync(FULL, rel, o);
+                uint32_t mine = 0xFFFFFFFFu;
+                if (lane < cnt_o) mine = (rel_o >= 0) ? __float_as_uint(stg[(size_t)(rel_o + lane) * RWc + F])
+                                                      : __float_as_uint(__ldg(grows + (size_t)(-1 - rel_o + lane) * RWc + F));
+                int rank = 0;
+                for (int q = 0; q < cnt_o; ++q) rank += (__shfl_sync(FULL, mine, q) < mine) ? 1 : 0;
+                if (lane < cnt_o) perm[o][rank] = (unsigned char)lane;
+            }
+            __syncwarp();
+            if (live) {
+                float row[RWc];
+                if (cnt == 1) {
+                    load_row(stg, rel, 0, row);
+                    mx = row[0]; my = row[1]; mz = row[2];       // mean of one point is the point (x/1 is exact)
+                } else {
+                    SlotSum sum;
+                    for (int s2 = 0; s2 < n_keep; ++s2) {
+                        load_row(stg, rel, perm[lane][s2], row);
+                        sum.add(s2, P4, row[0], row[1], row[2]);
+                    }
+                    const float fn = (float)n_keep;
+                    mx = __fdiv_rn(sum.sx(), fn); my = __fdiv_rn(sum.sy(), fn); mz = __fdiv_rn(sum.sz(), fn);
+                }
+            }
+            }
+            const unsigned sbal = __ballot_sync(FULL, live && n_keep == 1);
+            const unsigned mbal = __ballot_sync(FULL, live && n_keep > 1);
+            const int n_s = __popc(sbal), n_m = __popc(mbal);
+            if (live) {
+                const int slot = (n_keep == 1) ? __popc(sbal & lt) : 31 - __popc(mbal & lt);   // singles from the front, multis from the back
+#ifdef HGSF_EXPERIMENT
+                const int pos0 = (cnt == 1 || (p.dbg & 64)) ? 0 : (int)perm[lane][0];
+#else
+                const int pos0 = (cnt == 1) ? 0 : (int)perm[lane][0];   // the one evaluated point (rank 0 when P == 1 truncated)
+#endif
+                rec[slot][0] = make_float4(mx, my, mz, __int_as_float(n_keep | (lane << 8) | (pos0 << 16)));
+                rec[slot][1] = make_float4(__int_as_float(rel), __int_as_float(f), 0.f, 0.f);
+            }
+            // the tile buffer: wait until the previous store has read it, then clear what that tile dirtied
+            if (TMA && store_pending) {
+                if (lane == 0) tma_wait_read<0>();
+                store_pending = false;
+            }
+            __syncwarp();
+            if (__popc(dirty) > 2) {
+#pragma unroll
+                for (int t = 0; t < TILE / 128; ++t) *reinterpret_cast<float4 *>(tile + t * 128 + lane * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+            } else {
+                while (dirty) {
+                    const int dc = __ffs(dirty) - 1;
+                    dirty &= dirty - 1;
+                    tile[swz128(lane, dc)] = 0.f; tile[swz128(lane + 32, dc)] = 0.f;
+                }
+            }
+            dirty = bal_occ;
+            __syncwarp();
+            // ---- unit phase.  lane l always computes channels c0..c0+3 ----
+            const float cy = __fadd_rn(__fmul_rn((float)y, vsy), voy);   // pillar centre: fl(fl(c*v)+off), two roundings,
+                                                                         // no FMA (pillar_vfe.py:101-103)
+            // (a) single-point pillars: half-warp h takes list entries 4*j + h and 4*j + 2 + h -- two independent points per
+            //     iteration, so that their FMA chains interleave (the kernel is latency-bound at 12 warps per SM)
+#ifdef HGSF_EXPERIMENT
+            const int n_s_run = (p.dbg & 1) ? 0 : n_s, n_m_run = (p.dbg & 1) ? 0 : n_m;
+#else
+            const int n_s_run = n_s, n_m_run = n_m;
+#endif
+#pragma unroll 1
+            for (int j = 0; 4 * j < n_s_run; ++j) {
+                const int eA = 4 * j + half;
+                if (eA < n_s) {
+                    const bool okB = eA + 2 < n_s;
+                    const int eB = okB ? eA + 2 : eA;
+                    const float4 rA0 = rec[eA][0], rA1 = rec[eA][1], rB0 = rec[eB][0], rB1 = rec[eB][1];
+                    const int metaA = __float_as_int(rA0.w), metaB = __float_as_int(rB0.w);
+                    const int cellA = (metaA >> 8) & 0xFF, cellB = (metaB >> 8) & 0xFF;
+                    const float cxA = __fadd_rn(__fmul_rn((float)(x0 + cellA), vsx), vox);
+                    const float cxB = __fadd_rn(__fmul_rn((float)(x0 + cellB), vsx), vox);
+                    int a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+                    if (1 < Pmax) { a0 = __float_as_int(pv.x); a1 = __float_as_int(pv.y); a2 = __float_as_int(pv.z); a3 = __float_as_int(pv.w); }
+                    int b0 = a0, b1 = a1, b2 = a2, b3 = a3;
+                    float rowA[RWc], rowB[RWc];
+                    load_row(stg, __float_as_int(rA1.x), metaA >> 16, rowA);
+                    load_row(stg, __float_as_int(rB1.x), metaB >> 16, rowB);
+                    eval_row(rowA, rA0.x, rA0.y, rA0.z, cxA, cy, a0, a1, a2, a3);
+                    eval_row(rowB, rB0.x, rB0.y, rB0.z, cxB, cy, b0, b1, b2, b3);
+                    if (p.feats) {
+                        st_f4_hint(p.feats + (size_t)__float_as_int(rA1.y) * C + c0,
+                                   make_float4(__int_as_float(a0), __int_as_float(a1), __int_as_float(a2), __int_as_float(a3)), feats_policy);
+                        if (okB)
+                            st_f4_hint(p.feats + (size_t)__float_as_int(rB1.y) * C + c0,
+                                       make_float4(__int_as_float(b0), __int_as_float(b1), __int_as_float(b2), __int_as_float(b3)), feats_policy);
+                    }
+                    put_tile(cellA, a0, a1, a2, a3);
+                    if (okB) put_tile(cellB, b0, b1, b2, b3);
+                }
+            }
+            // (b) multi-point pillars: both half-warps on the same pillar, half h takes slots h, h+2, ... (two per iteration);
+            //     max-combined
+#pragma unroll 1
+            for (int j = 0; j < n_m_run; ++j) {
+                const float4 r0 = rec[31 - j][0], r1 = rec[31 - j][1];
+                const int meta = __float_as_int(r0.w);
+                const int nk = meta & 0xFF, cell = (meta >> 8) & 0xFF;
+                const int relp = __float_as_int(r1.x);
+                const float cx = __fadd_rn(__fmul_rn((float)(x0 + cell), vsx), vox);
+                int v0 = 0, v1 = 0, v2 = 0, v3 = 0;
+                if (nk < Pmax) { v0 = __float_as_int(pv.x); v1 = __float_as_int(pv.y); v2 = __float_as_int(pv.z); v3 = __float_as_int(pv.w); }
+                int u0 = v0, u1 = v1, u2 = v2, u3 = v3;
+#pragma unroll 1
+                for (int s2 = half; s2 < nk; s2 += 4) {
+                    const int s3 = (s2 + 2 < nk) ? s2 + 2 : s2;        // the last odd one is evaluated twice: max is idempotent
+                    float rowA[RWc], rowB[RWc];
+#ifdef HGSF_EXPERIMENT
+                    load_row(stg, relp, (p.dbg & 64) ? s2 : (int)perm[cell][s2], rowA);
+                    load_row(stg, relp, (p.dbg & 64) ? s3 : (int)perm[cell][s3], rowB);
+#else
+                    load_row(stg, relp, perm[cell][s2], rowA);
+                    load_row(stg, relp, perm[cell][s3], rowB);
+#endif
+                    eval_row(rowA, r0.x, r0.y, r0.z, cx, cy, v0, v1, v2, v3);
+                    eval_row(rowB, r0.x, r0.y, r0.z, cx, cy, u0, u1, u2, u3);
+                }
+                v0 = max(v0, u0); v1 = max(v1, u1); v2 = max(v2, u2); v3 = max(v3, u3);
+                v0 = max(v0, __shfl_xor_sync(FULL, v0, 16)); v1 = max(v1, __shfl_xor_sync(FULL, v1, 16));
+                v2 = max(v2, __shfl_xor_sync(FULL, v2, 16)); v3 = max(v3, __shfl_xor_sync(FULL, v3, 16));
+                if (half == 0) {
+                    if (p.feats)
+                        st_f4_hint(p.feats + (size_t)__float_as_int(r1.y) * C + c0,
+                                   make_float4(__int_as_float(v0), __int_as_float(v1), __int_as_float(v2), __int_as_float(v3)), feats_policy);
+                    put_tile(cell, v0, v1, v2, v3);
+                }
+            }
+            // ---- pillars with more than 32 arrivals: the warp selects the 32 smallest point indices, then as (b) ----
+            unsigned hm = __ballot_sync(FULL, occ && cnt > 32);
+            while (hm) {
+                const int o = __ffs(hm) - 1;
+                hm &= hm - 1;
+                const int cnt_o = __shfl_sync(FULL, cnt, o), start_o = __shfl_sync(FULL, start, o), f_o = __shfl_sync(FULL, f, o);
+                const int nk = min(cnt_o, Pmax);
+                const float *grow_o = grows + (size_t)start_o * RWc;
+                { uint32_t key_unused; bperm[lane] = select_next32(grow_o + F, RWc, cnt_o, lane, false, 0u, key_unused); }
+                __syncwarp();
+                if (p.voxels) {
+                    float *vo = p.voxels + (size_t)f_o * Pmax * F;
+                    for (int t = lane; t < Pmax * F; t += 32) {
+                        const int s2 = t / F, kk = t - s2 * F;
+                        vo[t] = (s2 < nk) ? __ldg(grow_o + (size_t)bperm[s2] * RWc + kk) : 0.f;
+                    }
+                }
+                SlotSum sum;
+                for (int s2 = 0; s2 < nk; ++s2) {
+                    const float4 v = __ldg(reinterpret_cast<const float4 *>(grow_o + (size_t)bperm[s2] * RWc));
+                    sum.add(s2, P4, v.x, v.y, v.z);
+                }
+                const float fn = (float)nk;
+                const float hx = __fdiv_rn(sum.sx(), fn), hy = __fdiv_rn(sum.sy(), fn), hz = __fdiv_rn(sum.sz(), fn);
+                const float cx = __fadd_rn(__fmul_rn((float)(x0 + o), vsx), vox);
+                int v0 = 0, v1 = 0, v2 = 0, v3 = 0;
+                if (nk < Pmax) { v0 = __float_as_int(pv.x); v1 = __float_as_int(pv.y); v2 = __float_as_int(pv.z); v3 = __float_as_int(pv.w); }
+#pragma unroll 1
+                for (int s2 = half; s2 < nk; s2 += 2) {
+                    float row[RWc];
+                    load_row(stg, -1 - start_o, bperm[s2], row);
+                    eval_row(row, hx, hy, hz, cx, cy, v0, v1, v2, v3);
+                }
+                v0 = max(v0, __shfl_xor_sync(FULL, v0, 16)); v1 = max(v1, __shfl_xor_sync(FULL, v1, 16));
+                v2 = max(v2, __shfl_xor_sync(FULL, v2, 16)); v3 = max(v3, __shfl_xor_sync(FULL, v3, 16));
+                if (half == 0) {
+                    if (p.feats)
+                        st_f4_hint(p.feats + (size_t)f_o * C + c0,
+                                   make_float4(__int_as_float(v0), __int_as_float(v1), __int_as_float(v2), __int_as_float(v3)), feats_policy);
+                    put_tile(o, v0, v1, v2, v3);
+                }
+                __syncwarp();
+            }
+            // ---- optional contract output: the padded voxels tensor [M, P, F], coalesced, one pillar at a time ----
+            if (p.voxels) {
+                unsigned todo = __ballot_sync(FULL, live);
+                while (todo) {
+                    const int o = __ffs(todo) - 1;
+                    todo &= todo - 1;
+                    const int cnt_o = __shfl_sync(FULL, cnt, o), rel_o = __shfl_sync(FULL, rel, o), f_o = __shfl_sync(FULL, f, o);
+                    const int nk = min(cnt_o, Pmax);
+                    float *vo = p.voxels + (size_t)f_o * Pmax * F;
+                    for (int t = lane; t < Pmax * F; t += 32) {
+                        const int s2 = t / F, kk = t - s2 * F;
+                        float v = 0.f;
+                        if (s2 < nk) {
+                            const int pos = (cnt_o == 1) ? 0 : (int)perm[o][s2];
+                            v = (rel_o >= 0) ? stg[(size_t)(rel_o + pos) * RWc + kk] : __ldg(grows + (size_t)(-1 - rel_o + pos) * RWc + kk);
+                        }
+                        vo[t] = v;
+                    }
+                }
+            }
+            // ---- the tile goes out in one piece ----
+            if (TMA) {
+                fence_proxy_async_smem();
+                __syncwarp();
+#ifdef HGSF_EXPERIMENT
+                if (lane == 0 && !(p.dbg & 2)) { if (p.dbg & 4) tma_store_3d(&tmap, tile, x0, y, b * C); else tma_store_3d_hint(&tmap, tile, x0, y, b * C, stream_policy); tma_commit(); }
+#else
+                if (lane == 0) { tma_store_3d_hint(&tmap, tile, x0, y, b * C, stream_policy); tma_commit(); }
+#endif
+                store_pending = true;
+            } else if (STORE == 1) {
+                __syncwarp();
+                const int xc = x0 + 4 * (lane & 7);
+                if (xc < p.nx) {
+                    float *dst = p.canvas + (((size_t)b * C + (lane >> 3)) * p.ny + y) * p.nx + xc;
+                    const size_t plane4 = (size_t)4 * p.ny * p.nx;
+#pragma unroll
+                    for (int i = 0; i < C / 4; ++i) {
+                        const int row = (lane >> 3) + 4 * i;
+                        const float4 v = *reinterpret_cast<const float4 *>(tile + row * 32 + (((lane & 7) ^ (row & 7)) << 2));
+                        __stcs(reinterpret_cast<float4 *>(dst + i * plane4), v);
+                    }
+                }
+            } else {
+                __syncwarp();
+                if (x0 + lane < p.nx)
+                    for (int ch = 0; ch < C; ++ch) p.canvas[(((size_t)b * C + ch) * p.ny + y) * p.nx + x0 + lane] = tile[swz128(ch, lane)];
+            }
+            __syncwarp();
+        }
+        e_cur = e_nxt; r_cur = r_nxt; r_nxt = r_nn;
+        cur = nxt; nxt = nxt2; nxt2 = next_tile();
+    }
+    cp_async_wait<0>();
+    if (TMA && lane <= 1) tma_wait_read<0>();        // shared memory must outlive the stores that read it
+    mark_table_clean(p);
+}
+
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
@@ -1305,10 +1898,50 @@ static int launch_pillars_t(const PathParams &p, cudaStream_t stream) {
     return go(k_pillars<F, ABS, DIST, true, false, false, true>);
 }
 
+template <int F, bool ABS, bool DIST>
+static int launch_emit_t(const PathParams &p, cudaStream_t stream) {
+    constexpr int C = 64;
+    constexpr int RWc = (F + 1 + 3) / 4 * 4;
+    CUtensorMap map, zmap;
+    int st = make_canvas_map(&map, p.canvas, p.B, C, p.ny, p.nx, C);
+    if (st == HGSF_OK) st = make_canvas_map(&zmap, p.canvas, p.B, C, p.ny, p.nx, C / 4);
+    if (st != HGSF_OK) return st;
+    const size_t smem = 1024 + sizeof(float) * (EMIT_WARPS * C * 32 + (C / 4) * 32 + EMIT_WARPS * 2 * STAGE_W * RWc) +
+                        sizeof(int) * 2 * (size_t)(p.B + 1);
+    const long long n_tiles = ((long long)p.B * p.cells) >> 5;
+    if (n_tiles == 0) return HGSF_OK;
+    int chunk = ((long long)p.n < 6 * n_tiles) ? 2 : 1;
+    if (const char *tc = getenv("HGSF_TILE_CHUNK")) chunk = atoi(tc) >= 2 ? 2 : 1;
+    const bool bn = p.bn_w != nullptr;
+    auto go = [&](auto kern) -> int {
+        int grid = 1;
+        const int s2 = launch_persistent(kern, EMIT_THREADS, smem, (n_tiles + EMIT_WARPS - 1) / EMIT_WARPS, stream, &grid);
+        if (s2 != HGSF_OK) return s2;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(EMIT_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+#ifdef HGSF_NO_PDL
+        cfg.numAttrs = 0;
+#else
+        cfg.numAttrs = 1;
+#endif
+        return (int)cudaLaunchKernelEx(&cfg, kern, map, zmap, p);
+    };
+    if (chunk == 2) return bn ? go(k_emit<F, ABS, DIST, true, 2>) : go(k_emit<F, ABS, DIST, false, 2>);
+    return bn ? go(k_emit<F, ABS, DIST, true, 1>) : go(k_emit<F, ABS, DIST, false, 1>);
+}
+
 static int launch_pillars(const PathParams &p, bool with_pfn, bool abs_xyz, bool dist, cudaStream_t s) {
     if (!with_pfn) return launch_pillars_t<4, true, false, false>(p, s);   // F / RW are read from the params when the PFN is off
     if (p.C != 64) return HGSF_ERR_UNSUPPORTED;
-#define HGSF_CASE(FV, A, D) if (p.F == FV && abs_xyz == A && dist == D) return launch_pillars_t<FV, A, D, true>(p, s);
+    // the tile-major kernel takes the fused canvas case it was built for; everything else goes pillar-major
+    static const bool force_pillars = getenv("HGSF_CONSUMER") && getenv("HGSF_CONSUMER")[0] == 'p';
+    const bool tile_major = p.canvas != nullptr && p.canvas_vec && p.P <= 32 && !(p.flags & HGSF_POINTS_SPCONV1_BREAK) && !force_pillars;
+#define HGSF_CASE(FV, A, D) if (p.F == FV && abs_xyz == A && dist == D) \
+        return tile_major ? launch_emit_t<FV, A, D>(p, s) : launch_pillars_t<FV, A, D, true>(p, s);
     HGSF_CASE(4, true, false) HGSF_CASE(5, true, false) HGSF_CASE(6, true, false) HGSF_CASE(7, true, false)
     HGSF_CASE(8, true, false) HGSF_CASE(7, false, false) HGSF_CASE(8, false, false)
     HGSF_CASE(7, true, true) HGSF_CASE(8, true, true)
