@@ -1207,22 +1207,38 @@ __global__ void __launch_bounds__(PT, HGSF_PILLARS_MINB) k_pillars(const PathPar
 }
 
 // ---- k_emit -------------------------------------------------------------------------------------
-// The fused kernel (used whenever the canvas is requested): order + decorate + PFN + max AND the canvas tile, one pass.
-// Every WARP is an autonomous worker walking its own sequence of canvas tiles (a tile = 32 cells of one BEV row x 64
-// channels = 64 rows of 128 B); no CTA barrier in the loop.  Because k_front laid the CSR out in cell order, the point
-// rows of a tile are ONE contiguous span of sorted_rows: they are staged with a single cooperative cp.async copy issued
-// a tile ahead, from table entries loaded two tiles ahead -- no dependent gathers anywhere.
+// The tile-major fused consumer (canvas requested, P <= 32, spconv-2 overflow rule, nx a multiple of 4): order + decorate +
+// PFN + max AND the canvas tile, one pass.  Every WARP is an autonomous worker walking its own sequence of canvas tiles (a
+// tile = 32 cells of one BEV row x 64 channels = 64 rows of 128 B); no CTA barrier in the loop.  Because k_front laid the
+// CSR out in cell order, the point rows of a tile are ONE contiguous span of sorted_rows: they are staged with a single
+// cooperative cp.async copy issued a tile ahead; the tile's record comes two tiles ahead, its table entries one -- no
+// dependent gathers anywhere, and empty cells / empty tiles are never looked up in the table.
 //   lane l OWNS cell l of the tile for the bookkeeping (ordering by point index, first P kept, mean in torch's
-//   summation order, voxel_coords / voxel_num_points);
+//   summation order, voxel_coords / voxel_num_points) and zeroes the table entry it read (k_front finds the table clean);
 //   the arithmetic is cut into UNITS of (pillar, 4 output channels): lane l always computes channels 4*(l&15)..+3, so
-//   its Linear weight float4s and BatchNorm constants stay in REGISTERS for the whole kernel (CUDA-core FMA: a 13x64
-//   contraction is far below a tensor-core tile).  Single-point pillars are paired across the half-warps; a
-//   multi-point pillar is taken by both halves, which split its points and max-combine.
+//   its Linear weights (packed pairs, one FFMA2 per channel pair and input feature) and BatchNorm constants stay in
+//   REGISTERS for the whole kernel (CUDA-core FMA: a 13x64 contraction is far below a tensor-core tile).  Single-point
+//   pillars are paired across the half-warps; a multi-point pillar is taken by both halves, which split its points and
+//   max-combine.
 //   A finished tile leaves in ONE TMA tensor store (128-byte swizzle so the column writes spread over banks); an
 //   empty tile is four stores of a shared 2 KB zero tile.  The canvas is written exactly once, zeros included.
-constexpr int EMIT_WARPS = 4;
+// Against the pillar-major k_pillars (groups of <= 32 pillars, st.cs tile writes) on one B200, ms per step:
+//   VoD clustered 0.178 / 0.190, VoD uniform 0.175 / 0.193, TJ4D clustered 0.315 / 0.320, stress 0.771 / 0.783.
+// Measured on this kernel and NOT kept (VoD clustered, ms in k_emit, baseline 0.129):
+//   tickets 2 ahead + records / entries 3 tiles ahead through a cp.async ring   0.144  (stalls gone, window wider: slower)
+//   one ticket per CTA = 4 / 8 / 16 adjacent tiles popped from a shared queue   0.163 / 0.162 / 0.168
+//   listed (heavy) tiles spread over 85 % / 100 % of the ticket sequence        0.141 / 0.146 (all first: 0.129)
+//   16 / 15 / 14 warps per SM at 128 registers (4x4, 3x5, 2x7 warps; no spills) 0.141 / 0.137 / 0.136
+//   listing threshold 40 / 28 / 20 / 12 points                                  0.132 / 0.133 / 0.133 / 0.134
+#ifndef HGSF_EMIT_WARPS
+#define HGSF_EMIT_WARPS 4
+#endif
+#ifndef HGSF_EMIT_STAGE
+#define HGSF_EMIT_STAGE 64
+#endif
+constexpr int EMIT_WARPS = HGSF_EMIT_WARPS;
 constexpr int EMIT_THREADS = EMIT_WARPS * 32;
-constexpr int STAGE_W = 64;           // staged point rows per tile (a typical tile holds ~10; the rest is read from L2)
+constexpr int STAGE_W = HGSF_EMIT_STAGE;           // staged point rows per tile (a typical tile holds ~10; the rest is read from L2)
 
 #ifndef HGSF_EMIT_MINB
 #define HGSF_EMIT_MINB 3
@@ -1236,8 +1252,6 @@ k_emit(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtenso
     constexpr int NV = RWc / 4;
     constexpr int TILE = C * 32;
     constexpr int ZC = C / 4;
-    constexpr bool TMA = true;
-    constexpr int STORE = 0;
     constexpr int NT = EMIT_THREADS;
 
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -1278,7 +1292,7 @@ k_emit(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtenso
         s_K[p.B] = acc;
         if (blockIdx.x == 0) p.num_pillars[0] = acc;
     }
-    if (TMA) fence_proxy_async_smem();
+    fence_proxy_async_smem();
     __syncthreads();
 
     // this lane's 4 channels: Linear rows and BatchNorm constants, in registers for the whole kernel
@@ -1477,24 +1491,12 @@ k_emit(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtenso
         if (skip) {
         } else if (bal_occ == 0u) {
             // empty tile: four stores of the shared zero tile
-            if (TMA) {
-                // issued by lane 1: bulk async-groups are per thread, so lane 0's wait for its tile store to have read the
-                // tile buffer (below) does not also wait for the zero stores of the empty tiles that came after it
-                if (lane == 1) {
+            // issued by lane 1: bulk async-groups are per thread, so lane 0's wait for its tile store to have read the
+            // tile buffer (below) does not also wait for the zero stores of the empty tiles that came after it
+            if (lane == 1) {
 #pragma unroll
-                    for (int q4 = 0; q4 < 4; ++q4) tma_store_3d_hint(&zmap, zerobuf, x0, y, b * C + q4 * ZC, stream_policy);
-                    tma_commit();
-                }
-            } else if (STORE == 1) {
-                const int xc = x0 + 4 * (lane & 7);      // lane l: 16-byte chunk (l & 7) of channel rows (l >> 3) + 4*i
-                if (xc < p.nx) {
-                    float *dst = p.canvas + (((size_t)b * C + (lane >> 3)) * p.ny + y) * p.nx + xc;
-                    const size_t plane4 = (size_t)4 * p.ny * p.nx;
-#pragma unroll
-                    for (int i = 0; i < C / 4; ++i) __stcs(reinterpret_cast<float4 *>(dst + i * plane4), make_float4(0.f, 0.f, 0.f, 0.f));
-                }
-            } else if (x0 + lane < p.nx) {
-                for (int ch = 0; ch < C; ++ch) p.canvas[(((size_t)b * C + ch) * p.ny + y) * p.nx + x0 + lane] = 0.f;
+                for (int q4 = 0; q4 < 4; ++q4) tma_store_3d_hint(&zmap, zerobuf, x0, y, b * C + q4 * ZC, stream_policy);
+                tma_commit();
             }
         } else {
             const int row0 = (int)r_cur.x;
@@ -1605,7 +1607,7 @@ k_emit(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtenso
                 rec[slot][1] = make_float4(__int_as_float(rel), __int_as_float(f), 0.f, 0.f);
             }
             // the tile buffer: wait until the previous store has read it, then clear what that tile dirtied
-            if (TMA && store_pending) {
+            if (store_pending) {
                 if (lane == 0) tma_wait_read<0>();
                 store_pending = false;
             }
@@ -1762,40 +1764,21 @@ k_emit(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtenso
                 }
             }
             // ---- the tile goes out in one piece ----
-            if (TMA) {
-                fence_proxy_async_smem();
-                __syncwarp();
+            fence_proxy_async_smem();
+            __syncwarp();
 #ifdef HGSF_EXPERIMENT
-                if (lane == 0 && !(p.dbg & 2)) { if (p.dbg & 4) tma_store_3d(&tmap, tile, x0, y, b * C); else tma_store_3d_hint(&tmap, tile, x0, y, b * C, stream_policy); tma_commit(); }
+            if (lane == 0 && !(p.dbg & 2)) { if (p.dbg & 4) tma_store_3d(&tmap, tile, x0, y, b * C); else tma_store_3d_hint(&tmap, tile, x0, y, b * C, stream_policy); tma_commit(); }
 #else
-                if (lane == 0) { tma_store_3d_hint(&tmap, tile, x0, y, b * C, stream_policy); tma_commit(); }
+            if (lane == 0) { tma_store_3d_hint(&tmap, tile, x0, y, b * C, stream_policy); tma_commit(); }
 #endif
-                store_pending = true;
-            } else if (STORE == 1) {
-                __syncwarp();
-                const int xc = x0 + 4 * (lane & 7);
-                if (xc < p.nx) {
-                    float *dst = p.canvas + (((size_t)b * C + (lane >> 3)) * p.ny + y) * p.nx + xc;
-                    const size_t plane4 = (size_t)4 * p.ny * p.nx;
-#pragma unroll
-                    for (int i = 0; i < C / 4; ++i) {
-                        const int row = (lane >> 3) + 4 * i;
-                        const float4 v = *reinterpret_cast<const float4 *>(tile + row * 32 + (((lane & 7) ^ (row & 7)) << 2));
-                        __stcs(reinterpret_cast<float4 *>(dst + i * plane4), v);
-                    }
-                }
-            } else {
-                __syncwarp();
-                if (x0 + lane < p.nx)
-                    for (int ch = 0; ch < C; ++ch) p.canvas[(((size_t)b * C + ch) * p.ny + y) * p.nx + x0 + lane] = tile[swz128(ch, lane)];
-            }
+            store_pending = true;
             __syncwarp();
         }
         e_cur = e_nxt; r_cur = r_nxt; r_nxt = r_nn;
         cur = nxt; nxt = nxt2; nxt2 = next_tile();
     }
     cp_async_wait<0>();
-    if (TMA && lane <= 1) tma_wait_read<0>();        // shared memory must outlive the stores that read it
+    if (lane <= 1) tma_wait_read<0>();        // shared memory must outlive the stores that read it
     mark_table_clean(p);
 }
 
