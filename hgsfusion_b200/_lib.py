@@ -20,7 +20,8 @@ EXPORTS = ["hgsf_abi_version", "hgsf_status_string", "hgsf_pillar_capacity", "hg
            "hgsf_pillarnet_workspace_size", "hgsf_pillarnet_indices", "hgsf_gather_feature", "hgsf_gather_feature_grad",
            "hgsf_scatter_max", "hgsf_scatter_max_grad", "hgsf_split_encode", "hgsf_pillarnet_reader",
            "hgsf_train_stats_doubles", "hgsf_train_scratch_doubles", "hgsf_pillar_vfe_batch_stats",
-           "hgsf_pillar_vfe_backward", "hgsf_pointpillar_scatter_backward", "hgsf_hybrid_workspace_size",
+           "hgsf_pillar_vfe_backward", "hgsf_pointpillar_scatter_backward", "hgsf_points_to_bev_train",
+           "hgsf_points_to_bev_train_backward", "hgsf_hybrid_workspace_size",
            "hgsf_assemble_hybrid_points", "hgsf_sparse_to_dense_workspace_size", "hgsf_sparse_to_dense",
            "hgsf_subm_neighbors", "hgsf_subm_conv3x3", "hgsf_sparse_conv_s2_workspace_size",
            "hgsf_sparse_conv_s2_indices"]
@@ -126,6 +127,14 @@ def load():
                                                         C.c_void_p]
     lib.hgsf_pointpillar_scatter_backward.argtypes = [C.POINTER(Geometry), C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int32,
                                                       C.c_int32, C.c_void_p, C.c_void_p]
+    if hasattr(lib, "hgsf_points_to_bev_train"):
+        lib.hgsf_points_to_bev_train.argtypes = path_args + [C.POINTER(Pfn), C.c_int32, C.c_int32, C.c_void_p, C.c_size_t,
+                                                             C.POINTER(PillarOutputs), C.c_float, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                             C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.hgsf_points_to_bev_train_backward.argtypes = [C.POINTER(Geometry), C.POINTER(Pfn), C.c_void_p, C.c_void_p, C.c_void_p,
+                                                          C.c_int64, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
+                                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                          C.c_void_p, C.c_void_p]
     lib.hgsf_hybrid_workspace_size.argtypes = [C.c_int64, C.POINTER(C.c_size_t)]
     lib.hgsf_assemble_hybrid_points.argtypes = [C.POINTER(HybridInputs), C.c_void_p, C.POINTER(C.c_double), C.c_void_p, C.c_size_t,
                                                 C.c_void_p, C.c_void_p, C.c_void_p]

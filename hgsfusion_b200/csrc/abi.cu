@@ -57,9 +57,8 @@ int hgsf_workspace_size(const hgsf_geometry *g, int64_t n, int32_t B, int32_t F,
     return HGSF_OK;
 }
 
-static int run_path(const hgsf_geometry *g, const hgsf_points *pt, const hgsf_pfn *pfn, int32_t P, int32_t max_voxels,
-                    void *ws, size_t ws_bytes, const hgsf_pillar_outputs *out, hgsf_stream_t stream) {
-    g_last_launches = 0;
+static int path_params(const hgsf_geometry *g, const hgsf_points *pt, const hgsf_pfn *pfn, int32_t P, int32_t max_voxels,
+                       void *ws, size_t ws_bytes, const hgsf_pillar_outputs *out, PathParams &p, bool &abs_xyz, bool &dist) {
     if (!geom_ok(g) || !pt || !out || !ws) return HGSF_ERR_INVALID_ARG;
     if (pt->n < 0 || pt->batch_size <= 0 || pt->num_features < 3 || pt->xyz_col < 0 ||
         pt->xyz_col + pt->num_features > pt->stride || (pt->n > 0 && !pt->data))
@@ -75,7 +74,7 @@ static int run_path(const hgsf_geometry *g, const hgsf_points *pt, const hgsf_pf
     if (out->pillar_capacity < hgsf_pillar_capacity(g, pt->n, pt->batch_size, max_voxels)) return HGSF_ERR_INVALID_ARG;
     if (ws_bytes < w.total || (reinterpret_cast<uintptr_t>(ws) & 255)) return HGSF_ERR_WORKSPACE;
 
-    PathParams p{};
+    p = PathParams{};
     p.pts = pt->data; p.n = (int)pt->n; p.stride = pt->stride; p.xyz_col = pt->xyz_col; p.F = pt->num_features;
     p.batch_col = pt->batch_col; p.frame_offsets_in = pt->frame_offsets; p.B = pt->batch_size;
     for (int j = 0; j < 3; ++j) { p.rmin[j] = g->pc_range[j]; p.vsize[j] = g->voxel_size[j]; p.voff[j] = g->centre_off[j]; }
@@ -109,7 +108,7 @@ static int run_path(const hgsf_geometry *g, const hgsf_points *pt, const hgsf_pf
     p.RW = w.RW;
     p.coords = out->voxel_coords; p.num = out->voxel_num_points; p.num_pillars = out->num_pillars;
     p.voxels = out->voxels;
-    bool abs_xyz = true, dist = false;
+    abs_xyz = true; dist = false;
     if (pfn) {
         if (!pfn->weight || pfn->out_channels <= 0) return HGSF_ERR_INVALID_ARG;
         const bool bn = pfn->bn_weight || pfn->bn_bias || pfn->bn_mean || pfn->bn_var;
@@ -124,6 +123,16 @@ static int run_path(const hgsf_geometry *g, const hgsf_points *pt, const hgsf_pf
         p.Cin = cin; p.C = pfn->out_channels;
         p.feats = out->pillar_features; p.canvas = out->spatial_features;
     }
+    return HGSF_OK;
+}
+
+static int run_path(const hgsf_geometry *g, const hgsf_points *pt, const hgsf_pfn *pfn, int32_t P, int32_t max_voxels,
+                    void *ws, size_t ws_bytes, const hgsf_pillar_outputs *out, hgsf_stream_t stream) {
+    g_last_launches = 0;
+    PathParams p{};
+    bool abs_xyz = true, dist = false;
+    const int st = path_params(g, pt, pfn, P, max_voxels, ws, ws_bytes, out, p, abs_xyz, dist);
+    if (st != HGSF_OK) return st;
     return launch_pillar_path(p, pfn != nullptr, abs_xyz, dist, static_cast<cudaStream_t>(stream), &g_last_launches);
 }
 
@@ -387,6 +396,51 @@ int hgsf_pointpillar_scatter_backward(const hgsf_geometry *g, const float *grad_
     const int st = launch_scatter_grad(grad_canvas, coords, coords_are_float, M, C, B, g->grid[1], g->grid[0], grad_feats,
                                        static_cast<cudaStream_t>(stream));
     if (st == HGSF_OK) g_last_launches = M > 0;
+    return st;
+}
+
+int hgsf_points_to_bev_train(const hgsf_geometry *g, const hgsf_points *pt, const hgsf_pfn *pfn, int32_t P, int32_t max_voxels,
+                             void *ws, size_t ws_bytes, const hgsf_pillar_outputs *out, float momentum, float *running_mean,
+                             float *running_var, float *batch_mean, float *batch_var, double *stats, hgsf_stream_t stream) {
+    g_last_launches = 0;
+    if (!pfn || !out || !pfn->bn_weight || !pfn->bn_bias || !batch_mean || !batch_var || !stats) return HGSF_ERR_INVALID_ARG;
+    if (!out->spatial_features || !out->pillar_features) return HGSF_ERR_INVALID_ARG;
+    hgsf_pfn train = *pfn;                       // the statistics the forward normalises with are this call's own
+    train.bn_mean = batch_mean; train.bn_var = batch_var;
+    PathParams p{};
+    bool abs_xyz = true, dist = false;
+    const int st = path_params(g, pt, &train, P, max_voxels, ws, ws_bytes, out, p, abs_xyz, dist);
+    if (st != HGSF_OK) return st;
+    p.stats = stats; p.batch_mean = batch_mean; p.batch_var = batch_var; p.run_mean = running_mean; p.run_var = running_var;
+    p.momentum = momentum;
+    return launch_pillar_path_train(p, abs_xyz, dist, static_cast<cudaStream_t>(stream), &g_last_launches);
+}
+
+int hgsf_points_to_bev_train_backward(const hgsf_geometry *g, const hgsf_pfn *pfn, const float *voxels, const int32_t *coords,
+                                      const int32_t *num, int64_t capacity, const int32_t *num_pillars, int32_t P, int32_t F,
+                                      int32_t B, const float *grad_canvas, const float *grad_feats_in, float *grad_rows,
+                                      double *stats, double *scratch, float *grad_weight, float *grad_bn_weight,
+                                      float *grad_bn_bias, hgsf_stream_t stream) {
+    g_last_launches = 0;
+    VfeParams q;
+    bool abs_xyz, dist;
+    int st = vfe_params(g, pfn, voxels, coords, num, 0, 0, capacity, P, F, q, abs_xyz, dist);
+    if (st != HGSF_OK) return st;
+    if (!num_pillars || !grad_rows || !stats || !scratch || !grad_weight || !grad_bn_weight || !grad_bn_bias || B <= 0 ||
+        g->grid[2] != 1)
+        return HGSF_ERR_INVALID_ARG;
+    if (!(pfn->bn_weight && pfn->bn_bias && pfn->bn_mean && pfn->bn_var)) return HGSF_ERR_INVALID_ARG;
+    if (capacity == 0) return HGSF_ERR_INVALID_ARG;
+    q.M_dev = num_pillars;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    st = launch_scatter_grad(grad_canvas, coords, 0, capacity, q.C, B, g->grid[1], g->grid[0], grad_rows, s, num_pillars,
+                             grad_feats_in);
+    if (st != HGSF_OK) return st;
+    st = launch_vfe_stats(q, abs_xyz, dist, stats, s);
+    if (st != HGSF_OK) return st;
+    int nl = 0;
+    st = launch_vfe_backward(q, abs_xyz, dist, grad_rows, stats, 0, scratch, grad_weight, grad_bn_weight, grad_bn_bias, s, &nl);
+    if (st == HGSF_OK) g_last_launches = 2 + nl;
     return st;
 }
 

@@ -19,6 +19,9 @@ struct VfeParams {
     // NUM_FILTERS[0] / 2) and pfn1 the last one, in_channels 2*C -> C1
     PfnArgs pfn1;
     int C1;
+    // train_ops.cu only: when set, the number of pillars is read on the device (min(M, *M_dev)): M is then the capacity of the
+    // buffers and nothing has to come back to the host between the forward and the backward
+    const int32_t *M_dev;
 };
 
 struct ScatterParams {

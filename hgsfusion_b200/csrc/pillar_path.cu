@@ -195,7 +195,9 @@ __global__ void __launch_bounds__(FRONT_THREADS, 4) k_front(const PathParams p) 
 
     // ---- phase 0: zero the cell table, unless the previous call's consumer kernel left it clean ----
     const bool clean = (ld_volatile_u64(p.state) == p.magic);        // grid-uniform: nobody writes p.state before the first barrier
-    if (cta == 0 && tid == 0) { p.ticket[0] = 0u; p.ticket[32] = 0u; p.ticket[64] = 0u; }      // run ticket, heavy-tile count, finished CTAs
+    if (cta == 0 && tid == 0) { p.ticket[0] = 0u; p.ticket[32] = 0u; p.ticket[64] = 0u; p.ticket[16] = 0u; p.ticket[48] = 0u; }   // run ticket, heavy-tile
+                                                          // count, finished CTAs; tickets / finished CTAs of the statistics pass
+    if (p.stats && cta == 0 && tid < 128) p.stats[tid] = 0.0;
     if ((p.flags & HGSF_POINTS_SPCONV1_BREAK) && cta == 0) for (int b = tid; b < p.B; b += FRONT_THREADS) p.cutoff[b] = INT_MAX;
     if (!clean) {
         uint4 *t4 = reinterpret_cast<uint4 *>(p.cell_tag);           // tag, cnt: two arrays back to back
@@ -1243,7 +1245,11 @@ constexpr int STAGE_W = HGSF_EMIT_STAGE;           // staged point rows per tile
 #ifndef HGSF_EMIT_MINB
 #define HGSF_EMIT_MINB 3
 #endif
-template <int F, bool ABS, bool DIST, bool BN, int CHUNK>
+// STATS: the train-mode statistics pass (BatchNorm1d on batch statistics, pillar_vfe.py:29-42): the same walk over the same
+// tiles with the same arithmetic up to the Linear output x, which is summed per channel (Sx, Sxx in fp64) instead of being
+// normalised and max-reduced; nothing is written but p.stats, the table is left as it is for the real pass that follows, and the
+// last CTA turns the sums into batch_mean / batch_var and updates the running statistics.
+template <int F, bool ABS, bool DIST, bool BN, int CHUNK, bool STATS>
 __global__ void __launch_bounds__(EMIT_THREADS, HGSF_EMIT_MINB)
 k_emit(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap zmap, const PathParams p) {
     constexpr int C = 64;
@@ -1286,11 +1292,11 @@ k_emit(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtenso
         for (int b = 0; b < p.B; ++b) {
             s_K[b] = acc;
             const int m = min(s_R[b + 1] - s_R[b], p.max_voxels);
-            if (blockIdx.x == 0) p.num_pillars[1 + b] = m;
+            if (!STATS && blockIdx.x == 0) p.num_pillars[1 + b] = m;
             acc += m;
         }
         s_K[p.B] = acc;
-        if (blockIdx.x == 0) p.num_pillars[0] = acc;
+        if (!STATS && blockIdx.x == 0) p.num_pillars[0] = acc;
     }
     fence_proxy_async_smem();
     __syncthreads();
@@ -1347,8 +1353,10 @@ k_emit(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtenso
 
     // one point through decorate + Linear + BN, folded into the running max (integer max on the float bits: exact for
     // the non-negative post-ReLU values, drops negatives and -0 = the ReLU, lets a NaN 0x7fffffff win as torch.max does)
+    float *const feats_out = STATS ? nullptr : p.feats, *const voxels_out = STATS ? nullptr : p.voxels;
+    double st_x[4] = {0.0, 0.0, 0.0, 0.0}, st_xx[4] = {0.0, 0.0, 0.0, 0.0};      // STATS: this lane's sums of x and x^2, channels c0..c0+3
     auto eval_row = [&](const float (&row)[RWc], float mx, float my, float mz, float cx, float cy,
-                        int &v0, int &v1, int &v2, int &v3) {
+                        int &v0, int &v1, int &v2, int &v3, bool counted = true) {
         float feat[CIN];
         {
             int kf = 0;
@@ -1365,6 +1373,15 @@ k_emit(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtenso
             const uint64_t ff = pack_f2(feat[kk], feat[kk]);
             a01 = fma2_rn(ff, w01[kk], a01);
             a23 = fma2_rn(ff, w23[kk], a23);
+        }
+        if (STATS) {                           // a row evaluated twice to fill a pair (below) counts once
+            float x0, x1, x2, x3;
+            unpack_f2(a01, x0, x1); unpack_f2(a23, x2, x3);
+            if (counted) {
+                st_x[0] += (double)x0; st_xx[0] += (double)x0 * (double)x0; st_x[1] += (double)x1; st_xx[1] += (double)x1 * (double)x1;
+                st_x[2] += (double)x2; st_xx[2] += (double)x2 * (double)x2; st_x[3] += (double)x3; st_xx[3] += (double)x3 * (double)x3;
+            }
+            return;
         }
         float y0, y1, y2, y3;
         if (BN) {                              // BN eval: (((x-mean)*invstd)*gamma)+beta, 4 roundings (:39); the last add scalar (common.cuh)
@@ -1391,6 +1408,7 @@ k_emit(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtenso
     float *const tbase = tile + c0 * 32;
     const int swb = (lane & 1) << 2;
     auto put_tile = [&](int cell, int v0, int v1, int v2, int v3) {
+        if (STATS) return;
         const int xs = (cell >> 2) ^ swb, xr = cell & 3;
         tbase[0 * 32 + (((xs ^ 0) << 2) | xr)] = __int_as_float(v0);
         tbase[1 * 32 + (((xs ^ 1) << 2) | xr)] = __int_as_float(v1);
@@ -1413,7 +1431,7 @@ k_emit(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtenso
     // stall the whole warp on the atomic's round trip
     auto fetch_raw = [&]() -> int {
         int v = 0;
-        if (lane == 0) v = (int)atomicAdd(p.ticket, 1u);
+        if (lane == 0) v = (int)atomicAdd(p.ticket + (STATS ? 16 : 0), 1u);
         return v;
     };
     struct Slot { int t; bool listed; };             // t == n_tiles: past the end
@@ -1480,7 +1498,7 @@ k_emit(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtenso
         const int b = (int)fastdiv(row_id, p.div_ny);
         const int y = (int)row_id - b * p.ny, x0 = (cur.t - (int)row_id * p.tiles_per_row) * 32;
         const bool skip = skipped(cur, r_cur);
-        if (e_cur.y) {                   // the entry has been read: leave the table clean for the next call's k_front
+        if (!STATS && e_cur.y) {         // the entry has been read: leave the table clean for the next call's k_front
             const size_t c = (size_t)cur.t * 32 + lane;
             p.cell_tag[c] = 0u; p.cell_cnt[c] = 0u;
         }
@@ -1490,6 +1508,8 @@ k_emit(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtenso
         const unsigned bal_occ = __ballot_sync(FULL, occ);
         if (skip) {
         } else if (bal_occ == 0u) {
+            if (STATS) {
+            } else
             // empty tile: four stores of the shared zero tile
             // issued by lane 1: bulk async-groups are per thread, so lane 0's wait for its tile store to have read the
             // tile buffer (below) does not also wait for the zero stores of the empty tiles that came after it
@@ -1505,7 +1525,7 @@ k_emit(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtenso
             const int rel = staged ? rel0 : (-1 - start);         // where the pillar's rows are (see load_row)
             const int n_keep = min(cnt, Pmax);
             const int f = s_K[b] + local;                          // final pillar id (first-seen order, frames concatenated)
-            if (occ) {
+            if (!STATS && occ) {
                 p.num[f] = n_keep;
                 *reinterpret_cast<int4 *>(p.coords + 4 * (size_t)f) = make_int4(b, 0, y, x0 + lane);
             }
@@ -1607,12 +1627,13 @@ k_emit(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtenso
                 rec[slot][1] = make_float4(__int_as_float(rel), __int_as_float(f), 0.f, 0.f);
             }
             // the tile buffer: wait until the previous store has read it, then clear what that tile dirtied
-            if (store_pending) {
+            if (!STATS && store_pending) {
                 if (lane == 0) tma_wait_read<0>();
                 store_pending = false;
             }
             __syncwarp();
-            if (__popc(dirty) > 2) {
+            if (STATS) {
+            } else if (__popc(dirty) > 2) {
 #pragma unroll
                 for (int t = 0; t < TILE / 128; ++t) *reinterpret_cast<float4 *>(tile + t * 128 + lane * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
             } else {
@@ -1652,12 +1673,12 @@ k_emit(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtenso
                     load_row(stg, __float_as_int(rA1.x), metaA >> 16, rowA);
                     load_row(stg, __float_as_int(rB1.x), metaB >> 16, rowB);
                     eval_row(rowA, rA0.x, rA0.y, rA0.z, cxA, cy, a0, a1, a2, a3);
-                    eval_row(rowB, rB0.x, rB0.y, rB0.z, cxB, cy, b0, b1, b2, b3);
-                    if (p.feats) {
-                        st_f4_hint(p.feats + (size_t)__float_as_int(rA1.y) * C + c0,
+                    eval_row(rowB, rB0.x, rB0.y, rB0.z, cxB, cy, b0, b1, b2, b3, okB);
+                    if (feats_out) {
+                        st_f4_hint(feats_out + (size_t)__float_as_int(rA1.y) * C + c0,
                                    make_float4(__int_as_float(a0), __int_as_float(a1), __int_as_float(a2), __int_as_float(a3)), feats_policy);
                         if (okB)
-                            st_f4_hint(p.feats + (size_t)__float_as_int(rB1.y) * C + c0,
+                            st_f4_hint(feats_out + (size_t)__float_as_int(rB1.y) * C + c0,
                                        make_float4(__int_as_float(b0), __int_as_float(b1), __int_as_float(b2), __int_as_float(b3)), feats_policy);
                     }
                     put_tile(cellA, a0, a1, a2, a3);
@@ -1688,14 +1709,14 @@ k_emit(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtenso
                     load_row(stg, relp, perm[cell][s3], rowB);
 #endif
                     eval_row(rowA, r0.x, r0.y, r0.z, cx, cy, v0, v1, v2, v3);
-                    eval_row(rowB, r0.x, r0.y, r0.z, cx, cy, u0, u1, u2, u3);
+                    eval_row(rowB, r0.x, r0.y, r0.z, cx, cy, u0, u1, u2, u3, s2 + 2 < nk);
                 }
                 v0 = max(v0, u0); v1 = max(v1, u1); v2 = max(v2, u2); v3 = max(v3, u3);
                 v0 = max(v0, __shfl_xor_sync(FULL, v0, 16)); v1 = max(v1, __shfl_xor_sync(FULL, v1, 16));
                 v2 = max(v2, __shfl_xor_sync(FULL, v2, 16)); v3 = max(v3, __shfl_xor_sync(FULL, v3, 16));
                 if (half == 0) {
-                    if (p.feats)
-                        st_f4_hint(p.feats + (size_t)__float_as_int(r1.y) * C + c0,
+                    if (feats_out)
+                        st_f4_hint(feats_out + (size_t)__float_as_int(r1.y) * C + c0,
                                    make_float4(__int_as_float(v0), __int_as_float(v1), __int_as_float(v2), __int_as_float(v3)), feats_policy);
                     put_tile(cell, v0, v1, v2, v3);
                 }
@@ -1710,8 +1731,8 @@ k_emit(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtenso
                 const float *grow_o = grows + (size_t)start_o * RWc;
                 { uint32_t key_unused; bperm[lane] = select_next32(grow_o + F, RWc, cnt_o, lane, false, 0u, key_unused); }
                 __syncwarp();
-                if (p.voxels) {
-                    float *vo = p.voxels + (size_t)f_o * Pmax * F;
+                if (voxels_out) {
+                    float *vo = voxels_out + (size_t)f_o * Pmax * F;
                     for (int t = lane; t < Pmax * F; t += 32) {
                         const int s2 = t / F, kk = t - s2 * F;
                         vo[t] = (s2 < nk) ? __ldg(grow_o + (size_t)bperm[s2] * RWc + kk) : 0.f;
@@ -1736,22 +1757,22 @@ k_emit(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtenso
                 v0 = max(v0, __shfl_xor_sync(FULL, v0, 16)); v1 = max(v1, __shfl_xor_sync(FULL, v1, 16));
                 v2 = max(v2, __shfl_xor_sync(FULL, v2, 16)); v3 = max(v3, __shfl_xor_sync(FULL, v3, 16));
                 if (half == 0) {
-                    if (p.feats)
-                        st_f4_hint(p.feats + (size_t)f_o * C + c0,
+                    if (feats_out)
+                        st_f4_hint(feats_out + (size_t)f_o * C + c0,
                                    make_float4(__int_as_float(v0), __int_as_float(v1), __int_as_float(v2), __int_as_float(v3)), feats_policy);
                     put_tile(o, v0, v1, v2, v3);
                 }
                 __syncwarp();
             }
             // ---- optional contract output: the padded voxels tensor [M, P, F], coalesced, one pillar at a time ----
-            if (p.voxels) {
+            if (voxels_out) {
                 unsigned todo = __ballot_sync(FULL, live);
                 while (todo) {
                     const int o = __ffs(todo) - 1;
                     todo &= todo - 1;
                     const int cnt_o = __shfl_sync(FULL, cnt, o), rel_o = __shfl_sync(FULL, rel, o), f_o = __shfl_sync(FULL, f, o);
                     const int nk = min(cnt_o, Pmax);
-                    float *vo = p.voxels + (size_t)f_o * Pmax * F;
+                    float *vo = voxels_out + (size_t)f_o * Pmax * F;
                     for (int t = lane; t < Pmax * F; t += 32) {
                         const int s2 = t / F, kk = t - s2 * F;
                         float v = 0.f;
@@ -1764,20 +1785,66 @@ k_emit(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtenso
                 }
             }
             // ---- the tile goes out in one piece ----
-            fence_proxy_async_smem();
-            __syncwarp();
+            if (!STATS) {
+                fence_proxy_async_smem();
+                __syncwarp();
 #ifdef HGSF_EXPERIMENT
-            if (lane == 0 && !(p.dbg & 2)) { if (p.dbg & 4) tma_store_3d(&tmap, tile, x0, y, b * C); else tma_store_3d_hint(&tmap, tile, x0, y, b * C, stream_policy); tma_commit(); }
+                if (lane == 0 && !(p.dbg & 2)) { if (p.dbg & 4) tma_store_3d(&tmap, tile, x0, y, b * C); else tma_store_3d_hint(&tmap, tile, x0, y, b * C, stream_policy); tma_commit(); }
 #else
-            if (lane == 0) { tma_store_3d_hint(&tmap, tile, x0, y, b * C, stream_policy); tma_commit(); }
+                if (lane == 0) { tma_store_3d_hint(&tmap, tile, x0, y, b * C, stream_policy); tma_commit(); }
 #endif
-            store_pending = true;
+                store_pending = true;
+            }
             __syncwarp();
         }
         e_cur = e_nxt; r_cur = r_nxt; r_nxt = r_nn;
         cur = nxt; nxt = nxt2; nxt2 = next_tile();
     }
     cp_async_wait<0>();
+    if (STATS) {
+        // lanes l and l + 16 hold the same four channels; then the warps of the CTA, then one fp64 atomic per channel and sum
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { st_x[i] += __shfl_xor_sync(FULL, st_x[i], 16); st_xx[i] += __shfl_xor_sync(FULL, st_xx[i], 16); }
+        __syncthreads();                                  // every warp is done with its tile buffer: reused for the reduction
+        double *red = reinterpret_cast<double *>(tiles);  // [EMIT_WARPS][2][C]
+        if (lane < 16) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { red[(warp * 2 + 0) * C + c0 + i] = st_x[i]; red[(warp * 2 + 1) * C + c0 + i] = st_xx[i]; }
+        }
+        __syncthreads();
+        for (int t = tid; t < 2 * C; t += NT) {
+            double acc = 0.0;
+            for (int w = 0; w < EMIT_WARPS; ++w) acc += red[w * 2 * C + t];
+            if (acc != 0.0) atomicAdd(p.stats + t, acc);
+        }
+        // the last CTA to get here turns the sums into the batch statistics (train_ops.cu k_bn_finalize, same arithmetic):
+        // N = M * P rows per channel, the zero-padded rows included (they add nothing to the sums)
+        __shared__ int s_last;
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) s_last = (atomicAdd(p.ticket + 48, 1u) == gridDim.x - 1u) ? 1 : 0;
+        __syncthreads();
+        if (s_last && tid < C) {
+            __threadfence();
+            const double n_rows = (double)s_K[p.B] * (double)p.P;
+            if (n_rows > 0.0) {
+                const double mean = __ldcg(p.stats + tid) / n_rows;
+                double var = __ldcg(p.stats + C + tid) / n_rows - mean * mean;
+                if (var < 0.0) var = 0.0;
+                p.batch_mean[tid] = (float)mean;
+                p.batch_var[tid] = (float)var;
+                if (p.run_mean) p.run_mean[tid] = (float)((1.0 - (double)p.momentum) * (double)p.run_mean[tid] + (double)p.momentum * mean);
+                if (p.run_var) {
+                    const double unbiased = n_rows > 1.0 ? var * n_rows / (n_rows - 1.0) : var;
+                    p.run_var[tid] = (float)((1.0 - (double)p.momentum) * (double)p.run_var[tid] + (double)p.momentum * unbiased);
+                }
+            } else {                                      // no pillar at all: nothing to normalise, running statistics untouched
+                p.batch_mean[tid] = 0.f;
+                p.batch_var[tid] = 1.f;
+            }
+        }
+        return;
+    }
     if (lane <= 1) tma_wait_read<0>();        // shared memory must outlive the stores that read it
     mark_table_clean(p);
 }
@@ -1882,7 +1949,7 @@ static int launch_pillars_t(const PathParams &p, cudaStream_t stream) {
 }
 
 template <int F, bool ABS, bool DIST>
-static int launch_emit_t(const PathParams &p, cudaStream_t stream) {
+static int launch_emit_t(const PathParams &p, cudaStream_t stream, bool stats_pass = false) {
     constexpr int C = 64;
     constexpr int RWc = (F + 1 + 3) / 4 * 4;
     CUtensorMap map, zmap;
@@ -1913,8 +1980,9 @@ static int launch_emit_t(const PathParams &p, cudaStream_t stream) {
 #endif
         return (int)cudaLaunchKernelEx(&cfg, kern, map, zmap, p);
     };
-    if (chunk == 2) return bn ? go(k_emit<F, ABS, DIST, true, 2>) : go(k_emit<F, ABS, DIST, false, 2>);
-    return bn ? go(k_emit<F, ABS, DIST, true, 1>) : go(k_emit<F, ABS, DIST, false, 1>);
+    if (stats_pass) return chunk == 2 ? go(k_emit<F, ABS, DIST, true, 2, true>) : go(k_emit<F, ABS, DIST, true, 1, true>);
+    if (chunk == 2) return bn ? go(k_emit<F, ABS, DIST, true, 2, false>) : go(k_emit<F, ABS, DIST, false, 2, false>);
+    return bn ? go(k_emit<F, ABS, DIST, true, 1, false>) : go(k_emit<F, ABS, DIST, false, 1, false>);
 }
 
 static int launch_pillars(const PathParams &p, bool with_pfn, bool abs_xyz, bool dist, cudaStream_t s) {
@@ -1966,12 +2034,11 @@ int emit_timing_collect(float *ms, int n) {
     return out;
 }
 
-int launch_pillar_path(const PathParams &p_in, bool with_pfn, bool abs_xyz, bool dist, cudaStream_t stream, int *launches) {
-    PathParams p = p_in;
+// heavy-tile threshold, canvas store mode, CTA slices; then k_front (cooperative)
+static int launch_front(PathParams &p, cudaStream_t stream) {
 #ifdef HGSF_EXPERIMENT
     { static const int dbg = getenv("HGSF_DBG") ? atoi(getenv("HGSF_DBG")) : 0; p.dbg = dbg; }
 #endif
-    int nl = 0;
     {
         // heavy tile = more than 6 times the average tile's points, at least 48 (HGSF_HEAVY_PTS overrides; huge = none)
         const long long n_tt = ((long long)p.B * p.cells) >> 5;
@@ -1981,38 +2048,62 @@ int launch_pillar_path(const PathParams &p_in, bool with_pfn, bool abs_xyz, bool
     }
     p.canvas_vec = (p.canvas != nullptr) && (p.nx % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.canvas) & 15) == 0) &&
                    !(getenv("HGSF_CANVAS_STORE") && getenv("HGSF_CANVAS_STORE")[0] == 's');       // 's': force scalar stores (tests)
-    {
-        // cooperative launch: every CTA must be resident, so the grid is the occupancy limit (capped: ~4 CTAs/SM is
-        // plenty of parallelism for a latency-bound front end and keeps the grid barriers cheap)
-        static int per_sm_cached = []() {
-            int per_sm = 1;
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_front, FRONT_THREADS, 0);
-            const char *env = getenv("HGSF_FRONT_CTAS");
-            const int cap = env ? atoi(env) : 4;
-            return std::max(1, std::min(per_sm, cap));
-        }();
-        const int max_ctas = std::min(sm_count() * per_sm_cached, MAX_FRONT_CTAS);
-        const long long n_cells = (long long)p.B * p.cells;
-        const long long want = std::max<long long>((n_cells + FRONT_THREADS * 8 - 1) / (FRONT_THREADS * 8),
-                                                   ((long long)p.n + FRONT_THREADS - 1) / FRONT_THREADS);
-        const int grid = (int)std::max<long long>(1, std::min<long long>(want, max_ctas));
-        // every CTA gets the same number of points / cells (multiples of 32)
-        const long long n_pad = ((long long)p.n + 31) / 32 * 32;
-        p.pslice = (int)(((n_pad + grid - 1) / grid + 31) / 32 * 32);
-        p.cslice = (int)(((n_cells + grid - 1) / grid + 31) / 32 * 32);
-        PathParams pp = p;
-        void *args[] = {&pp};
-        cudaError_t e = cudaLaunchCooperativeKernel((const void *)k_front, dim3(grid), dim3(FRONT_THREADS), args, 0, stream);
-        if (e != cudaSuccess) return (int)e;
-        ++nl;
-    }
+    // cooperative launch: every CTA must be resident, so the grid is the occupancy limit (capped: ~4 CTAs/SM is
+    // plenty of parallelism for a latency-bound front end and keeps the grid barriers cheap)
+    static int per_sm_cached = []() {
+        int per_sm = 1;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_front, FRONT_THREADS, 0);
+        const char *env = getenv("HGSF_FRONT_CTAS");
+        const int cap = env ? atoi(env) : 4;
+        return std::max(1, std::min(per_sm, cap));
+    }();
+    const int max_ctas = std::min(sm_count() * per_sm_cached, MAX_FRONT_CTAS);
+    const long long n_cells = (long long)p.B * p.cells;
+    const long long want = std::max<long long>((n_cells + FRONT_THREADS * 8 - 1) / (FRONT_THREADS * 8),
+                                               ((long long)p.n + FRONT_THREADS - 1) / FRONT_THREADS);
+    const int grid = (int)std::max<long long>(1, std::min<long long>(want, max_ctas));
+    // every CTA gets the same number of points / cells (multiples of 32)
+    const long long n_pad = ((long long)p.n + 31) / 32 * 32;
+    p.pslice = (int)(((n_pad + grid - 1) / grid + 31) / 32 * 32);
+    p.cslice = (int)(((n_cells + grid - 1) / grid + 31) / 32 * 32);
+    PathParams pp = p;
+    void *args[] = {&pp};
+    return (int)cudaLaunchCooperativeKernel((const void *)k_front, dim3(grid), dim3(FRONT_THREADS), args, 0, stream);
+}
+
+int launch_pillar_path(const PathParams &p_in, bool with_pfn, bool abs_xyz, bool dist, cudaStream_t stream, int *launches) {
+    PathParams p = p_in;
+    p.stats = nullptr;
+    int st = launch_front(p, stream);
+    if (st != HGSF_OK) return st;
     const bool timed = g_timing.capacity > 0 && g_timing.count < g_timing.capacity;
     if (timed) cudaEventRecord(g_timing.ev[2 * g_timing.count], stream);
-    const int st = launch_pillars(p, with_pfn, abs_xyz, dist, stream);
+    st = launch_pillars(p, with_pfn, abs_xyz, dist, stream);
     if (st != HGSF_OK) return st;
     if (timed) cudaEventRecord(g_timing.ev[2 * g_timing.count++ + 1], stream);
-    ++nl;
-    if (launches) *launches = nl;
+    if (launches) *launches = 2;
+    return HGSF_OK;
+}
+
+int launch_pillar_path_train(const PathParams &p_in, bool abs_xyz, bool dist, cudaStream_t stream, int *launches) {
+    PathParams p = p_in;
+    if (!p.stats || !p.batch_mean || !p.batch_var || !p.bn_w || !p.bn_b || !p.canvas || p.C != 64) return HGSF_ERR_INVALID_ARG;
+    if (p.nx % 4 != 0 || (reinterpret_cast<uintptr_t>(p.canvas) & 15) || p.P > 32 || (p.flags & HGSF_POINTS_SPCONV1_BREAK))
+        return HGSF_ERR_UNSUPPORTED;
+    int st = launch_front(p, stream);
+    if (st != HGSF_OK) return st;
+    if (!p.canvas_vec) return HGSF_ERR_UNSUPPORTED;      // HGSF_CANVAS_STORE=s (tests of the scalar store path)
+    // pass 1 (statistics) normalises nothing: it needs valid pointers only; pass 2 normalises with what pass 1 left
+    p.bn_m = p.batch_mean; p.bn_v = p.batch_var;
+    st = HGSF_ERR_UNSUPPORTED;
+#define HGSF_CASE(FV, A, D) if (p.F == FV && abs_xyz == A && dist == D) { \
+        st = launch_emit_t<FV, A, D>(p, stream, true); if (st == HGSF_OK) st = launch_emit_t<FV, A, D>(p, stream, false); }
+    HGSF_CASE(4, true, false) HGSF_CASE(5, true, false) HGSF_CASE(6, true, false) HGSF_CASE(7, true, false)
+    HGSF_CASE(8, true, false) HGSF_CASE(7, false, false) HGSF_CASE(8, false, false)
+    HGSF_CASE(7, true, true) HGSF_CASE(8, true, true)
+#undef HGSF_CASE
+    if (st != HGSF_OK) return st;
+    if (launches) *launches = 3;
     return HGSF_OK;
 }
 

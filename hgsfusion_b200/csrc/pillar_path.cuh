@@ -71,6 +71,11 @@ struct PathParams {
     const float *W, *bias, *bn_w, *bn_b, *bn_m, *bn_v;
     float eps;
     int Cin, C;
+    // ---- train mode (launch_pillar_path_train): BatchNorm1d on the statistics of the batch ----
+    double *stats;                     // [2*64] per-channel sums of the Linear output x and of x^2 over every kept point (zeroed by k_front)
+    float *batch_mean, *batch_var;     // [64] out: what the forward normalises with (biased variance)
+    float *run_mean, *run_var;         // [64] updated in place as torch.nn.BatchNorm1d does (may be null)
+    float momentum;
     // ---- outputs ----
     int32_t *coords, *num, *num_pillars;
     float *voxels, *feats, *canvas;
@@ -113,6 +118,9 @@ inline WorkspaceLayout workspace_layout(int64_t n, int B, int nx, int ny, int nz
 
 // launchers (pillar_path.cu); return a cudaError_t-or-HGSF status and count launches
 int launch_pillar_path(const PathParams &p, bool with_pfn, bool abs_xyz, bool dist, cudaStream_t stream, int *launches);
+// train-mode forward: k_front, the statistics pass, the fused pass on the batch statistics (3 launches, no host round trip).
+// HGSF_ERR_UNSUPPORTED outside the tile-major kernel's domain (BatchNorm, canvas, P <= 32, spconv-2 rule, nx % 4 == 0).
+int launch_pillar_path_train(const PathParams &p, bool abs_xyz, bool dist, cudaStream_t stream, int *launches);
 
 int emit_timing_begin(int capacity);
 int emit_timing_collect(float *ms, int n);

@@ -99,6 +99,10 @@ __device__ __forceinline__ void merge_and_add(double (&v)[NV], double *s_red, do
     }
 }
 
+__device__ __forceinline__ long long pillar_count(const VfeParams &q) {
+    return q.M_dev ? min((long long)max(__ldg(q.M_dev), 0), q.M) : q.M;
+}
+
 template <int F, bool ABS, bool DIST>
 __global__ void __launch_bounds__(TR_WARPS * 32) k_vfe_stats(const VfeParams q, double *stats) {
     using D = Deco<F, ABS, DIST>;
@@ -119,7 +123,8 @@ __global__ void __launch_bounds__(TR_WARPS * 32) k_vfe_stats(const VfeParams q, 
 #pragma unroll
     for (int k = 0; k < CIN; ++k) sf[k] = 0.0;
     const long long nwarps = (long long)gridDim.x * TR_WARPS;
-    for (long long m = (long long)blockIdx.x * TR_WARPS + warp; m < q.M; m += nwarps) {
+    const long long M = pillar_count(q);
+    for (long long m = (long long)blockIdx.x * TR_WARPS + warp; m < M; m += nwarps) {
         const PillarHead h = load_pillar<F>(q, m, buf, lane);
         for (int s = 0; s < h.cnt; ++s) {
             float f[CIN];
@@ -226,7 +231,8 @@ __global__ void __launch_bounds__(TR_WARPS * 32) k_vfe_backward(const VfeParams 
 #pragma unroll
     for (int k = 0; k < 2 * CIN; ++k) A[k] = 0.0;
     const long long nwarps = (long long)gridDim.x * TR_WARPS;
-    for (long long m = (long long)blockIdx.x * TR_WARPS + warp; m < q.M; m += nwarps) {
+    const long long M = pillar_count(q);
+    for (long long m = (long long)blockIdx.x * TR_WARPS + warp; m < M; m += nwarps) {
         const PillarHead h = load_pillar<F>(q, m, buf, lane);
         float best_y[2], best_x[2];
         int best_s[2];
@@ -281,11 +287,12 @@ __global__ void __launch_bounds__(TR_WARPS * 32) k_vfe_backward(const VfeParams 
 }
 
 // mode 0: batch statistics (train);  1: running statistics (frozen BN);  2: no BN (Linear with bias)
-__global__ void k_vfe_combine(const double *acc, const double *stats, double n_rows, int C, int CIN, int mode, const float *gamma,
-                              const float *bn_mean, const float *bn_var, float eps, float *grad_weight, float *grad_gamma,
-                              float *grad_beta) {
+__global__ void k_vfe_combine(const double *acc, const double *stats, double n_rows, const int32_t *M_dev, long long cap, int P,
+                              int C, int CIN, int mode, const float *gamma, const float *bn_mean, const float *bn_var, float eps,
+                              float *grad_weight, float *grad_gamma, float *grad_beta) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= C * CIN) return;
+    if (M_dev) n_rows = (double)min((long long)max(__ldg(M_dev), 0), cap) * (double)P;
     const int c = t / CIN, k = t - c * CIN;
     const double A = acc[t], dG = acc[C * CIN + c], dB = acc[C * CIN + C + c];
     double dW;
@@ -309,8 +316,10 @@ __global__ void k_vfe_combine(const double *acc, const double *stats, double n_r
 }
 
 __global__ void __launch_bounds__(256) k_scatter_grad(const float *__restrict__ grad_canvas, const void *coords, int coords_float,
-                                                      long long M, int C, int B, int ny, int nx, float *__restrict__ grad_feats) {
+                                                      long long M, const int32_t *M_dev, int C, int B, int ny, int nx,
+                                                      float *__restrict__ grad_feats, const float *__restrict__ add) {
     const int lane = threadIdx.x & 31;
+    if (M_dev) M = min((long long)max(__ldg(M_dev), 0), M);
     const long long w0 = ((long long)blockIdx.x * 256 + threadIdx.x) >> 5, nw = ((long long)gridDim.x * 256) >> 5;
     for (long long m = w0; m < M; m += nw) {
         int b, y, x;
@@ -321,9 +330,13 @@ __global__ void __launch_bounds__(256) k_scatter_grad(const float *__restrict__ 
             const int4 c = __ldg(reinterpret_cast<const int4 *>(coords) + m);
             b = c.x; y = c.z; x = c.w;
         }
-        const bool ok = b >= 0 && b < B && y >= 0 && y < ny && x >= 0 && x < nx;
+        const bool ok = grad_canvas && b >= 0 && b < B && y >= 0 && y < ny && x >= 0 && x < nx;
         const float *src = grad_canvas + (((size_t)(ok ? b : 0) * C) * ny + (ok ? y : 0)) * nx + (ok ? x : 0);
-        for (int c = lane; c < C; c += 32) grad_feats[(size_t)m * C + c] = ok ? __ldg(src + (size_t)c * ny * nx) : 0.f;
+        for (int c = lane; c < C; c += 32) {
+            float g = ok ? __ldg(src + (size_t)c * ny * nx) : 0.f;
+            if (add) g = __fadd_rn(g, __ldg(add + (size_t)m * C + c));       // a cotangent on pillar_features itself
+            grad_feats[(size_t)m * C + c] = g;
+        }
     }
 }
 
@@ -383,19 +396,19 @@ int launch_vfe_backward(const VfeParams &q, bool abs_xyz, bool dist, const float
         ++nl;
     }
     const int n = q.C * cin;
-    k_vfe_combine<<<(n + 127) / 128, 128, 0, s>>>(acc, stats, (double)q.M * q.P, q.C, cin, mode, q.pfn.bn_w, q.pfn.bn_m, q.pfn.bn_v,
-                                                  q.pfn.eps, grad_weight, grad_gamma, grad_beta);
+    k_vfe_combine<<<(n + 127) / 128, 128, 0, s>>>(acc, stats, (double)q.M * q.P, q.M_dev, q.M, q.P, q.C, cin, mode, q.pfn.bn_w,
+                                                  q.pfn.bn_m, q.pfn.bn_v, q.pfn.eps, grad_weight, grad_gamma, grad_beta);
     ++nl;
     if (launches) *launches = nl;
     return (int)cudaGetLastError();
 }
 
 int launch_scatter_grad(const float *grad_canvas, const void *coords, int coords_float, long long M, int C, int B, int ny, int nx,
-                        float *grad_feats, cudaStream_t s) {
+                        float *grad_feats, cudaStream_t s, const int32_t *M_dev, const float *add) {
     if (M == 0) return HGSF_OK;
     const long long blocks = (M * 32 + 255) / 256;
     k_scatter_grad<<<(unsigned)std::max<long long>(1, std::min<long long>(blocks, 148 * 32)), 256, 0, s>>>(
-        grad_canvas, coords, coords_float, M, C, B, ny, nx, grad_feats);
+        grad_canvas, coords, coords_float, M, M_dev, C, B, ny, nx, grad_feats, add);
     return (int)cudaGetLastError();
 }
 

@@ -15,6 +15,6 @@ int launch_bn_finalize(const double *stats, double n_rows, int C, float momentum
 int launch_vfe_backward(const VfeParams &q, bool abs_xyz, bool dist, const float *grad_out, const double *stats, int mode,
                         double *acc, float *grad_weight, float *grad_gamma, float *grad_beta, cudaStream_t s, int *launches);
 int launch_scatter_grad(const float *grad_canvas, const void *coords, int coords_float, long long M, int C, int B, int ny, int nx,
-                        float *grad_feats, cudaStream_t s);
+                        float *grad_feats, cudaStream_t s, const int32_t *M_dev = nullptr, const float *add = nullptr);
 
 }  // namespace hgsf

@@ -75,6 +75,30 @@ class _ScatterFunction(torch.autograd.Function):
         return None, ctx.path.pointpillar_scatter_backward(grad_canvas.contiguous(), coords, ctx.batch_size), None, None
 
 
+class _FusedTrainFunction(torch.autograd.Function):
+    """Train-mode FusedPillarVFE on the batch statistics: points -> (pillar_features, spatial_features) in three launches,
+    backward in four, no host round trip in either (hgsf_points_to_bev_train / _backward).  Differentiable w.r.t.
+    linear.weight, norm.weight, norm.bias; the points are data."""
+
+    @staticmethod
+    def forward(ctx, path, points, batch_size, weight, gamma, beta, running_mean, running_var, eps, momentum,
+                use_absolute_xyz, with_distance):
+        kw = dict(eps=eps, use_absolute_xyz=use_absolute_xyz, with_distance=with_distance)
+        w, g, b = weight.detach().contiguous(), gamma.detach(), beta.detach()
+        probe = PfnWeights(weight=w, bn_weight=g, bn_bias=b, running_mean=running_mean, running_var=running_var, **kw)
+        res, mean, var = path.points_to_bev_train(points, batch_size, probe, momentum, running_mean, running_var)
+        ctx.path, ctx.res, ctx.batch_size = path, res, batch_size
+        ctx.pfn = PfnWeights(weight=w, bn_weight=g, bn_bias=b, running_mean=mean, running_var=var, **kw)
+        for t in (res.voxel_coords, res.voxel_num_points, res.num_pillars, res.voxels):
+            ctx.mark_non_differentiable(t)
+        return res.pillar_features, res.spatial_features, res.voxel_coords, res.voxel_num_points, res.num_pillars, res.voxels
+
+    @staticmethod
+    def backward(ctx, g_feats, g_canvas, *unused):
+        dW, dg, db = ctx.path.points_to_bev_train_backward(ctx.res, ctx.pfn, ctx.batch_size, g_canvas, g_feats)
+        return None, None, None, dW, dg, db, None, None, None, None, None, None
+
+
 def _pfn_forward(path, layer, voxels, coords, num, use_absolute_xyz, with_distance, training, weight=None):
     """Eval without gradients: the plain native forward.  Otherwise the autograd function (batch statistics in train mode)."""
     weight = layer.linear.weight if weight is None else weight
@@ -330,10 +354,36 @@ class FusedPillarVFE(_VFEBase):
             out.pop('voxels')
         return out
 
+    def _forward_train_fused(self, points, batch_size):
+        """Train mode with BatchNorm inside the fused kernel's domain: three launches from points to the canvas, the batch
+        statistics computed on the way, nothing read back unless TRIM asks for reference-shaped outputs."""
+        path, layer = self._path(), self.pfn_layers[0]
+        n = layer.norm
+        if n.num_batches_tracked is not None:
+            n.num_batches_tracked += 1
+        feats, canvas, coords, num, counts, voxels = _FusedTrainFunction.apply(
+            path, points, batch_size, layer.linear.weight, n.weight, n.bias, n.running_mean, n.running_var, n.eps,
+            n.momentum, self.use_absolute_xyz, self.with_distance)
+        out = dict(voxel_coords=coords, voxel_num_points=num, pillar_features=feats, spatial_features=canvas)
+        if self.return_voxels:
+            out['voxels'] = voxels
+        if self.trim:
+            M = int(counts[0])                       # the one host sync, after everything has been queued
+            for k in ('voxel_coords', 'voxel_num_points', 'pillar_features', 'voxels'):
+                if k in out:
+                    out[k] = out[k][:M]
+        else:
+            out['num_pillars'] = counts
+        return out
+
     def forward(self, batch_dict, **kwargs):
         points = batch_dict['points']
         batch_size = int(batch_dict['batch_size'])
         layer = self.pfn_layers[0]
+        if (self.fused_ok and self.training and layer.use_norm and layer.norm.momentum is not None and
+                layer.norm.track_running_stats and points.is_cuda and self._path().fused_train_supported()):
+            batch_dict.update(self._forward_train_fused(points, batch_size))
+            return batch_dict
         if (not self.fused_ok or (self.training and layer.use_norm) or
                 (torch.is_grad_enabled() and any(p.requires_grad for p in layer.parameters()))):
             # train mode / gradients, or a PFN outside the fused kernel set (stacked, or not 64 channels): the composed native path

@@ -150,7 +150,7 @@ class PillarPath:
         return s, keep
 
     def _run(self, points, batch_size, pfn, xyz_col, batch_col, frame_offsets, want_voxels, want_features,
-             want_canvas, out: PillarResult | None, flip=(False, False)):
+             want_canvas, out: PillarResult | None, flip=(False, False), train=None):
         ps, keep = self._points_struct(points, batch_size, xyz_col, batch_col, frame_offsets, flip)
         dev = points.device
         cap = max(self.capacity(ps.n, batch_size), 1)
@@ -180,6 +180,13 @@ class PillarPath:
                 st = self.lib.hgsf_pillarize(C.byref(self.geom), C.byref(ps), self.P, self.max_voxels,
                                              C.c_void_p(ws_ptr), ws_bytes, C.byref(o), _stream(dev))
                 _lib.check(st, "hgsf_pillarize")
+            elif train is not None:
+                pf = pfn.to_struct()
+                momentum, run_mean, run_var, mean, var, stats = train
+                st = self.lib.hgsf_points_to_bev_train(C.byref(self.geom), C.byref(ps), C.byref(pf), self.P, self.max_voxels,
+                                                       C.c_void_p(ws_ptr), ws_bytes, C.byref(o), float(momentum), _ptr(run_mean),
+                                                       _ptr(run_var), _ptr(mean), _ptr(var), _ptr(stats), _stream(dev))
+                _lib.check(st, "hgsf_points_to_bev_train")
             else:
                 pf = pfn.to_struct()
                 st = self.lib.hgsf_points_to_bev(C.byref(self.geom), C.byref(ps), C.byref(pf), self.P, self.max_voxels,
@@ -208,6 +215,52 @@ class PillarPath:
         """points [n, stride] -> voxel_coords, voxel_num_points, pillar_features, spatial_features, one pass."""
         return self._run(points, batch_size, pfn, xyz_col, batch_col, frame_offsets, want_voxels, want_features,
                          want_canvas, out)
+
+    def fused_train_supported(self) -> bool:
+        """hgsf_points_to_bev_train's domain (besides BatchNorm and 64 channels, which the module checks)."""
+        return self.P <= 32 and self.nz == 1 and self.nx % 4 == 0 and not (self.flags & _lib.POINTS_SPCONV1_BREAK)
+
+    def points_to_bev_train(self, points, batch_size, pfn: PfnWeights, momentum: float, running_mean=None, running_var=None,
+                            xyz_col=1, batch_col=0, frame_offsets=None):
+        """Train-mode forward from points in three launches and no host round trip: BatchNorm1d on the statistics of this
+        batch (pillar_vfe.py:38-40), running statistics updated in place.  Returns (PillarResult with voxels -- all at
+        capacity rows, the count stays in num_pillars on the device --, batch_mean, batch_var)."""
+        dev = points.device
+        Cc = int(pfn.weight.shape[0])
+        mean = torch.empty(Cc, dtype=torch.float32, device=dev)
+        var = torch.empty(Cc, dtype=torch.float32, device=dev)
+        stats = torch.empty(2 * Cc, dtype=torch.float64, device=dev)
+        res = self._run(points, batch_size, pfn, xyz_col, batch_col, frame_offsets, True, True, True, None,
+                        train=(momentum, running_mean, running_var, mean, var, stats))
+        return res, mean, var
+
+    def points_to_bev_train_backward(self, res: PillarResult, pfn: PfnWeights, batch_size, grad_spatial_features=None,
+                                     grad_pillar_features=None):
+        """Gradients (linear.weight, norm.weight, norm.bias) of points_to_bev_train; `pfn` carries the batch statistics the
+        forward returned as bn_mean / bn_var.  Nothing is read back: the pillar count comes from res.num_pillars."""
+        vox = res.voxels
+        dev = vox.device
+        cap, P, F = (int(v) for v in vox.shape)
+        Cc, cin = int(pfn.weight.shape[0]), int(pfn.weight.shape[1])
+        gc = _f32c(grad_spatial_features, "grad_spatial_features") if grad_spatial_features is not None else None
+        gp = _f32c(grad_pillar_features, "grad_pillar_features") if grad_pillar_features is not None else None
+        if gp is not None and tuple(gp.shape) != (cap, Cc):
+            raise ValueError("grad_pillar_features must be [capacity, C]")
+        rows = torch.empty((cap, Cc), dtype=torch.float32, device=dev)
+        stats = torch.empty(int(self.lib.hgsf_train_stats_doubles(Cc, cin)), dtype=torch.float64, device=dev)
+        scratch = torch.empty(int(self.lib.hgsf_train_scratch_doubles(Cc, cin)), dtype=torch.float64, device=dev)
+        dW = torch.empty((Cc, cin), dtype=torch.float32, device=dev)
+        dg = torch.empty(Cc, dtype=torch.float32, device=dev)
+        db = torch.empty(Cc, dtype=torch.float32, device=dev)
+        pf = pfn.to_struct()
+        with torch.cuda.device(dev):
+            st = self.lib.hgsf_points_to_bev_train_backward(
+                C.byref(self.geom), C.byref(pf), _ptr(vox), _ptr(res.voxel_coords), _ptr(res.voxel_num_points), cap,
+                _ptr(res.num_pillars), P, F, int(batch_size), _ptr(gc), _ptr(gp), _ptr(rows), _ptr(stats), _ptr(scratch),
+                _ptr(dW), _ptr(dg), _ptr(db), _stream(dev))
+        _lib.check(st, "hgsf_points_to_bev_train_backward")
+        self.last_launches = int(self.lib.hgsf_last_launch_count())
+        return dW, dg, db
 
     def pillar_vfe(self, voxels, voxel_coords, voxel_num_points, pfn: PfnWeights) -> torch.Tensor:
         """batch_dict contract: voxels [M,P,F], voxel_coords [M,4], voxel_num_points [M] -> pillar_features [M,C].

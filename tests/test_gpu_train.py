@@ -169,3 +169,57 @@ def test_radar7_trains_only_the_selected_columns(cuda):
     pf.square().sum().backward()
     gw = m.pfn_layers[0].linear.weight.grad
     assert gw.shape == m.pfn_layers[0].linear.weight.shape and torch.isfinite(gw).all() and gw.abs().sum() > 0
+
+
+@pytest.mark.parametrize("cfgname,npts,P", [("vod", 1500, 10), ("tj4d", 2500, 32), ("vod", 40000, 5)])
+def test_fused_train_path_three_launches_and_no_readback(cuda, cfgname, npts, P):
+    """Train mode inside the fused kernel's domain: forward = k_front + statistics pass + fused pass (3 launches), backward 4,
+    capacity-sized outputs with the count on the device; same results as the contract-layout train path (pillarize ->
+    batch statistics -> PFN -> scatter) on the same points."""
+    cfg = synthetic.CONFIGS[cfgname]
+    B = 2
+    pts, offs = synthetic.make_batch(cfgname, B, npts, "clustered", seed0=11)
+    F = cfg["F"]
+    w = synthetic.make_pfn(F + 6, 64, seed=5)
+    state = {"pfn_layers.0.linear.weight": torch.from_numpy(w.weight), "pfn_layers.0.norm.weight": torch.from_numpy(w.gamma),
+             "pfn_layers.0.norm.bias": torch.from_numpy(w.beta), "pfn_layers.0.norm.running_mean": torch.from_numpy(w.running_mean),
+             "pfn_layers.0.norm.running_var": torch.from_numpy(w.running_var)}
+
+    def make(trim):
+        mc = SimpleNamespace(USE_NORM=True, WITH_DISTANCE=False, USE_ABSLOTE_XYZ=True, NUM_FILTERS=[64], MAX_POINTS_PER_VOXEL=P,
+                             MAX_NUMBER_OF_VOXELS={'train': 16000, 'test': 40000}, TRIM=trim, RETURN_VOXELS=True)
+        m = modules.FusedPillarVFE(model_cfg=mc, num_point_features=F, voxel_size=list(cfg["voxel_size"]),
+                                   point_cloud_range=np.array(cfg["pc_range"], dtype=np.float32)).to(cuda)
+        m.load_state_dict(state, strict=False)
+        return m.train()
+
+    dpts = torch.from_numpy(pts).to(cuda)
+    fused, ref = make(False), make(True)
+    bd = fused(dict(points=dpts, batch_size=B))
+    assert fused._path().last_launches == 3
+    out_ref = ref._forward_train(dpts, B)                       # the contract-layout chain (trimmed, one sync)
+    counts = bd["num_pillars"].cpu().numpy()
+    M = int(counts[0])
+    assert M == out_ref["pillar_features"].shape[0] and bd["pillar_features"].shape[0] >= M
+    assert torch.equal(bd["voxel_coords"][:M], out_ref["voxel_coords"]) and torch.equal(bd["voxels"][:M], out_ref["voxels"])
+    assert features_close(bd["pillar_features"][:M].detach().cpu().numpy(), out_ref["pillar_features"].detach().cpu().numpy(), rtol=1e-5)
+    assert features_close(bd["spatial_features"].detach().cpu().numpy(), out_ref["spatial_features"].detach().cpu().numpy(), rtol=1e-5)
+    bn_f, bn_r = fused.pfn_layers[0].norm, ref.pfn_layers[0].norm
+    ref.pfn_layers[0].norm.num_batches_tracked += 0
+    assert rel(bn_f.running_mean, bn_r.running_mean.cpu().numpy()) < 2e-6 and rel(bn_f.running_var, bn_r.running_var.cpu().numpy()) < 2e-6
+    assert int(bn_f.num_batches_tracked) == 1
+    rng = np.random.default_rng(1)
+    R = torch.from_numpy(rng.standard_normal((M, 64)).astype(np.float32)).to(cuda)
+    Rc = torch.from_numpy(rng.standard_normal(tuple(bd["spatial_features"].shape)).astype(np.float32)).to(cuda)
+    ((bd["pillar_features"][:M] * R).sum() + (bd["spatial_features"] * Rc).sum()).backward()
+    assert fused._path().last_launches == 4
+    ((out_ref["pillar_features"] * R).sum() + (out_ref["spatial_features"] * Rc).sum()).backward()
+    for a, b in ((fused.pfn_layers[0].linear.weight, ref.pfn_layers[0].linear.weight), (bn_f.weight, bn_r.weight), (bn_f.bias, bn_r.bias)):
+        assert rel(a.grad, b.grad.cpu().numpy()) < 2e-5
+    # only a canvas cotangent (what a detector's loss gives): the pillar_features one is absent
+    fused.zero_grad(); ref.zero_grad()
+    bd = fused(dict(points=dpts, batch_size=B))
+    (bd["spatial_features"] * Rc).sum().backward()
+    out_ref = ref._forward_train(dpts, B)
+    (out_ref["spatial_features"] * Rc).sum().backward()
+    assert rel(fused.pfn_layers[0].linear.weight.grad, ref.pfn_layers[0].linear.weight.grad.cpu().numpy()) < 2e-5
