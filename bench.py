@@ -332,7 +332,7 @@ def main_ours(args):
     barrier()
     ms_dev = sharding.reduce_max(e0.elapsed_time(e1), dev)
 
-    # ---- the same K steps once more with a CUDA event pair around the dominant kernel (k_pillars) on the launch stream: the
+    # ---- the same K steps once more with a CUDA event pair around the dominant kernel (k_emit) on the launch stream: the
     #      roofline leg.  Its step time is reported too (instrumented_ms_per_step) ----
     lib.hgsf_emit_timing_begin(min(args.steps, 1024))
     barrier()
@@ -440,8 +440,8 @@ def main_ours(args):
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
     else:
         peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md); MEASURED_PEAKS.json absent"
-    dominant_kernel = ("k_pillars (per run of canvas tiles: order + decorate + PFN + max of the tiles' pillars, pillar rows, and the tiles "
-                       "themselves with coalesced 16-byte stores, zeros included)")
+    dominant_kernel = ("k_emit (per canvas tile of 32 cells x 64 channels: order + decorate + PFN + max of the tile's pillars, pillar "
+                       "rows, and the tile itself in one TMA tensor store, zero tiles included)")
     traffic, traffic_src = None, None
     tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tp):
@@ -464,7 +464,7 @@ def main_ours(args):
                 step_achieved=alg / (step_ms * 1e-3) / 1e9, step_frac=alg / (step_ms * 1e-3) / 1e9 / peak,
                 note="achieved = SURVEY 8(d) algorithmic bytes of one batch / mean duration of the dominant kernel (CUDA event pairs on the "
                      "launch stream, in a second pass over the same K steps: instrumented_ms_per_step); step_* = the same bytes / the "
-                     "whole-step time of the un-instrumented timed region (k_front + k_pillars)")
+                     "whole-step time of the un-instrumented timed region (k_front + k_emit)")
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=warm,
                 ms_per_step=step_ms, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
                 data="synthetic", impl="ours",

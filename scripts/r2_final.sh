@@ -12,3 +12,4 @@ python bench.py --impl reference --steps 50 --warmup 3 > gpurun_out/r02_bench_re
 python scripts/prof_step.py vod clustered 16 30000 8 > /dev/null 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/r02_launches_vod_clustered.csv python scripts/prof_step.py vod clustered 16 30000 8 > /dev/null 2>&1
 # ncu --set full captures: scripts/r2_ncu.sh <tag> <config> <mode> <B> <n>, two per gpurun call (the reports are ~15 MB each and
 # gpurun_out/ brings back 64 MiB at most)
+python scripts/bench_train.py vod clustered 16 30000 > gpurun_out/r02_train_step_vod_clustered.json 2>> gpurun_out/b.err; cat gpurun_out/r02_train_step_vod_clustered.json
