@@ -450,9 +450,12 @@ def main_ours(args):
         traffic_src = dict(kind="ncu capture committed under profiles/ (NOT measured in this run)", source=ent.get("source"),
                            commit=ent.get("commit"))
         try:
-            head = subprocess.run(["git", "rev-parse", "--short", "HEAD"], cwd=ROOT, capture_output=True, text=True).stdout.strip()
-            if head and ent.get("commit") and not head.startswith(ent["commit"][:7]):
-                traffic_src["warning"] = f"captured at {ent['commit']}, HEAD is {head}"
+            # stale = the kernels changed since the capture (docs / scripts moving HEAD do not count); no .git on the GPU box: no check
+            if ent.get("commit"):
+                r = subprocess.run(["git", "diff", "--quiet", ent["commit"], "HEAD", "--", "hgsfusion_b200/csrc", "include"],
+                                   cwd=ROOT, capture_output=True, text=True)
+                if r.returncode == 1:
+                    traffic_src["warning"] = f"kernel sources changed since the capture at {ent['commit']}"
         except OSError:
             pass
     step_ms = ms_dev / args.steps
