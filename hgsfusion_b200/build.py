@@ -20,7 +20,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 
 def _newest_source() -> float:
     files = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
-    files.append(os.path.join(os.path.dirname(HERE), "include", "hgsfusion_b200.h"))
+    files += [os.path.join(os.path.dirname(HERE), "include", h) for h in ("hgsfusion_b200.h", "hgsfusion_b200_debug.h")]
     return max(os.path.getmtime(f) for f in files)
 
 

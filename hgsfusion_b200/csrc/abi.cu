@@ -1,5 +1,6 @@
 // abi.cu -- the extern "C" surface declared in include/hgsfusion_b200.h.
 // Validation, parameter packing, workspace carving; no allocation, no host synchronisation.
+#include "../../include/hgsfusion_b200_debug.h"
 #include "contract_ops.cuh"
 #include "hybrid_points.cuh"
 #include "pillar_path.cuh"

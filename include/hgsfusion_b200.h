@@ -171,13 +171,7 @@ HGSF_API int hgsf_pointpillar_scatter(const hgsf_geometry *geom, const float *pi
 /* Number of kernels (memsets excluded) the last call on this host thread enqueued (bench.py's gpu_launches). */
 HGSF_API int hgsf_last_launch_count(void);
 
-/* Measurement hook (off by default): after hgsf_emit_timing_begin(capacity > 0), every hgsf_points_to_bev /
- * hgsf_pillarize call made by this host thread records a CUDA event pair on its stream around the launch of
- * the path's dominant kernel (k_emit), up to `capacity` calls.  hgsf_emit_timing_collect synchronises those
- * events, writes the per-launch durations (ms) and returns how many (<0: -cudaError_t), and rearms the ring.
- * hgsf_emit_timing_begin(0) switches it off.  These two are the only entry points that synchronise. */
-HGSF_API int hgsf_emit_timing_begin(int capacity);
-HGSF_API int hgsf_emit_timing_collect(float *ms, int n);
+/* (Measurement hooks that synchronise -- bench.py's roofline leg -- live in hgsfusion_b200_debug.h, not in the product ABI.) */
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Path B -- the PillarNet reader the shipped HGSFusion YAMLs run.  These replace the reference's pybind module
