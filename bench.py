@@ -50,11 +50,21 @@ def parse():
 
 
 def workload(args):
+    """The `config` object of BOTH arms (ours and --impl reference): everything in it follows from the arguments, so the two
+    lines carry the same dictionary.  `l2` / `parallelism` describe the GPU arm's timed region."""
     cfg = synthetic.CONFIGS[args.config]
+    rng, vs = cfg["pc_range"], cfg["voxel_size"]
+    nx, ny = int(round((rng[3] - rng[0]) / vs[0])), int(round((rng[4] - rng[1]) / vs[1]))
+    ring = max(1, args.ring)
+    in_mb = ring * args.batch * args.points * (1 + cfg["F"]) * 4 / 1e6
+    canvas_mb = args.batch * 64 * ny * nx * 4 / 1e6
     return dict(workload=f"{args.config}_{args.mode}_b{args.batch}_n{args.points}", dataset_shape=args.config,
                 points_per_frame=args.points, point_features=cfg["F"], frames_per_gpu_per_step=args.batch,
                 max_points_per_voxel=args.max_points, max_voxels=args.max_voxels, channels=64,
-                pc_range=cfg["pc_range"], voxel_size=cfg["voxel_size"], point_distribution=args.mode)
+                pc_range=cfg["pc_range"], voxel_size=cfg["voxel_size"], point_distribution=args.mode, grid=[nx, ny, 1],
+                l2=f"ring of {ring} distinct input batches ({in_mb:.0f} MB) and a {canvas_mb:.0f} MB canvas rewritten every step, "
+                   f"both > 126 MB L2",
+                parallelism=f"frames sharded by rank, {args.batch} per GPU, no collective")
 
 
 def alg_bytes_per_frame(n, F, C, ny, nx, M):
@@ -471,10 +481,7 @@ def main_ours(args):
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=warm,
                 ms_per_step=step_ms, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
                 data="synthetic", impl="ours",
-                config=dict(workload(args), pillars_per_frame=M / B, grid=[nx, ny, 1],
-                            l2=f"ring of {ring} distinct input batches ({ring * host[0].nbytes / 1e6:.0f} MB) and a "
-                               f"{res.spatial_features.numel() * 4 / 1e6:.0f} MB canvas rewritten every step, both > 126 MB L2",
-                            parallelism=f"frames sharded by rank, {B} per GPU, no collective"),
+                config=workload(args), pillars_per_frame=M / B,
                 e2e=dict(value=frames * e2e_steps / (ms_e2e * 1e-3), unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                          steps=e2e_steps, h2d_gbs_per_rank=h2d_gbs_rank,
                          note="pinned host points [sum N, F] + frame_offsets -> H2D -> hgsf_points_to_bev -> D2H pillar counts; the canvas "
