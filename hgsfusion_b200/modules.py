@@ -89,12 +89,15 @@ class _FusedTrainFunction(torch.autograd.Function):
         res, mean, var = path.points_to_bev_train(points, batch_size, probe, momentum, running_mean, running_var)
         ctx.path, ctx.res, ctx.batch_size = path, res, batch_size
         ctx.pfn = PfnWeights(weight=w, bn_weight=g, bn_bias=b, running_mean=mean, running_var=var, **kw)
+        ctx.set_materialize_grads(False)             # an unused output's cotangent stays None (no capacity-sized zero fill)
         for t in (res.voxel_coords, res.voxel_num_points, res.num_pillars, res.voxels):
             ctx.mark_non_differentiable(t)
         return res.pillar_features, res.spatial_features, res.voxel_coords, res.voxel_num_points, res.num_pillars, res.voxels
 
     @staticmethod
     def backward(ctx, g_feats, g_canvas, *unused):
+        if g_feats is None and g_canvas is None:
+            return (None,) * 12
         dW, dg, db = ctx.path.points_to_bev_train_backward(ctx.res, ctx.pfn, ctx.batch_size, g_canvas, g_feats)
         return None, None, None, dW, dg, db, None, None, None, None, None, None
 

@@ -20,30 +20,52 @@ m = modules.FusedPillarVFE(model_cfg=mc, num_point_features=cfg["F"], voxel_size
 Rc = None
 
 
-def run(fused, what):
-    """what: 'fwd' = the module's train-mode forward; 'bwd' = autograd.backward of the canvas with a ready cotangent (no loss
-    kernels in the timed region); the forward of 'bwd' runs outside the events."""
+def run(fused):
+    """GPU time of the forward and of the backward with the launches already queued (a spin kernel in front keeps the GPU busy
+    while the host enqueues), and the host time of the same calls with the GPU idle."""
     global Rc
-    K = 30
-    e = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    import time
+    K = 20
+    gf = gb = hf = hb = 0.0
+    ev = lambda: torch.cuda.Event(enable_timing=True)
     for i in range(-5, K):
         m.zero_grad(set_to_none=True)
-        if what == 'fwd' and i >= 0: e[i][0].record()
+        torch.cuda.synchronize()
+        e0, e1, e2, e3 = ev(), ev(), ev(), ev()
+        torch.cuda._sleep(6_000_000)                      # ~3 ms: the host runs ahead
+        e0.record()
         out = m._forward_train_fused(d, B) if fused else m._forward_train(d, B)
-        if what == 'fwd' and i >= 0: e[i][1].record()
+        e1.record()
+        torch.cuda.synchronize()
         if Rc is None:
             Rc = torch.randn_like(out['spatial_features'])
-        if what == 'bwd' and i >= 0: e[i][0].record()
+        torch.cuda._sleep(6_000_000)
+        e2.record()
         torch.autograd.backward([out['spatial_features']], [Rc])
-        if what == 'bwd' and i >= 0: e[i][1].record()
-    torch.cuda.synchronize()
-    return round(sum(a.elapsed_time(b) for a, b in e) / K, 4)
+        e3.record()
+        torch.cuda.synchronize()
+        # host time, GPU idle
+        m.zero_grad(set_to_none=True)
+        t0 = time.perf_counter()
+        out = m._forward_train_fused(d, B) if fused else m._forward_train(d, B)
+        t1 = time.perf_counter()
+        torch.cuda.synchronize()
+        t2 = time.perf_counter()
+        torch.autograd.backward([out['spatial_features']], [Rc])
+        t3 = time.perf_counter()
+        torch.cuda.synchronize()
+        if i >= 0:
+            gf += e0.elapsed_time(e1); gb += e2.elapsed_time(e3); hf += (t1 - t0) * 1e3; hb += (t3 - t2) * 1e3
+    return dict(forward_gpu_ms=round(gf / K, 4), backward_gpu_ms=round(gb / K, 4), forward_host_ms=round(hf / K, 4),
+                backward_host_ms=round(hb / K, 4))
 
 
 res = {"workload": f"{cfgname}_{mode}_b{B}_n{n}"}
 for name, fused in (("fused_train", True), ("contract_chain", False)):
-    res[name] = dict(forward_ms=run(fused, 'fwd'), backward_ms=run(fused, 'bwd'))
+    res[name] = run(fused)
 res["note"] = ("train-mode FusedPillarVFE, TRIM False; forward = points -> canvas on batch statistics (fused: 3 launches, no read-back; "
                "contract chain: pillarize -> trim (host sync) -> batch statistics -> PFN -> scatter); backward = canvas cotangent -> "
-               "grads of linear.weight / norm.weight / norm.bias; torch autograd dispatch included, no loss kernels")
+               "grads of linear.weight / norm.weight / norm.bias, no loss kernels; *_gpu_ms = device time with the launches queued behind a "
+               "spin kernel (the contract chain's forward contains a host sync, so its figure includes that round trip); *_host_ms = time "
+               "of the Python call with the GPU idle")
 print(json.dumps(res))
