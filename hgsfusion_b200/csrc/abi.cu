@@ -334,7 +334,8 @@ int hgsf_pillarnet_reader(const float *xyz, const float *pt_features, int32_t Cf
 }
 
 // ---- training (train_ops.cu) ------------------------------------------------------------------------------------------
-int64_t hgsf_train_stats_doubles(int32_t C, int32_t cin) { return (C > 0 && cin > 0) ? (int64_t)train_stats_len(C, cin) : 0; }
+// the statistics layout of train_ops.cu + the second-moment scratch of hgsf_points_to_bev_train behind it (16 rows of cin)
+int64_t hgsf_train_stats_doubles(int32_t C, int32_t cin) { return (C > 0 && cin > 0) ? (int64_t)(train_stats_len(C, cin) + 16 * (size_t)cin) : 0; }
 int64_t hgsf_train_scratch_doubles(int32_t C, int32_t cin) { return (C > 0 && cin > 0) ? (int64_t)train_acc_len(C, cin) : 0; }
 
 static int vfe_params(const hgsf_geometry *g, const hgsf_pfn *pfn, const float *voxels, const void *coords, const void *num,
@@ -412,7 +413,7 @@ int hgsf_points_to_bev_train(const hgsf_geometry *g, const hgsf_points *pt, cons
     bool abs_xyz = true, dist = false;
     const int st = path_params(g, pt, &train, P, max_voxels, ws, ws_bytes, out, p, abs_xyz, dist);
     if (st != HGSF_OK) return st;
-    p.stats = stats; p.batch_mean = batch_mean; p.batch_var = batch_var; p.run_mean = running_mean; p.run_var = running_var;
+    p.stats = stats; p.stats_S = stats + train_stats_len(p.C, p.Cin); p.batch_mean = batch_mean; p.batch_var = batch_var; p.run_mean = running_mean; p.run_var = running_var;
     p.momentum = momentum;
     return launch_pillar_path_train(p, abs_xyz, dist, static_cast<cudaStream_t>(stream), &g_last_launches);
 }
@@ -420,7 +421,7 @@ int hgsf_points_to_bev_train(const hgsf_geometry *g, const hgsf_points *pt, cons
 int hgsf_points_to_bev_train_backward(const hgsf_geometry *g, const hgsf_pfn *pfn, const float *voxels, const int32_t *coords,
                                       const int32_t *num, int64_t capacity, const int32_t *num_pillars, int32_t P, int32_t F,
                                       int32_t B, const float *grad_canvas, const float *grad_feats_in, float *grad_rows,
-                                      double *stats, double *scratch, float *grad_weight, float *grad_bn_weight,
+                                      const double *stats, double *scratch, float *grad_weight, float *grad_bn_weight,
                                       float *grad_bn_bias, hgsf_stream_t stream) {
     g_last_launches = 0;
     VfeParams q;
@@ -437,11 +438,9 @@ int hgsf_points_to_bev_train_backward(const hgsf_geometry *g, const hgsf_pfn *pf
     st = launch_scatter_grad(grad_canvas, coords, 0, capacity, q.C, B, g->grid[1], g->grid[0], grad_rows, s, num_pillars,
                              grad_feats_in);
     if (st != HGSF_OK) return st;
-    st = launch_vfe_stats(q, abs_xyz, dist, stats, s);
-    if (st != HGSF_OK) return st;
     int nl = 0;
     st = launch_vfe_backward(q, abs_xyz, dist, grad_rows, stats, 0, scratch, grad_weight, grad_bn_weight, grad_bn_bias, s, &nl);
-    if (st == HGSF_OK) g_last_launches = 2 + nl;
+    if (st == HGSF_OK) g_last_launches = 1 + nl;
     return st;
 }
 

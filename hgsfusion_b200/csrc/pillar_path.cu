@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(FRONT_THREADS, 4) k_front(const PathParams p) 
     const bool clean = (ld_volatile_u64(p.state) == p.magic);        // grid-uniform: nobody writes p.state before the first barrier
     if (cta == 0 && tid == 0) { p.ticket[0] = 0u; p.ticket[32] = 0u; p.ticket[64] = 0u; p.ticket[16] = 0u; p.ticket[48] = 0u; }   // run ticket, heavy-tile
                                                           // count, finished CTAs; tickets / finished CTAs of the statistics pass
-    if (p.stats && cta == 0 && tid < 128) p.stats[tid] = 0.0;
+    if (p.stats && cta == 0 && tid < 16 * p.Cin) p.stats_S[tid] = 0.0;      // 16 * Cin <= 240 < FRONT_THREADS
     if ((p.flags & HGSF_POINTS_SPCONV1_BREAK) && cta == 0) for (int b = tid; b < p.B; b += FRONT_THREADS) p.cutoff[b] = INT_MAX;
     if (!clean) {
         uint4 *t4 = reinterpret_cast<uint4 *>(p.cell_tag);           // tag, cnt: two arrays back to back
@@ -1247,14 +1247,18 @@ constexpr int STAGE_W = HGSF_EMIT_STAGE;           // staged point rows per tile
 #define HGSF_EMIT_MINB 3
 #endif
 // STATS: the train-mode statistics pass (BatchNorm1d on batch statistics, pillar_vfe.py:29-42): the same walk over the same
-// tiles with the same arithmetic up to the Linear output x, which is summed per channel (Sx, Sxx in fp64) instead of being
-// normalised and max-reduced; nothing is written but p.stats, the table is left as it is for the real pass that follows, and the
-// last CTA turns the sums into batch_mean / batch_var and updates the running statistics.
+// tiles with the same decoration, but instead of Linear + BN + max it accumulates the SECOND MOMENTS of the decorated features
+// over every kept point, S = sum f f^T [Cin, Cin] and s = sum f [Cin] in fp64 (lane r of a half-warp owns row r of S, the lane
+// after the last row owns s).  Everything BatchNorm's forward and backward need follows from them, because x = W f is linear:
+// sum x_c = w_c . s,  sum x_c^2 = w_c^T S w_c,  T[c,k] = sum x_c f_k = (W S)[c,k].  Nothing is written but p.stats_S, the table
+// is left as it is for the real pass that follows, and the last CTA expands S, s into the train_ops.cu statistics layout
+// (Sx, Sxx, T, s: the backward reads it as it is), batch_mean / batch_var, and updates the running statistics.
 template <int F, bool ABS, bool DIST, bool BN, int CHUNK, bool STATS>
 __global__ void __launch_bounds__(EMIT_THREADS, HGSF_EMIT_MINB)
 k_emit(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap zmap, const PathParams p) {
     constexpr int C = 64;
     constexpr int CIN = (ABS ? F : F - 3) + 6 + (DIST ? 1 : 0);
+    static_assert(CIN <= 15, "STATS: rows of S on lanes 0..CIN-1 of a half-warp, s on lane CIN");
     constexpr int RWc = (F + 1 + 3) / 4 * 4;   // F features + the point index, padded to float4
     constexpr int NV = RWc / 4;
     constexpr int TILE = C * 32;
@@ -1355,7 +1359,10 @@ k_emit(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtenso
     // one point through decorate + Linear + BN, folded into the running max (integer max on the float bits: exact for
     // the non-negative post-ReLU values, drops negatives and -0 = the ReLU, lets a NaN 0x7fffffff win as torch.max does)
     float *const feats_out = STATS ? nullptr : p.feats, *const voxels_out = STATS ? nullptr : p.voxels;
-    double st_x[4] = {0.0, 0.0, 0.0, 0.0}, st_xx[4] = {0.0, 0.0, 0.0, 0.0};      // STATS: this lane's sums of x and x^2, channels c0..c0+3
+    double st_S[STATS ? CIN : 1];                    // STATS: row (lane & 15) of S = sum f f^T; the lane after the last row: s = sum f
+#pragma unroll
+    for (int k = 0; k < (STATS ? CIN : 1); ++k) st_S[k] = 0.0;
+    const int st_role = lane & 15;
     auto eval_row = [&](const float (&row)[RWc], float mx, float my, float mz, float cx, float cy,
                         int &v0, int &v1, int &v2, int &v3, bool counted = true) {
         float feat[CIN];
@@ -1368,21 +1375,23 @@ k_emit(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtenso
             // torch.norm(xyz, 2, 2) on the CPU: sqrt(fma(z,z, fma(y,y, x*x)))  (pillar_vfe.py:110-112)
             if (DIST) feat[kf++] = __fsqrt_rn(fmaf(row[2], row[2], fmaf(row[1], row[1], __fmul_rn(row[0], row[0]))));
         }
+        if (STATS) {                           // a row evaluated twice to fill a pair (below) counts once
+            if (counted) {
+                float fr = 1.f;                // the s lane multiplies by one
+#pragma unroll
+                for (int kk = 0; kk < CIN; ++kk) if (kk == st_role) fr = feat[kk];
+                const double dr = (double)fr;
+#pragma unroll
+                for (int kk = 0; kk < CIN; ++kk) st_S[kk] = fma(dr, (double)feat[kk], st_S[kk]);
+            }
+            return;
+        }
         uint64_t a01 = 0ull, a23 = 0ull;       // (+0, +0)
 #pragma unroll
         for (int kk = 0; kk < CIN; ++kk) {     // Linear: sequential FMA in k order (pillar_vfe.py:37), two channels per FFMA2
             const uint64_t ff = pack_f2(feat[kk], feat[kk]);
             a01 = fma2_rn(ff, w01[kk], a01);
             a23 = fma2_rn(ff, w23[kk], a23);
-        }
-        if (STATS) {                           // a row evaluated twice to fill a pair (below) counts once
-            float x0, x1, x2, x3;
-            unpack_f2(a01, x0, x1); unpack_f2(a23, x2, x3);
-            if (counted) {
-                st_x[0] += (double)x0; st_xx[0] += (double)x0 * (double)x0; st_x[1] += (double)x1; st_xx[1] += (double)x1 * (double)x1;
-                st_x[2] += (double)x2; st_xx[2] += (double)x2 * (double)x2; st_x[3] += (double)x3; st_xx[3] += (double)x3 * (double)x3;
-            }
-            return;
         }
         float y0, y1, y2, y3;
         if (BN) {                              // BN eval: (((x-mean)*invstd)*gamma)+beta, 4 roundings (:39); the last add scalar (common.cuh)
@@ -1803,46 +1812,67 @@ k_emit(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtenso
     }
     cp_async_wait<0>();
     if (STATS) {
-        // lanes l and l + 16 hold the same four channels; then the warps of the CTA, then one fp64 atomic per channel and sum
+        // lanes l and l + 16 hold the same row; then the warps of the CTA, then one fp64 atomic per entry
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { st_x[i] += __shfl_xor_sync(FULL, st_x[i], 16); st_xx[i] += __shfl_xor_sync(FULL, st_xx[i], 16); }
+        for (int k = 0; k < CIN; ++k) st_S[k] += __shfl_xor_sync(FULL, st_S[k], 16);
         __syncthreads();                                  // every warp is done with its tile buffer: reused for the reduction
-        double *red = reinterpret_cast<double *>(tiles);  // [EMIT_WARPS][2][C]
+        double *red = reinterpret_cast<double *>(tiles);  // [EMIT_WARPS][16][CIN]
         if (lane < 16) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) { red[(warp * 2 + 0) * C + c0 + i] = st_x[i]; red[(warp * 2 + 1) * C + c0 + i] = st_xx[i]; }
+            for (int k = 0; k < CIN; ++k) red[(warp * 16 + lane) * CIN + k] = (lane <= CIN) ? st_S[k] : 0.0;
         }
         __syncthreads();
-        for (int t = tid; t < 2 * C; t += NT) {
+        for (int t = tid; t < 16 * CIN; t += NT) {
             double acc = 0.0;
-            for (int w = 0; w < EMIT_WARPS; ++w) acc += red[w * 2 * C + t];
-            if (acc != 0.0) atomicAdd(p.stats + t, acc);
+            for (int w = 0; w < EMIT_WARPS; ++w) acc += red[w * 16 * CIN + t];
+            if (acc != 0.0) atomicAdd(p.stats_S + t, acc);
         }
-        // the last CTA to get here turns the sums into the batch statistics (train_ops.cu k_bn_finalize, same arithmetic):
-        // N = M * P rows per channel, the zero-padded rows included (they add nothing to the sums)
+        // the last CTA to get here expands the moments: N = M * P rows per channel, the zero-padded rows included (they add
+        // nothing to the sums); then train_ops.cu k_bn_finalize's arithmetic
         __shared__ int s_last;
         __threadfence();
         __syncthreads();
         if (tid == 0) s_last = (atomicAdd(p.ticket + 48, 1u) == gridDim.x - 1u) ? 1 : 0;
         __syncthreads();
-        if (s_last && tid < C) {
+        if (s_last) {
             __threadfence();
-            const double n_rows = (double)s_K[p.B] * (double)p.P;
-            if (n_rows > 0.0) {
-                const double mean = __ldcg(p.stats + tid) / n_rows;
-                double var = __ldcg(p.stats + C + tid) / n_rows - mean * mean;
-                if (var < 0.0) var = 0.0;
-                p.batch_mean[tid] = (float)mean;
-                p.batch_var[tid] = (float)var;
-                if (p.run_mean) p.run_mean[tid] = (float)((1.0 - (double)p.momentum) * (double)p.run_mean[tid] + (double)p.momentum * mean);
-                if (p.run_var) {
-                    const double unbiased = n_rows > 1.0 ? var * n_rows / (n_rows - 1.0) : var;
-                    p.run_var[tid] = (float)((1.0 - (double)p.momentum) * (double)p.run_var[tid] + (double)p.momentum * unbiased);
+            double *Sm = red;                             // S rows 0..CIN-1, then s
+            for (int t = tid; t < (CIN + 1) * CIN; t += NT) Sm[t] = __ldcg(p.stats_S + t);
+            __syncthreads();
+            if (tid < C) {
+                double w[CIN];
+#pragma unroll
+                for (int k = 0; k < CIN; ++k) w[k] = (double)__ldg(p.W + tid * CIN + k);
+                double sx = 0.0, sxx = 0.0;
+#pragma unroll
+                for (int k = 0; k < CIN; ++k) {
+                    double tk = 0.0;                      // T[c,k] = sum_a W[c,a] S[a,k]
+#pragma unroll
+                    for (int a2 = 0; a2 < CIN; ++a2) tk = fma(w[a2], Sm[a2 * CIN + k], tk);
+                    p.stats[2 * C + tid * CIN + k] = tk;
+                    sxx = fma(tk, w[k], sxx);             // w^T S w
+                    sx = fma(w[k], Sm[CIN * CIN + k], sx);
                 }
-            } else {                                      // no pillar at all: nothing to normalise, running statistics untouched
-                p.batch_mean[tid] = 0.f;
-                p.batch_var[tid] = 1.f;
+                p.stats[tid] = sx;
+                p.stats[C + tid] = sxx;
+                const double n_rows = (double)s_K[p.B] * (double)p.P;
+                if (n_rows > 0.0) {
+                    const double mean = sx / n_rows;
+                    double var = sxx / n_rows - mean * mean;
+                    if (var < 0.0) var = 0.0;
+                    p.batch_mean[tid] = (float)mean;
+                    p.batch_var[tid] = (float)var;
+                    if (p.run_mean) p.run_mean[tid] = (float)((1.0 - (double)p.momentum) * (double)p.run_mean[tid] + (double)p.momentum * mean);
+                    if (p.run_var) {
+                        const double unbiased = n_rows > 1.0 ? var * n_rows / (n_rows - 1.0) : var;
+                        p.run_var[tid] = (float)((1.0 - (double)p.momentum) * (double)p.run_var[tid] + (double)p.momentum * unbiased);
+                    }
+                } else {                                  // no pillar at all: nothing to normalise, running statistics untouched
+                    p.batch_mean[tid] = 0.f;
+                    p.batch_var[tid] = 1.f;
+                }
             }
+            if (tid < CIN) p.stats[2 * C + C * CIN + tid] = Sm[CIN * CIN + tid];      // s
         }
         return;
     }

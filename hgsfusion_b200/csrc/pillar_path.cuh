@@ -72,7 +72,8 @@ struct PathParams {
     float eps;
     int Cin, C;
     // ---- train mode (launch_pillar_path_train): BatchNorm1d on the statistics of the batch ----
-    double *stats;                     // [2*64] per-channel sums of the Linear output x and of x^2 over every kept point (zeroed by k_front)
+    double *stats;                     // out: train_ops.cu's statistics layout (Sx [C], Sxx [C], T [C][Cin], s [Cin]), read by the backward
+    double *stats_S;                   // [16 * Cin] scratch behind it: second moments S = sum f f^T and s = sum f (zeroed by k_front)
     float *batch_mean, *batch_var;     // [64] out: what the forward normalises with (biased variance)
     float *run_mean, *run_var;         // [64] updated in place as torch.nn.BatchNorm1d does (may be null)
     float momentum;

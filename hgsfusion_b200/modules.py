@@ -19,6 +19,8 @@ There is no PyTorch fallback: without the CUDA library these modules raise at co
 """
 from __future__ import annotations
 
+from types import SimpleNamespace
+
 import numpy as np
 import torch
 import torch.nn as nn
@@ -77,7 +79,7 @@ class _ScatterFunction(torch.autograd.Function):
 
 class _FusedTrainFunction(torch.autograd.Function):
     """Train-mode FusedPillarVFE on the batch statistics: points -> (pillar_features, spatial_features) in three launches,
-    backward in four, no host round trip in either (hgsf_points_to_bev_train / _backward).  Differentiable w.r.t.
+    backward in three, no host round trip in either (hgsf_points_to_bev_train / _backward).  Differentiable w.r.t.
     linear.weight, norm.weight, norm.bias; the points are data."""
 
     @staticmethod
@@ -86,9 +88,12 @@ class _FusedTrainFunction(torch.autograd.Function):
         kw = dict(eps=eps, use_absolute_xyz=use_absolute_xyz, with_distance=with_distance)
         w, g, b = weight.detach().contiguous(), gamma.detach(), beta.detach()
         probe = PfnWeights(weight=w, bn_weight=g, bn_bias=b, running_mean=running_mean, running_var=running_var, **kw)
-        res, mean, var = path.points_to_bev_train(points, batch_size, probe, momentum, running_mean, running_var)
-        ctx.path, ctx.res, ctx.batch_size = path, res, batch_size
+        res, mean, var, stats = path.points_to_bev_train(points, batch_size, probe, momentum, running_mean, running_var)
+        ctx.path, ctx.batch_size = path, batch_size
         ctx.pfn = PfnWeights(weight=w, bn_weight=g, bn_bias=b, running_mean=mean, running_var=var, **kw)
+        # only what the backward reads, and through save_for_backward: keeping `res` itself on ctx would tie the differentiable
+        # outputs to their own grad_fn (a reference cycle: every step's 1 GB of outputs would wait for the cyclic GC)
+        ctx.save_for_backward(res.voxels, res.voxel_coords, res.voxel_num_points, res.num_pillars, stats)
         ctx.set_materialize_grads(False)             # an unused output's cotangent stays None (no capacity-sized zero fill)
         for t in (res.voxel_coords, res.voxel_num_points, res.num_pillars, res.voxels):
             ctx.mark_non_differentiable(t)
@@ -98,7 +103,9 @@ class _FusedTrainFunction(torch.autograd.Function):
     def backward(ctx, g_feats, g_canvas, *unused):
         if g_feats is None and g_canvas is None:
             return (None,) * 12
-        dW, dg, db = ctx.path.points_to_bev_train_backward(ctx.res, ctx.pfn, ctx.batch_size, g_canvas, g_feats)
+        voxels, coords, num, counts, stats = ctx.saved_tensors
+        res = SimpleNamespace(voxels=voxels, voxel_coords=coords, voxel_num_points=num, num_pillars=counts)
+        dW, dg, db = ctx.path.points_to_bev_train_backward(res, ctx.pfn, stats, ctx.batch_size, g_canvas, g_feats)
         return None, None, None, dW, dg, db, None, None, None, None, None, None
 
 

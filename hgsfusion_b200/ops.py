@@ -224,20 +224,20 @@ class PillarPath:
                             xyz_col=1, batch_col=0, frame_offsets=None):
         """Train-mode forward from points in three launches and no host round trip: BatchNorm1d on the statistics of this
         batch (pillar_vfe.py:38-40), running statistics updated in place.  Returns (PillarResult with voxels -- all at
-        capacity rows, the count stays in num_pillars on the device --, batch_mean, batch_var)."""
+        capacity rows, the count stays in num_pillars on the device --, batch_mean, batch_var, stats for the backward)."""
         dev = points.device
         Cc = int(pfn.weight.shape[0])
         mean = torch.empty(Cc, dtype=torch.float32, device=dev)
         var = torch.empty(Cc, dtype=torch.float32, device=dev)
-        stats = torch.empty(2 * Cc, dtype=torch.float64, device=dev)
+        stats = torch.empty(int(self.lib.hgsf_train_stats_doubles(Cc, int(pfn.weight.shape[1]))), dtype=torch.float64, device=dev)
         res = self._run(points, batch_size, pfn, xyz_col, batch_col, frame_offsets, True, True, True, None,
                         train=(momentum, running_mean, running_var, mean, var, stats))
-        return res, mean, var
+        return res, mean, var, stats
 
-    def points_to_bev_train_backward(self, res: PillarResult, pfn: PfnWeights, batch_size, grad_spatial_features=None,
+    def points_to_bev_train_backward(self, res: PillarResult, pfn: PfnWeights, stats, batch_size, grad_spatial_features=None,
                                      grad_pillar_features=None):
         """Gradients (linear.weight, norm.weight, norm.bias) of points_to_bev_train; `pfn` carries the batch statistics the
-        forward returned as bn_mean / bn_var.  Nothing is read back: the pillar count comes from res.num_pillars."""
+        forward returned as bn_mean / bn_var, `stats` its statistics buffer.  Nothing is read back: the pillar count comes from res.num_pillars."""
         vox = res.voxels
         dev = vox.device
         cap, P, F = (int(v) for v in vox.shape)
@@ -247,7 +247,6 @@ class PillarPath:
         if gp is not None and tuple(gp.shape) != (cap, Cc):
             raise ValueError("grad_pillar_features must be [capacity, C]")
         rows = torch.empty((cap, Cc), dtype=torch.float32, device=dev)
-        stats = torch.empty(int(self.lib.hgsf_train_stats_doubles(Cc, cin)), dtype=torch.float64, device=dev)
         scratch = torch.empty(int(self.lib.hgsf_train_scratch_doubles(Cc, cin)), dtype=torch.float64, device=dev)
         dW = torch.empty((Cc, cin), dtype=torch.float32, device=dev)
         dg = torch.empty(Cc, dtype=torch.float32, device=dev)

@@ -288,18 +288,19 @@ HGSF_API int hgsf_pillar_vfe_backward(const hgsf_geometry *geom, const hgsf_pfn 
 /* Train mode from points, without the contract tensors in between and without a host round trip (replaces the reference's
  * train-mode chain data_processor.py:140-178 -> pillar_vfe.py:29-49,84-123 -> pointpillar_scatter.py:17-41).
  *
- * hgsf_points_to_bev_train: three launches -- the pillarization front end, a statistics pass (per-channel sums of the Linear
- * output over every kept point -> batch_mean / batch_var [C], running_mean / running_var updated in place with `momentum`,
- * either may be NULL), and the fused pass of hgsf_points_to_bev normalising with those batch statistics.  pfn->bn_mean /
- * bn_var are ignored.  `stats` is device scratch of 2*C doubles.  out->spatial_features and out->pillar_features are
+ * hgsf_points_to_bev_train: three launches -- the pillarization front end, a statistics pass (second moments of the decorated
+ * features over every kept point; from them batch_mean / batch_var [C], running_mean / running_var updated in place with
+ * `momentum`, either may be NULL, and the sums the backward needs), and the fused pass of hgsf_points_to_bev normalising with
+ * those batch statistics.  pfn->bn_mean / bn_var are ignored.  `stats`: hgsf_train_stats_doubles(C, Cin) doubles of device
+ * memory, written here and read by the backward (keep it between the two).  out->spatial_features and out->pillar_features are
  * required; pass out->voxels when a backward follows.  HGSF_ERR_UNSUPPORTED outside the fused kernel's domain (BatchNorm,
  * 64 channels, max_points_per_voxel <= 32, spconv-2 overflow rule, grid[0] % 4 == 0): use the three contract calls above.
  *
  * hgsf_points_to_bev_train_backward: gradients of linear.weight [C,Cin], norm.weight [C], norm.bias [C] from the cotangents
  * of spatial_features (may be NULL) and of pillar_features ([capacity,C], may be NULL).  voxels / voxel_coords /
  * voxel_num_points are the forward's outputs as they are (capacity rows); the pillar count is read on the device from
- * num_pillars[0].  pfn->bn_mean / bn_var = the forward's batch_mean / batch_var.  grad_rows: device scratch
- * [capacity, C]; stats: hgsf_train_stats_doubles doubles; scratch: hgsf_train_scratch_doubles doubles. */
+ * num_pillars[0].  pfn->bn_mean / bn_var = the forward's batch_mean / batch_var; stats = the forward's buffer.  grad_rows:
+ * device scratch [capacity, C]; scratch: hgsf_train_scratch_doubles doubles.  Three launches. */
 HGSF_API int hgsf_points_to_bev_train(const hgsf_geometry *geom, const hgsf_points *points, const hgsf_pfn *pfn,
                                       int32_t max_points_per_voxel, int32_t max_voxels, void *workspace, size_t workspace_bytes,
                                       const hgsf_pillar_outputs *out, float momentum, float *running_mean, float *running_var,
@@ -309,7 +310,7 @@ HGSF_API int hgsf_points_to_bev_train_backward(const hgsf_geometry *geom, const 
                                                int64_t pillar_capacity, const int32_t *num_pillars,
                                                int32_t max_points_per_voxel, int32_t num_features, int32_t batch_size,
                                                const float *grad_spatial_features, const float *grad_pillar_features,
-                                               float *grad_rows, double *stats, double *scratch, float *grad_weight,
+                                               float *grad_rows, const double *stats, double *scratch, float *grad_weight,
                                                float *grad_bn_weight, float *grad_bn_bias, hgsf_stream_t stream);
 
 /* PointPillarScatter backward (autograd of pointpillar_scatter.py:33-35): grad_pillar_features[m, :] =
