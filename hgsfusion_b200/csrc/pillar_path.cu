@@ -1233,6 +1233,10 @@ __global__ void __launch_bounds__(PT, HGSF_PILLARS_MINB) k_pillars(const PathPar
 //   16 / 15 / 14 warps per SM at 128 registers (4x4, 3x5, 2x7 warps; no spills) 0.141 / 0.137 / 0.136
 //   listing threshold 40 / 28 / 20 / 12 points                                  0.132 / 0.133 / 0.133 / 0.134
 //   two tiles per ticket half the table apart instead of adjacent               0.1323 vs 0.1318 (TJ4D 0.255 vs 0.247)
+//   2 / 4 / 8 ticket counters on separate lines, interleaved sequence numbers    0.130 / 0.128 / 0.129 (TJ4D 0.249 vs 0.247):
+//                                                  the same-address atomic is not what the warps wait for
+// The statistics pass of the train mode (no Linear, no stores, no outputs) takes 115 us of the 143 us the full kernel takes
+// under ncu: the walk itself -- ticket, record, entries, staging, ordering, means -- is the cost, not arithmetic or DRAM.
 #ifndef HGSF_EMIT_WARPS
 #define HGSF_EMIT_WARPS 4
 #endif
