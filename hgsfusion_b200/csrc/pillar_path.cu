@@ -1233,10 +1233,15 @@ __global__ void __launch_bounds__(PT, HGSF_PILLARS_MINB) k_pillars(const PathPar
 //   16 / 15 / 14 warps per SM at 128 registers (4x4, 3x5, 2x7 warps; no spills) 0.141 / 0.137 / 0.136
 //   listing threshold 40 / 28 / 20 / 12 points                                  0.132 / 0.133 / 0.133 / 0.134
 //   two tiles per ticket half the table apart instead of adjacent               0.1323 vs 0.1318 (TJ4D 0.255 vs 0.247)
+//   two tickets in flight, record + (unconditional) entries three tiles ahead, in registers (163, no spills)   0.144
+//   last iteration's loads consumed before this iteration's instances are issued (address tied to them)       0.131
 //   2 / 4 / 8 ticket counters on separate lines, interleaved sequence numbers    0.130 / 0.128 / 0.129 (TJ4D 0.249 vs 0.247):
 //                                                  the same-address atomic is not what the warps wait for
 // The statistics pass of the train mode (no Linear, no stores, no outputs) takes 115 us of the 143 us the full kernel takes
 // under ncu: the walk itself -- ticket, record, entries, staging, ordering, means -- is the cost, not arithmetic or DRAM.
+// Per-tile clocks (-DHGSF_TILE_CLOCKS, profiles/r02_tile_clocks_k_emit.txt): every tile, whatever its class, spends ~2 000 cycles
+// waiting for the entries / record fetched one (mostly short) iteration earlier and for its ticket: L2 round trips take 2-4 k
+// cycles under this kernel's own load, and fetching further ahead raised them further.
 #ifndef HGSF_EMIT_WARPS
 #define HGSF_EMIT_WARPS 4
 #endif
@@ -1500,12 +1505,25 @@ k_emit(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtenso
     unsigned dirty = 0;                  // cells of the tile buffer that hold non-zero columns
     bool store_pending = false;          // a TMA store from the tile buffer may still be reading it
 
+#ifdef HGSF_TILE_CLOCKS
+    // measurement build (scripts/tile_clocks.py): cycles per tile by class {empty, 1..10 points, 11.., listed heavy, skipped} x
+    // {front of the iteration, the tile itself, the hand-out at the end}, summed per warp, then into scan_desc's tail
+    unsigned long long tc_cyc[5][3] = {}, tc_cnt[5] = {};
+    const long long tc_begin = clock64();
+#endif
     for (int it = 0; cur.t < n_tiles; ++it) {
+#ifdef HGSF_TILE_CLOCKS
+        const long long tc0 = clock64();
+#endif
         const float *stg = stage + (size_t)(it & 1) * STAGE_W * RWc;
         // ---- pipeline: record of the tile after next, entries and rows of the next tile ----
         const uint4 r_nn = load_rec(nxt2);
         const uint4 e_nxt = load_entry(nxt, r_nxt);
         issue_stage(nxt, r_nxt, stage + (size_t)((it + 1) & 1) * STAGE_W * RWc);
+#ifdef HGSF_TILE_CLOCKS
+        const int tc_class = skipped(cur, r_cur) ? 4 : (cur.listed ? 3 : (r_cur.y == 0 ? 0 : (r_cur.y <= 10 ? 1 : 2)));
+        const long long tc1 = clock64();
+#endif
 
         // tile t = (frame b, BEV row y, 32 cells from x0)
         const uint32_t row_id = fastdiv((uint32_t)cur.t, p.div_tpr);
@@ -1811,9 +1829,27 @@ k_emit(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtenso
             }
             __syncwarp();
         }
+#ifdef HGSF_TILE_CLOCKS
+        const long long tc2 = clock64();
+#endif
         e_cur = e_nxt; r_cur = r_nxt; r_nxt = r_nn;
         cur = nxt; nxt = nxt2; nxt2 = next_tile();
+#ifdef HGSF_TILE_CLOCKS
+        const long long tc3 = clock64();
+        tc_cyc[tc_class][0] += tc1 - tc0; tc_cyc[tc_class][1] += tc2 - tc1; tc_cyc[tc_class][2] += tc3 - tc2; ++tc_cnt[tc_class];
+#endif
     }
+#ifdef HGSF_TILE_CLOCKS
+    if (lane == 0) {
+        unsigned long long *dst = reinterpret_cast<unsigned long long *>(p.scan_desc + 3 * 2048 - 128);     // 64 u64 at the tail
+        for (int c = 0; c < 5; ++c) {
+            for (int q = 0; q < 3; ++q) atomicAdd(dst + c * 4 + q, tc_cyc[c][q]);
+            atomicAdd(dst + c * 4 + 3, tc_cnt[c]);
+        }
+        atomicAdd(dst + 20, (unsigned long long)(clock64() - tc_begin));       // the warp's whole loop
+        atomicAdd(dst + 21, 1ull);
+    }
+#endif
     cp_async_wait<0>();
     if (STATS) {
         // lanes l and l + 16 hold the same row; then the warps of the CTA, then one fp64 atomic per entry
