@@ -287,3 +287,16 @@ def test_more_than_32_points_per_pillar(cuda, P):
     r = path.pillarize(torch.from_numpy(pts).to(cuda), 2).trim()
     assert bits_equal(r["voxels"].cpu().numpy(), ref["voxels"])
     assert np.array_equal(r["voxel_num_points"].cpu().numpy(), n)
+
+
+@pytest.mark.parametrize("heavy_pts,chunk", [("0", "1"), ("1", "2"), ("3", "1"), ("1000000", "2")])
+def test_tile_hand_out_variants_do_not_change_results(cuda, monkeypatch, heavy_pts, chunk):
+    """The consumer's scheduling knobs -- which tiles k_front lists as heavy (handed out first, stepped over by the moving
+    window) and how many tiles a ticket covers -- must not change a bit: thresholds that list every occupied tile, almost all,
+    some, none; one and two tiles per ticket; clustered points with a binding max_voxels."""
+    monkeypatch.setenv("HGSF_HEAVY_PTS", heavy_pts)
+    monkeypatch.setenv("HGSF_TILE_CHUNK", chunk)
+    cfg = synthetic.CONFIGS["vod"]
+    pts, offs = synthetic.make_batch("vod", 3, 4000, "clustered", seed0=21)
+    ref, got = both(pts, offs, cfg["pc_range"], cfg["voxel_size"], 4, 900, 7, cuda)
+    assert ref["num_pillars"] == 2700 and ref["voxel_num_points"].max() == 4       # both limits bind
