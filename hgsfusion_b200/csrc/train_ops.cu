@@ -82,14 +82,6 @@ __device__ __forceinline__ PillarHead pillar_head(const VfeParams &q, long long 
     return h;
 }
 
-template <int F>
-__device__ __forceinline__ PillarHead load_pillar(const VfeParams &q, long long m, float *buf, int lane) {
-    const float *src = q.voxels + (size_t)m * q.P * F;
-    for (int t = lane; t < q.P * F; t += 32) buf[t] = __ldg(src + t);
-    __syncwarp();
-    return pillar_head<F>(q, m, buf);
-}
-
 constexpr int TR_WARPS = 8;
 constexpr int TR_C = 64;
 
@@ -124,7 +116,8 @@ __global__ void __launch_bounds__(TR_WARPS * 32) k_vfe_stats(const VfeParams q, 
     double *s_red = reinterpret_cast<double *>(tr_raw);                          // [TR_WARPS*32]
     float *s_vox = reinterpret_cast<float *>(tr_raw + sizeof(double) * TR_WARPS * 32);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float *buf = s_vox + (size_t)warp * q.P * F;
+    const int PF = q.P * F;
+    float *buf0 = s_vox + (size_t)warp * 2 * PF;                 // two staging buffers (as in k_vfe_backward)
     float w[2][CIN];
 #pragma unroll
     for (int j = 0; j < 2; ++j)
@@ -137,8 +130,21 @@ __global__ void __launch_bounds__(TR_WARPS * 32) k_vfe_stats(const VfeParams q, 
     for (int k = 0; k < CIN; ++k) sf[k] = 0.0;
     const long long nwarps = (long long)gridDim.x * TR_WARPS;
     const long long M = pillar_count(q);
-    for (long long m = (long long)blockIdx.x * TR_WARPS + warp; m < M; m += nwarps) {
-        const PillarHead h = load_pillar<F>(q, m, buf, lane);
+    auto issue = [&](long long m, float *b) {
+        if (m < M) {
+            const float *src = q.voxels + (size_t)m * PF;
+            for (int t = lane; t < PF; t += 32) cp_async4(b + t, src + t);
+        }
+        cp_async_commit();
+    };
+    int cur = 0;
+    issue((long long)blockIdx.x * TR_WARPS + warp, buf0);
+    for (long long m = (long long)blockIdx.x * TR_WARPS + warp; m < M; m += nwarps, cur ^= 1) {
+        const float *buf = buf0 + cur * PF;
+        issue(m + nwarps, buf0 + (cur ^ 1) * PF);            // the next pillar's voxel arrives under this one's rows
+        cp_async_wait<1>();
+        __syncwarp();
+        const PillarHead h = pillar_head<F>(q, m, buf);
         for (int s = 0; s < h.cnt; ++s) {
             float f[CIN];
             D::feat(buf + s * F, h.mx, h.my, h.mz, h.cx, h.cy, h.cz, f);
@@ -157,6 +163,7 @@ __global__ void __launch_bounds__(TR_WARPS * 32) k_vfe_stats(const VfeParams q, 
         }
         __syncwarp();
     }
+    cp_async_wait<0>();
     // layout of stats: Sx [C], Sxx [C], T [C][CIN], s [CIN]
     {
         double v[2];
