@@ -460,9 +460,11 @@ def main_ours(args):
         traffic_src = dict(kind="ncu capture committed under profiles/ (NOT measured in this run)", source=ent.get("source"),
                            commit=ent.get("commit"))
         try:
-            # stale = the kernels changed since the capture (docs / scripts moving HEAD do not count); no .git on the GPU box: no check
+            # stale = the path's kernel sources changed since the capture (docs / scripts / other kernels moving HEAD do not count); no .git on
+            # the GPU box: no check
             if ent.get("commit"):
-                r = subprocess.run(["git", "diff", "--quiet", ent["commit"], "HEAD", "--", "hgsfusion_b200/csrc", "include"],
+                r = subprocess.run(["git", "diff", "--quiet", ent["commit"], "HEAD", "--"] +
+                                   [f"hgsfusion_b200/csrc/{f}" for f in ("pillar_path.cu", "pillar_path.cuh", "common.cuh", "pfn.cuh")],
                                    cwd=ROOT, capture_output=True, text=True)
                 if r.returncode == 1:
                     traffic_src["warning"] = f"kernel sources changed since the capture at {ent['commit']}"
