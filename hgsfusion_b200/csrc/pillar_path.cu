@@ -1239,6 +1239,10 @@ __global__ void __launch_bounds__(PT, HGSF_PILLARS_MINB) k_pillars(const PathPar
 //                                                  the same-address atomic is not what the warps wait for
 // The statistics pass of the train mode (no Linear, no stores, no outputs) takes 115 us of the 143 us the full kernel takes
 // under ncu: the walk itself -- ticket, record, entries, staging, ordering, means -- is the cost, not arithmetic or DRAM.
+// Warm-cache L2 counters (ncu --cache-control none, one pass): 59 % of this kernel's read sectors miss the L2 and come from DRAM
+// (20 MB per launch) although k_front wrote them just before -- the 432 MB write stream pushes them out.  Pinning the workspace
+// with a persisting access-policy window (whole carve-out / 32 MB) halves the misses and makes the kernel 0.248 / 0.164 ms: the
+// write stream needs the L2 capacity more than the reads need the hits.
 // Per-tile clocks (-DHGSF_TILE_CLOCKS, profiles/r02_tile_clocks_k_emit.txt): every tile, whatever its class, spends ~2 000 cycles
 // waiting for the entries / record fetched one (mostly short) iteration earlier and for its ticket: L2 round trips take 2-4 k
 // cycles under this kernel's own load, and fetching further ahead raised them further.
