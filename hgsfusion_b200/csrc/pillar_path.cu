@@ -1492,7 +1492,7 @@ k_emit(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtenso
         uint4 e = make_uint4(0, 0, 0, 0);
         if (((r.w >> lane) & 1u) && !skipped(s, r)) {
             const size_t c = (size_t)s.t * 32 + lane;
-            e.x = __ldg(p.cell_tag + c); e.y = __ldg(p.cell_cnt + c); e.z = __ldg(p.cell_start + c);
+            e.x = __ldg(p.cell_tag + c); e.y = __ldg(p.cell_cnt + c);     // (cell_start is not read: see `start` below)
         }
         return e;
     };
@@ -1540,7 +1540,19 @@ k_emit(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtenso
             const size_t c = (size_t)cur.t * 32 + lane;
             p.cell_tag[c] = 0u; p.cell_cnt[c] = 0u;
         }
-        const int m = (int)(e_cur.x - 1u), cnt = (int)e_cur.y, start = (int)e_cur.z;
+        // the CSR is in cell order and the tile's rows are one span from its record's first row: a cell's start is that row plus the
+        // counts of the cells before it (one warp scan instead of a third table load per tile)
+        const int m = (int)(e_cur.x - 1u), cnt = (int)e_cur.y;
+        int start;
+        {
+            int incl = cnt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int o = __shfl_up_sync(FULL, incl, d);
+                if (lane >= d) incl += o;
+            }
+            start = (int)r_cur.x + incl - cnt;
+        }
         const int local = m - s_R[b];
         const bool occ = (e_cur.x != 0u) && (local < maxv);     // pillars beyond max_voxels were never created
         const unsigned bal_occ = __ballot_sync(FULL, occ);
