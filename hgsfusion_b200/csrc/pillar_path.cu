@@ -1245,6 +1245,8 @@ __global__ void __launch_bounds__(PT, HGSF_PILLARS_MINB) k_pillars(const PathPar
 // write stream needs the L2 capacity more than the reads need the hits.
 // prefetch.global.L2 of the table lines / rows of the tile 2 048 / 4 096 / 8 192 positions down the window: the demand misses stay
 // (562 k sectors), 0.135 / 0.134 / 0.134 ms.
+// Entries out of k_front's pillar list (one coalesced 16-byte-per-pillar load + three shuffles to cell order) instead of the table
+// arrays: no change on VoD (0.1284 vs 0.1286), 1 % slower on TJ4D / stress.
 // Per-tile clocks (-DHGSF_TILE_CLOCKS, profiles/r02_tile_clocks_k_emit.txt): every tile, whatever its class, spends ~2 000 cycles
 // waiting for the entries / record fetched one (mostly short) iteration earlier and for its ticket: L2 round trips take 2-4 k
 // cycles under this kernel's own load, and fetching further ahead raised them further.
